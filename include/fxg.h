@@ -1,0 +1,213 @@
+/* fxg.h -- C-ABI of the B200-native pyfastx hot path (libfxg.so).
+ *
+ * This is the drop-in boundary: plain C types, caller-owned buffers, int status codes,
+ * no Python.h / torch types, callable with the GIL released.  The reference (lmdu/pyfastx
+ * v2.3.1) has no FFI of its own -- its hot path is C functions inside a CPython
+ * extension -- so each entry point cites the reference function(s) it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the binding a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *   - every function returns FXG_OK (0) or a negative FXG_E* code; fxg_last_error()
+ *     gives a thread-local message for the last failure;
+ *   - "dev" pointers are CUDA device pointers on the context's device, "host" pointers
+ *     are ordinary (pageable or pinned) host memory;
+ *   - all work is enqueued on the context's stream (fxg_ctx_set_stream lets the caller
+ *     pass its own cudaStream_t, e.g. torch's current stream); *_host entry points
+ *     synchronise before returning, *_dev entry points do not unless stated;
+ *   - there is NO CPU fallback anywhere: without a CUDA device every compute entry point
+ *     fails with FXG_ENODEV.
+ */
+#ifndef FXG_H
+#define FXG_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FXG_ABI_VERSION 1
+
+enum {
+    FXG_OK       = 0,
+    FXG_ENODEV   = -1,  /* no usable CUDA device                           */
+    FXG_ECUDA    = -2,  /* CUDA runtime error (see fxg_last_error)         */
+    FXG_EINVAL   = -3,  /* bad argument                                    */
+    FXG_ENOMEM   = -4,  /* host or device allocation failed                */
+    FXG_ECAP     = -5,  /* caller buffer too small (required size returned)*/
+    FXG_EIO      = -6,  /* file I/O error                                  */
+    FXG_EFORMAT  = -7   /* malformed compressed stream                     */
+};
+
+/* ---- row layouts (device and host, little endian) ------------------------------------- */
+
+/* One `seq` table row of the .fxi (DDL: src/index.c:178-188).  48 bytes.
+ * chrom name bytes live in the file at [boff - elen - dlen, +nlen). */
+typedef struct fxg_fasta_row {
+    int64_t boff;     /* offset of first sequence byte            index.c:258      */
+    int64_t blen;     /* bytes to next header / end position      index.c:243,348  */
+    int64_t slen;     /* sequence length                          index.c:335-338  */
+    int64_t llen;     /* first line length incl. line ending      index.c:330-332  */
+    int32_t dlen;     /* header length w/o '>' and line ending    index.c:271      */
+    int32_t nlen;     /* chrom name length                        index.c:282-301  */
+    uint8_t elen;     /* 1 = "\n", 2 = "\r\n" (from the header)   index.c:267-269  */
+    uint8_t norm;     /* <= 1 line differing from the first       index.c:237,342  */
+    uint8_t pad[6];
+} fxg_fasta_row;
+
+/* One `read` table row (DDL: src/fastq.c:29-37).  32 bytes.
+ * read name bytes live in the file at [soff - dlen, +nlen). */
+typedef struct fxg_fastq_row {
+    int64_t soff;     /* offset of the sequence line              fastq.c:122      */
+    int64_t qoff;     /* offset of the quality line               fastq.c:133      */
+    int64_t rlen;     /* read length without '\r'                 fastq.c:124-128  */
+    int32_t dlen;     /* name line length incl. '@' and '\r'      fastq.c:103      */
+    int32_t nlen;     /* read name length                         fastq.c:104-117  */
+} fxg_fastq_row;
+
+/* Totals the scans report next to the rows (the `stat` rows, index.c:367-371,
+ * fastq.c:159-171) plus what a multi-GPU shard merge needs. */
+typedef struct fxg_scan_stats {
+    int64_t n_rows;        /* FASTA: header lines seen; FASTQ: n_lines / 4                 */
+    int64_t n_lines;       /* lines incl. an unterminated last line                         */
+    int64_t total_len;     /* FASTA: sum(slen) -> stat.seqlen; FASTQ: sum(rlen) -> stat.size */
+    int64_t end_position;  /* n, or n+1 when the last line has no '\n' (index.c:231)       */
+    int64_t lead_lines;    /* FASTA shard merge: lines before the first header of this buffer */
+    int64_t lead_bytes;    /* bytes before the first header (== buffer size if none)       */
+    int64_t lead_llen;     /* first line length of that lead part, 0 if none               */
+    int64_t reserved;
+} fxg_scan_stats;
+
+/* scan flags */
+enum {
+    FXG_SCAN_FULL_NAME = 1   /* Fasta(full_name=True): name = whole header (index.c:282-285) */
+};
+
+/* per-query extraction flags */
+enum {
+    FXG_X_UPPER      = 1,   /* Fasta(uppercase=True): remove_space_uppercase  util.c:181-194 */
+    FXG_X_REVERSE    = 2,   /* Sequence.reverse                               util.c:251-260 */
+    FXG_X_COMPLEMENT = 4,   /* Sequence.complement (both = antisense)         util.c:239-269 */
+    FXG_X_RAW        = 8    /* no whitespace stripping (FASTQ reads)          read.c:37-45   */
+};
+
+typedef struct fxg_ctx  fxg_ctx;    /* one per (process, GPU)                    */
+typedef struct fxg_file fxg_file;   /* a FASTA/FASTQ byte stream resident in HBM */
+
+/* ---- library / context ----------------------------------------------------------------- */
+int         fxg_abi_version(void);
+const char *fxg_last_error(void);
+int         fxg_device_count(void);
+int         fxg_ctx_create(int device, fxg_ctx **out);
+void        fxg_ctx_destroy(fxg_ctx *ctx);
+int         fxg_ctx_set_stream(fxg_ctx *ctx, void *cuda_stream);
+int         fxg_ctx_sync(fxg_ctx *ctx);
+int         fxg_ctx_sm_count(fxg_ctx *ctx);
+
+/* measurement hooks (bench.py): with profiling on, the dominant kernels are bracketed by
+ * CUDA events on the context's stream; slot 0 = scan kernel, 1 = FASTA finalize,
+ * 2 = extract/reads kernel, 3 = offset prefix-sum kernels.  fxg_profile_last_ms waits for
+ * the slot's end event.  fxg_ctx_launch_count = kernels launched by this context so far. */
+enum { FXG_PROF_SCAN = 0, FXG_PROF_FINALIZE = 1, FXG_PROF_GATHER = 2, FXG_PROF_PLAN = 3, FXG_PROF_SLOTS = 4 };
+int         fxg_profile_enable(fxg_ctx *ctx, int on);
+int         fxg_profile_last_ms(fxg_ctx *ctx, int slot, float *ms);
+int64_t     fxg_ctx_launch_count(fxg_ctx *ctx);
+
+/* pinned host memory for staging (cudaHostAlloc / cudaFreeHost) */
+int         fxg_host_alloc(int64_t nbytes, void **out);
+void        fxg_host_free(void *p);
+
+/* ---- file staging: raw bytes -> HBM ------------------------------------------------------
+ * Replaces the reference's read side: gzread into a 1 MiB kstream buffer (src/kseq.c:70)
+ * for the scan, fseeko+fread per request for random access (src/index.c:683-692,
+ * src/read.c:37-45).  The whole file becomes one padded device buffer. */
+int      fxg_file_alloc(fxg_ctx *ctx, int64_t nbytes, fxg_file **out);
+int      fxg_file_upload(fxg_ctx *ctx, fxg_file *f, int64_t dst_off, const void *host, int64_t nbytes);
+int      fxg_file_from_host(fxg_ctx *ctx, const void *host, int64_t nbytes, fxg_file **out);
+int      fxg_file_from_path(fxg_ctx *ctx, const char *path, fxg_file **out);
+int      fxg_file_wrap(fxg_ctx *ctx, void *dev_ptr, int64_t nbytes, int64_t capacity, fxg_file **out);
+int      fxg_file_download(fxg_ctx *ctx, const fxg_file *f, int64_t src_off, void *host, int64_t nbytes);
+void    *fxg_file_devptr(const fxg_file *f);
+int64_t  fxg_file_size(const fxg_file *f);
+void     fxg_file_free(fxg_file *f);
+
+/* ---- K1: FASTA index scan -----------------------------------------------------------------
+ * Replaces the scan loop of pyfastx_create_index (src/index.c:226-361) over
+ * ks_getuntil2 (src/kseq.c:59-109).  One pass over the resident bytes; rows land in a
+ * device array owned by the context (valid until the next scan on this context or
+ * fxg_ctx_destroy) and can be copied out with fxg_rows_download.
+ *   base_offset : file offset of byte 0 of `f` (added to every boff; 0 for a whole file)
+ *   d_rows_out  : receives the device pointer to n_rows fxg_fasta_row
+ * Synchronises (the row count is needed on the host). */
+int fxg_fasta_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int flags,
+                   fxg_fasta_row **d_rows_out, fxg_scan_stats *stats);
+
+/* ---- K2: FASTQ index scan -----------------------------------------------------------------
+ * Replaces the scan loop of pyfastx_fastq_create_index (src/fastq.c:84-171).
+ *   first_line  : global 0-based line number of the first line of `f` (0 for a whole
+ *                 file; the shard's line-count prefix in a multi-GPU build, section 8e)
+ * Rows are indexed by global read id minus first_line/4; a read whose four lines straddle
+ * two shards gets its fields from both (fields not owned are left zero). */
+int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int64_t first_line,
+                   fxg_fastq_row **d_rows_out, fxg_scan_stats *stats);
+
+/* newline count of a resident buffer (FASTQ multi-GPU phase pass, section 8e) */
+int fxg_count_lines(fxg_ctx *ctx, const fxg_file *f, int64_t *n_newlines, int *ends_with_newline);
+
+/* copy rows device -> host (row_bytes = 48 or 32) */
+int fxg_rows_download(fxg_ctx *ctx, const void *d_rows, int64_t n_rows, int row_bytes, void *host_rows);
+int fxg_rows_upload(fxg_ctx *ctx, const void *host_rows, int64_t n_rows, int row_bytes, void **d_rows_out);
+void fxg_dev_free(void *d_ptr);
+
+/* One-call, host-buffer form (end-to-end path: H2D staging + scan + D2H rows).
+ * rows_cap < n_rows -> FXG_ECAP with stats->n_rows set. */
+int fxg_fasta_build_index_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, int flags,
+                               fxg_fasta_row *rows, int64_t rows_cap, fxg_scan_stats *stats);
+int fxg_fastq_build_index_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes,
+                               fxg_fastq_row *rows, int64_t rows_cap, fxg_scan_stats *stats);
+
+/* ---- K3/K4: batched subsequence extraction (+ fused A/C/G/T counts) ----------------------
+ * Replaces, per query: the slice -> byte-range math of pyfastx_sequence_subscript
+ * (src/sequence.c:498-510), pyfastx_index_random_read + pyfastx_index_fill_cache
+ * (src/index.c:683-707), remove_space[_uppercase] (src/util.c:166-194), the strand
+ * transforms (src/util.c:239-269 via src/sequence.c:337-398) and, when d_acgt != NULL,
+ * the base counting loop of gc_content/gc_skew (src/sequence.c:607-631).
+ * Query q = (row_id[q], s[q], e[q], flags[q]) with 0-based half-open [s, e) already
+ * clamped to [0, slen] (PySlice_AdjustIndices, sequence.c:446).  Output q is written at
+ * d_out + d_out_off[q], length e-s; d_out_off has nq+1 entries (exclusive prefix sum,
+ * computed by fxg_extract_plan_dev).  norm=0 records are served by stripping the whole
+ * record and indexing into it (sequence.c:100-102). */
+int fxg_extract_plan_dev(fxg_ctx *ctx, const int64_t *d_s, const int64_t *d_e, int64_t nq,
+                         int64_t *d_out_off, int64_t *total_bytes /* host, may be NULL */);
+int fxg_extract_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                    const int64_t *d_row_id, const int64_t *d_s, const int64_t *d_e,
+                    const int32_t *d_flags, int64_t nq,
+                    const int64_t *d_out_off, uint8_t *d_out, int64_t *d_acgt /* nq*4 or NULL */);
+/* host-buffer form: H2D queries, plan, extract, D2H output.  out_off_host has nq+1 entries. */
+int fxg_extract_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                     const int64_t *row_id, const int64_t *s, const int64_t *e, const int32_t *flags,
+                     int64_t nq, int64_t *out_off_host, uint8_t *out_host, int64_t out_cap,
+                     int64_t *acgt_host /* nq*4 or NULL */);
+
+/* ---- K5: batched FASTQ read fetch ----------------------------------------------------------
+ * Replaces pyfastx_read_random_reader + the seq/qual getters (src/read.c:37-45,152-167,
+ * 237-249): for read ids[q] copies rlen raw bytes at soff (seq) and at qoff (qual).
+ * Both outputs share out_off (prefix sum of rlen, nq+1 entries, filled by the call). */
+int fxg_reads_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows,
+                  const int64_t *d_ids, int64_t nq, int32_t flags,
+                  int64_t *d_out_off, uint8_t *d_seq_out, uint8_t *d_qual_out, int64_t out_cap,
+                  int64_t *total_bytes);
+int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows,
+                   const int64_t *ids, int64_t nq, int32_t flags,
+                   int64_t *out_off_host, uint8_t *seq_host, uint8_t *qual_host, int64_t out_cap);
+
+/* ---- synthetic inputs generated directly in HBM (bench / test tooling) -------------------
+ * Byte-identical to pyfastx_b200/synth.py.  rec_off has n_records+1 entries (device). */
+int fxg_synth_fasta_dev(fxg_ctx *ctx, uint64_t seed, const int64_t *d_lengths, const int64_t *d_rec_off,
+                        int64_t n_records, int64_t first_record, int width, uint8_t *d_out);
+int fxg_synth_fastq_dev(fxg_ctx *ctx, uint64_t seed, int64_t n_reads, int64_t first_read, int read_len,
+                        const int64_t *d_rec_off, uint8_t *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FXG_H */

@@ -1,0 +1,130 @@
+"""ctypes binding of libfxg.so -- the C-ABI declared in include/fxg.h.
+
+This is the only place the package touches native code.  There is no CPU fallback: if the
+library is missing or no CUDA device is usable, the compute entry points raise.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfxg.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fxg.h")
+
+FASTA_ROW = np.dtype([("boff", "<i8"), ("blen", "<i8"), ("slen", "<i8"), ("llen", "<i8"),
+                      ("dlen", "<i4"), ("nlen", "<i4"), ("elen", "u1"), ("norm", "u1"),
+                      ("pad", "u1", (6,))])
+FASTQ_ROW = np.dtype([("soff", "<i8"), ("qoff", "<i8"), ("rlen", "<i8"),
+                      ("dlen", "<i4"), ("nlen", "<i4")])
+
+FXG_OK, FXG_ENODEV, FXG_ECUDA, FXG_EINVAL, FXG_ENOMEM, FXG_ECAP, FXG_EIO, FXG_EFORMAT = 0, -1, -2, -3, -4, -5, -6, -7
+SCAN_FULL_NAME = 1
+X_UPPER, X_REVERSE, X_COMPLEMENT, X_RAW = 1, 2, 4, 8
+
+
+class ScanStats(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_lines", C.c_int64), ("total_len", C.c_int64),
+                ("end_position", C.c_int64), ("lead_lines", C.c_int64), ("lead_bytes", C.c_int64),
+                ("lead_llen", C.c_int64), ("reserved", C.c_int64)]
+
+
+class FxgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libfxg error %d: %s" % (code, msg))
+        self.code = code
+
+
+class NoDeviceError(FxgError):
+    pass
+
+
+vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint64
+P = C.POINTER
+
+# name -> (restype, argtypes); every symbol declared in include/fxg.h
+SIGNATURES = {
+    "fxg_abi_version": (i32, []),
+    "fxg_last_error": (C.c_char_p, []),
+    "fxg_device_count": (i32, []),
+    "fxg_ctx_create": (i32, [i32, P(vp)]),
+    "fxg_ctx_destroy": (None, [vp]),
+    "fxg_ctx_set_stream": (i32, [vp, vp]),
+    "fxg_ctx_sync": (i32, [vp]),
+    "fxg_ctx_sm_count": (i32, [vp]),
+    "fxg_profile_enable": (i32, [vp, i32]),
+    "fxg_profile_last_ms": (i32, [vp, i32, P(C.c_float)]),
+    "fxg_ctx_launch_count": (i64, [vp]),
+    "fxg_host_alloc": (i32, [i64, P(vp)]),
+    "fxg_host_free": (None, [vp]),
+    "fxg_file_alloc": (i32, [vp, i64, P(vp)]),
+    "fxg_file_upload": (i32, [vp, vp, i64, vp, i64]),
+    "fxg_file_from_host": (i32, [vp, vp, i64, P(vp)]),
+    "fxg_file_from_path": (i32, [vp, C.c_char_p, P(vp)]),
+    "fxg_file_wrap": (i32, [vp, vp, i64, i64, P(vp)]),
+    "fxg_file_download": (i32, [vp, vp, i64, vp, i64]),
+    "fxg_file_devptr": (vp, [vp]),
+    "fxg_file_size": (i64, [vp]),
+    "fxg_file_free": (None, [vp]),
+    "fxg_fasta_scan": (i32, [vp, vp, i64, i32, P(vp), P(ScanStats)]),
+    "fxg_fastq_scan": (i32, [vp, vp, i64, i64, P(vp), P(ScanStats)]),
+    "fxg_count_lines": (i32, [vp, vp, P(i64), P(i32)]),
+    "fxg_rows_download": (i32, [vp, vp, i64, i32, vp]),
+    "fxg_rows_upload": (i32, [vp, vp, i64, i32, P(vp)]),
+    "fxg_dev_free": (None, [vp]),
+    "fxg_fasta_build_index_host": (i32, [vp, vp, i64, i32, vp, i64, P(ScanStats)]),
+    "fxg_fastq_build_index_host": (i32, [vp, vp, i64, vp, i64, P(ScanStats)]),
+    "fxg_extract_plan_dev": (i32, [vp, vp, vp, i64, vp, P(i64)]),
+    "fxg_extract_dev": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp]),
+    "fxg_extract_host": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, i64, vp]),
+    "fxg_reads_dev": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64, P(i64)]),
+    "fxg_reads_host": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64]),
+    "fxg_synth_fasta_dev": (i32, [vp, u64, vp, vp, i64, i64, i32, vp]),
+    "fxg_synth_fastq_dev": (i32, [vp, u64, i64, i64, i32, vp, vp]),
+}
+
+_lib = None
+
+
+def declared_symbols():
+    """Function names declared in include/fxg.h (parsed, so the header stays the source of truth)."""
+    with open(HEADER_PATH) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(fxg_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """Load libfxg.so; raise loudly if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FxgError(FXG_ENODEV, "libfxg.so not built (run pyfastx_b200/csrc/build.sh or "
+                                       "__graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != FXG_OK:
+        msg = lib().fxg_last_error().decode("utf-8", "replace")
+        raise (NoDeviceError if rc == FXG_ENODEV else FxgError)(rc, msg)
+    return rc
+
+
+def ptr(a):
+    """device/host pointer of a numpy array, a torch tensor, an int or None"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError("cannot take a pointer of %r" % type(a))

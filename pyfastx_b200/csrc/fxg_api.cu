@@ -1,0 +1,381 @@
+// fxg_api.cu -- context, error reporting, HBM file buffers and pinned-chunk staging.
+#include "fxg_common.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
+#include <thread>
+#include <vector>
+#include <atomic>
+
+static thread_local char g_err[512] = "";
+
+void fxg_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int FxgScratch::reserve(size_t bytes) {
+    if (bytes <= cap) return FXG_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&ptr, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ptr = nullptr;
+        fxg_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return FXG_ENOMEM;
+    }
+    cap = want;
+    return FXG_OK;
+}
+void FxgScratch::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+}
+
+extern "C" int fxg_abi_version(void) { return FXG_ABI_VERSION; }
+extern "C" const char *fxg_last_error(void) { return g_err; }
+
+extern "C" int fxg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static const size_t PINNED_CHUNK = (size_t)64 << 20;
+
+extern "C" int fxg_ctx_create(int device, fxg_ctx **out) {
+    FXG_CHECK_ARG(out, "out == NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fxg_set_error("no CUDA device available (%s); libfxg has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return FXG_ENODEV;
+    }
+    FXG_CHECK_ARG(device >= 0 && device < n, "device index out of range");
+    FXG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FXG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        fxg_set_error("device %d is sm_%d%d; libfxg is built for sm_100a only", device, prop.major, prop.minor);
+        return FXG_ENODEV;
+    }
+    fxg_ctx *c = new fxg_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    FXG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    *out = c;
+    return FXG_OK;
+}
+
+extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
+        if (c->pinned_ev[i]) cudaEventDestroy(c->pinned_ev[i]);
+    }
+    for (int i = 0; i < FXG_PROF_SLOTS; ++i)
+        for (int j = 0; j < 2; ++j) if (c->prof_ev[i][j]) cudaEventDestroy(c->prof_ev[i][j]);
+    c->tile_desc.release(); c->row_tmp.release(); c->rows.release();
+    c->counters.release(); c->plan.release(); c->misc.release();
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int fxg_ctx_set_stream(fxg_ctx *c, void *cuda_stream) {
+    FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_CUDA(cudaSetDevice(c->device));
+    FXG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return FXG_OK;
+}
+
+extern "C" int fxg_ctx_sync(fxg_ctx *c) {
+    FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_CUDA(cudaSetDevice(c->device));
+    FXG_CUDA(cudaStreamSynchronize(c->stream));
+    return FXG_OK;
+}
+
+extern "C" int fxg_ctx_sm_count(fxg_ctx *c) { return c ? c->sm_count : 0; }
+
+extern "C" int fxg_profile_enable(fxg_ctx *c, int on) {
+    FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_CUDA(cudaSetDevice(c->device));
+    if (on && !c->prof_ev[0][0])
+        for (int i = 0; i < FXG_PROF_SLOTS; ++i)
+            for (int j = 0; j < 2; ++j) FXG_CUDA(cudaEventCreate(&c->prof_ev[i][j]));
+    c->profiling = on != 0;
+    for (int i = 0; i < FXG_PROF_SLOTS; ++i) c->prof_valid[i] = false;
+    return FXG_OK;
+}
+extern "C" int fxg_profile_last_ms(fxg_ctx *c, int slot, float *ms) {
+    FXG_CHECK_ARG(c && ms && slot >= 0 && slot < FXG_PROF_SLOTS, "bad arguments");
+    FXG_CHECK_ARG(c->prof_valid[slot], "no measurement recorded for this slot");
+    FXG_CUDA(cudaEventSynchronize(c->prof_ev[slot][1]));
+    FXG_CUDA(cudaEventElapsedTime(ms, c->prof_ev[slot][0], c->prof_ev[slot][1]));
+    return FXG_OK;
+}
+extern "C" int64_t fxg_ctx_launch_count(fxg_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int fxg_host_alloc(int64_t nbytes, void **out) {
+    FXG_CHECK_ARG(out && nbytes >= 0, "bad arguments");
+    *out = nullptr;
+    FXG_CUDA(cudaHostAlloc(out, (size_t)(nbytes > 0 ? nbytes : 1), cudaHostAllocPortable));
+    return FXG_OK;
+}
+extern "C" void fxg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---- device file buffers ------------------------------------------------------------------
+extern "C" int fxg_file_alloc(fxg_ctx *c, int64_t nbytes, fxg_file **out) {
+    FXG_CHECK_ARG(c && out && nbytes >= 0, "bad arguments");
+    *out = nullptr;
+    FXG_CUDA(cudaSetDevice(c->device));
+    fxg_file *f = new fxg_file();
+    f->size = nbytes;
+    f->capacity = fxg_round_up(nbytes + 1, FXG_FILE_PAD) + FXG_FILE_PAD;
+    f->owned = true;
+    f->device = c->device;
+    cudaError_t e = cudaMalloc((void **)&f->d, (size_t)f->capacity);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete f;
+        fxg_set_error("cudaMalloc(%lld) for file buffer failed: %s", (long long)nbytes, cudaGetErrorString(e));
+        return FXG_ENOMEM;
+    }
+    // zero the padding (never contains '\n'); data region is overwritten by uploads
+    const int64_t pad_from = nbytes & ~(int64_t)15;
+    FXG_CUDA(cudaMemsetAsync(f->d + pad_from, 0, (size_t)(f->capacity - pad_from), c->stream));
+    *out = f;
+    return FXG_OK;
+}
+
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_pinned(fxg_ctx *c) {
+    if (c->pinned[0]) return FXG_OK;
+    for (int i = 0; i < 2; ++i) {
+        FXG_CUDA(cudaHostAlloc(&c->pinned[i], PINNED_CHUNK, cudaHostAllocDefault));
+        FXG_CUDA(cudaEventCreateWithFlags(&c->pinned_ev[i], cudaEventDisableTiming));
+    }
+    c->pinned_bytes = PINNED_CHUNK;
+    return FXG_OK;
+}
+
+// parallel memcpy into a pinned staging buffer (a single core cannot feed PCIe Gen5)
+static void parallel_memcpy(void *dst, const void *src, size_t n) {
+    const size_t kMin = (size_t)4 << 20;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 8) nt = 8;
+    if (nt < 1) nt = 1;
+    if (n < 2 * kMin || nt == 1) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned i = 0; i < nt; ++i) {
+        const size_t o = (size_t)i * per;
+        if (o >= n) break;
+        const size_t len = (o + per <= n) ? per : n - o;
+        th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, len); });
+    }
+    for (auto &t : th) t.join();
+}
+
+extern "C" int fxg_file_upload(fxg_ctx *c, fxg_file *f, int64_t dst_off, const void *host, int64_t nbytes) {
+    FXG_CHECK_ARG(c && f && (host || nbytes == 0), "bad arguments");
+    FXG_CHECK_ARG(dst_off >= 0 && nbytes >= 0 && dst_off + nbytes <= f->size, "upload range outside file");
+    FXG_CUDA(cudaSetDevice(c->device));
+    if (nbytes == 0) return FXG_OK;
+    if (host_ptr_is_pinned(host)) {
+        // pinned source: DMA straight from the caller's buffer, in chunks so the copy engine pipelines
+        const int64_t chunk = (int64_t)256 << 20;
+        for (int64_t o = 0; o < nbytes; o += chunk) {
+            const int64_t len = (nbytes - o < chunk) ? nbytes - o : chunk;
+            FXG_CUDA(cudaMemcpyAsync(f->d + dst_off + o, (const char *)host + o, (size_t)len,
+                                     cudaMemcpyHostToDevice, c->stream));
+        }
+        return FXG_OK;
+    }
+    int rc = ensure_pinned(c);
+    if (rc) return rc;
+    int which = 0;
+    for (int64_t o = 0; o < nbytes; o += (int64_t)c->pinned_bytes, which ^= 1) {
+        const int64_t len = (nbytes - o < (int64_t)c->pinned_bytes) ? nbytes - o : (int64_t)c->pinned_bytes;
+        FXG_CUDA(cudaEventSynchronize(c->pinned_ev[which]));   // previous DMA out of this buffer done
+        parallel_memcpy(c->pinned[which], (const char *)host + o, (size_t)len);
+        FXG_CUDA(cudaMemcpyAsync(f->d + dst_off + o, c->pinned[which], (size_t)len, cudaMemcpyHostToDevice, c->stream));
+        FXG_CUDA(cudaEventRecord(c->pinned_ev[which], c->stream));
+    }
+    return FXG_OK;
+}
+
+extern "C" int fxg_file_from_host(fxg_ctx *c, const void *host, int64_t nbytes, fxg_file **out) {
+    int rc = fxg_file_alloc(c, nbytes, out);
+    if (rc) return rc;
+    rc = fxg_file_upload(c, *out, 0, host, nbytes);
+    if (rc) { fxg_file_free(*out); *out = nullptr; }
+    return rc;
+}
+
+extern "C" int fxg_file_from_path(fxg_ctx *c, const char *path, fxg_file **out) {
+    FXG_CHECK_ARG(c && path && out, "bad arguments");
+    *out = nullptr;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { fxg_set_error("cannot open %s", path); return FXG_EIO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); fxg_set_error("cannot stat %s", path); return FXG_EIO; }
+    const int64_t n = (int64_t)st.st_size;
+    int rc = fxg_file_alloc(c, n, out);
+    if (rc) { close(fd); return rc; }
+    rc = ensure_pinned(c);
+    if (rc) { close(fd); fxg_file_free(*out); *out = nullptr; return rc; }
+    int which = 0;
+    for (int64_t o = 0; o < n; which ^= 1) {
+        const int64_t len = (n - o < (int64_t)c->pinned_bytes) ? n - o : (int64_t)c->pinned_bytes;
+        cudaEventSynchronize(c->pinned_ev[which]);
+        // parallel pread into the pinned chunk
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt > 8) nt = 8;
+        if (nt < 1 || len < ((int64_t)8 << 20)) nt = 1;
+        std::atomic<int> bad(0);
+        std::vector<std::thread> th;
+        const int64_t per = (len + nt - 1) / nt;
+        for (unsigned i = 0; i < nt; ++i) {
+            const int64_t lo = (int64_t)i * per;
+            if (lo >= len) break;
+            const int64_t cnt = (lo + per <= len) ? per : len - lo;
+            char *dst = (char *)c->pinned[which] + lo;
+            const int64_t fo = o + lo;
+            th.emplace_back([=, &bad] {
+                int64_t done = 0;
+                while (done < cnt) {
+                    ssize_t r = pread(fd, dst + done, (size_t)(cnt - done), (off_t)(fo + done));
+                    if (r <= 0) { bad = 1; return; }
+                    done += r;
+                }
+            });
+        }
+        for (auto &t : th) t.join();
+        if (bad) { close(fd); fxg_file_free(*out); *out = nullptr; fxg_set_error("read error on %s", path); return FXG_EIO; }
+        cudaError_t e = cudaMemcpyAsync((*out)->d + o, c->pinned[which], (size_t)len, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { close(fd); fxg_file_free(*out); *out = nullptr; fxg_set_error("H2D failed: %s", cudaGetErrorString(e)); return FXG_ECUDA; }
+        cudaEventRecord(c->pinned_ev[which], c->stream);
+        o += len;
+    }
+    close(fd);
+    FXG_CUDA(cudaStreamSynchronize(c->stream));
+    return FXG_OK;
+}
+
+extern "C" int fxg_file_wrap(fxg_ctx *c, void *dev_ptr, int64_t nbytes, int64_t capacity, fxg_file **out) {
+    FXG_CHECK_ARG(c && out && dev_ptr && nbytes >= 0 && capacity >= nbytes, "bad arguments");
+    FXG_CHECK_ARG(((uintptr_t)dev_ptr & 15) == 0, "device pointer must be 16-byte aligned");
+    FXG_CHECK_ARG(capacity >= fxg_round_up(nbytes, 16), "capacity must cover nbytes rounded up to 16");
+    fxg_file *f = new fxg_file();
+    f->d = (uint8_t *)dev_ptr; f->size = nbytes; f->capacity = capacity; f->owned = false; f->device = c->device;
+    *out = f;
+    return FXG_OK;
+}
+
+extern "C" int fxg_file_download(fxg_ctx *c, const fxg_file *f, int64_t src_off, void *host, int64_t nbytes) {
+    FXG_CHECK_ARG(c && f && host && src_off >= 0 && nbytes >= 0 && src_off + nbytes <= f->size, "bad arguments");
+    FXG_CUDA(cudaSetDevice(c->device));
+    FXG_CUDA(cudaMemcpyAsync(host, f->d + src_off, (size_t)nbytes, cudaMemcpyDeviceToHost, c->stream));
+    FXG_CUDA(cudaStreamSynchronize(c->stream));
+    return FXG_OK;
+}
+
+extern "C" void *fxg_file_devptr(const fxg_file *f) { return f ? f->d : nullptr; }
+extern "C" int64_t fxg_file_size(const fxg_file *f) { return f ? f->size : 0; }
+extern "C" void fxg_file_free(fxg_file *f) {
+    if (!f) return;
+    if (f->owned && f->d) { cudaSetDevice(f->device); cudaFree(f->d); }
+    delete f;
+}
+
+// ---- rows up/down ------------------------------------------------------------------------------
+extern "C" int fxg_rows_download(fxg_ctx *c, const void *d_rows, int64_t n_rows, int row_bytes, void *host_rows) {
+    FXG_CHECK_ARG(c && (n_rows == 0 || (d_rows && host_rows)) && n_rows >= 0 && row_bytes > 0, "bad arguments");
+    FXG_CUDA(cudaSetDevice(c->device));
+    if (n_rows) {
+        FXG_CUDA(cudaMemcpyAsync(host_rows, d_rows, (size_t)n_rows * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+        FXG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return FXG_OK;
+}
+
+extern "C" int fxg_rows_upload(fxg_ctx *c, const void *host_rows, int64_t n_rows, int row_bytes, void **d_rows_out) {
+    FXG_CHECK_ARG(c && d_rows_out && n_rows >= 0 && row_bytes > 0 && (n_rows == 0 || host_rows), "bad arguments");
+    FXG_CUDA(cudaSetDevice(c->device));
+    *d_rows_out = nullptr;
+    void *d = nullptr;
+    FXG_CUDA(cudaMalloc(&d, (size_t)(n_rows > 0 ? n_rows : 1) * row_bytes));
+    if (n_rows) {
+        cudaError_t e = cudaMemcpyAsync(d, host_rows, (size_t)n_rows * row_bytes, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cudaFree(d); fxg_set_error("rows upload failed: %s", cudaGetErrorString(e)); return FXG_ECUDA; }
+    }
+    *d_rows_out = d;
+    return FXG_OK;
+}
+
+extern "C" void fxg_dev_free(void *d) {
+    if (d) cudaFree(d);
+}
+
+// ---- one-call host-buffer index builds (end-to-end path) ------------------------------------------
+extern "C" int fxg_fasta_build_index_host(fxg_ctx *c, const void *host_buf, int64_t nbytes, int flags,
+                                          fxg_fasta_row *rows, int64_t rows_cap, fxg_scan_stats *stats) {
+    FXG_CHECK_ARG(c && stats && (host_buf || nbytes == 0), "bad arguments");
+    fxg_file *f = nullptr;
+    int rc = fxg_file_from_host(c, host_buf, nbytes, &f);
+    if (rc) return rc;
+    fxg_fasta_row *d_rows = nullptr;
+    rc = fxg_fasta_scan(c, f, 0, flags, &d_rows, stats);
+    if (rc == FXG_OK) {
+        if (stats->n_rows > rows_cap) { fxg_set_error("rows_cap %lld < n_rows %lld", (long long)rows_cap, (long long)stats->n_rows); rc = FXG_ECAP; }
+        else rc = fxg_rows_download(c, d_rows, stats->n_rows, (int)sizeof(fxg_fasta_row), rows);
+    }
+    fxg_file_free(f);
+    return rc;
+}
+
+extern "C" int fxg_fastq_build_index_host(fxg_ctx *c, const void *host_buf, int64_t nbytes,
+                                          fxg_fastq_row *rows, int64_t rows_cap, fxg_scan_stats *stats) {
+    FXG_CHECK_ARG(c && stats && (host_buf || nbytes == 0), "bad arguments");
+    fxg_file *f = nullptr;
+    int rc = fxg_file_from_host(c, host_buf, nbytes, &f);
+    if (rc) return rc;
+    fxg_fastq_row *d_rows = nullptr;
+    rc = fxg_fastq_scan(c, f, 0, 0, &d_rows, stats);
+    if (rc == FXG_OK) {
+        if (stats->n_rows > rows_cap) { fxg_set_error("rows_cap %lld < n_rows %lld", (long long)rows_cap, (long long)stats->n_rows); rc = FXG_ECAP; }
+        else rc = fxg_rows_download(c, d_rows, stats->n_rows, (int)sizeof(fxg_fastq_row), rows);
+    }
+    fxg_file_free(f);
+    return rc;
+}

@@ -1,0 +1,502 @@
+// fxg_extract.cu -- K3/K4 batched subsequence extraction and K5 batched read fetch (sm_100a).
+//
+// Replaces, per query, the reference chain
+//   pyfastx_sequence_subscript  (src/sequence.c:498-510)  slice -> (offset, byte_len)
+//   pyfastx_index_random_read   (src/index.c:683-692)     fseeko + fread of the byte range
+//   remove_space[_uppercase]    (src/util.c:166-194)      drop 10/13/32, optional toupper
+//   reverse/complement getters  (src/util.c:239-269)      strand transforms via comp_map
+//   gc_content counting loop    (src/sequence.c:607-631)  A/C/G/T counters (fused, optional)
+// and for FASTQ  pyfastx_read_random_reader (src/read.c:37-45): raw copies of rlen bytes.
+//
+// One warp serves one query.  The covering byte range is streamed in 512-byte rounds
+// (32 lanes x 16 B, 16-byte aligned loads); a warp prefix sum of per-lane kept-byte counts
+// gives every kept byte its rank ("strip" semantics, exact also for records with an odd
+// line); kept bytes are transformed (toupper / complement LUT) and staged in shared memory
+// at their output position (mirrored for reverse strands), then flushed with aligned
+// 16-byte stores; only the ragged first/last words of a round use byte stores.
+#include "fxg_common.cuh"
+
+namespace fxg {
+
+constexpr int XTHREADS = 256;
+constexpr int XWARPS = XTHREADS / 32;
+constexpr int XSTAGE = 512 + 32;   // staging bytes per warp (512 payload + alignment slack)
+
+struct GatherJob {
+    int64_t src;       // first source byte (buffer relative)
+    int64_t src_len;   // bytes to scan
+    int64_t skip;      // kept bytes to skip before emitting (norm=0 records)
+    int64_t out_len;   // bytes to emit
+    uint8_t *dst;      // output position
+    int     flags;
+};
+
+__device__ __forceinline__ uint32_t keep_mask16(const uint4 &v) {
+    // combined-mask layout (see chunk_eq_mask): 1 = byte is one of 10, 13, 32
+    return chunk_eq_mask(v, 0x0a0a0a0au) | chunk_eq_mask(v, 0x0d0d0d0du) | chunk_eq_mask(v, 0x20202020u);
+}
+// combined-mask bit for chunk byte `off` (0..15)
+__device__ __forceinline__ uint32_t bit_of_off(int off) { return 1u << (8 * (off & 3) + 7 - (off >> 2)); }
+
+// counts of bytes equal (case-insensitively) to the letter in c4 (lower case x4), within `valid` (0x80 per byte)
+__device__ __forceinline__ int count_letter(uint32_t w, uint32_t c4, uint32_t valid) {
+    return __popc(byte_eq_mask(w | 0x20202020u, c4) & valid);
+}
+
+template <bool WANT_ACGT>
+__device__ void gather_one(const uint8_t *__restrict__ file, int64_t fsize, const GatherJob &job,
+                           const uint8_t *__restrict__ s_lut, uint8_t *__restrict__ stage,
+                           int lane, int64_t *acgt_out) {
+    const bool raw = (job.flags & FXG_X_RAW) != 0;
+    const bool upper = (job.flags & FXG_X_UPPER) != 0;
+    const bool comp = (job.flags & FXG_X_COMPLEMENT) != 0;
+    const bool rev = (job.flags & FXG_X_REVERSE) != 0;
+    int64_t src_end = job.src + job.src_len;
+    if (src_end > fsize) src_end = fsize;                       // fread past EOF returns short
+    const int64_t want_end = job.skip + job.out_len;            // kept-rank window [skip, want_end)
+    int64_t done = 0;                                           // kept bytes seen so far
+    int cntA = 0, cntC = 0, cntG = 0, cntT = 0;
+
+    for (int64_t cbase = job.src & ~(int64_t)15; cbase < src_end && done < want_end; cbase += 512) {
+        const int64_t my = cbase + lane * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t valid = 0;                                      // combined-mask bits of in-range bytes
+        if (my < src_end && my + 16 > job.src) {
+            v = *reinterpret_cast<const uint4 *>(file + my);
+            int lo = (int)(job.src > my ? job.src - my : 0);
+            int hi = (int)(src_end - my < 16 ? src_end - my : 16);
+            // mask with bytes lo..hi-1
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                // bytes 4w..4w+3 -> combined bits (8b + 7 - w)
+                int l = lo - 4 * w, h = hi - 4 * w;
+                l = l < 0 ? 0 : (l > 4 ? 4 : l);
+                h = h < 0 ? 0 : (h > 4 ? 4 : h);
+                if (h > l) {
+                    uint32_t word_bits = ((h == 4 ? 0xffffffffu : ((1u << (8 * h)) - 1u)) & ~((1u << (8 * l)) - 1u)) & 0x80808080u;
+                    if (l == 0 && h == 4) word_bits = 0x80808080u;
+                    m |= word_bits >> w;
+                }
+            }
+            valid = m;
+        }
+        uint32_t keep = raw ? valid : (valid & ~keep_mask16(v));
+        const int cnt = __popc(keep);
+        // warp exclusive prefix of cnt
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int64_t rank = done + (incl - cnt);                      // rank of this lane's first kept byte
+        // this round emits kept ranks [r0, r1)
+        const int64_t r0 = done > job.skip ? done : job.skip;
+        int64_t r1 = done + total;
+        if (r1 > want_end) r1 = want_end;
+        const int nout = (int)(r1 > r0 ? r1 - r0 : 0);
+        if (nout > 0) {
+            // output byte index of rank r is (r - skip), or out_len-1-(r-skip) when reversed.
+            // the round's outputs form one contiguous range [o0, o0+nout)
+            const int64_t o0 = rev ? (job.out_len - (r1 - job.skip)) : (r0 - job.skip);
+            uint8_t *g0 = job.dst + o0;
+            const int a = (int)((uintptr_t)g0 & 15);
+            if (cnt) {
+                const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int off = 0; off < 16; ++off) {
+                    if (keep & bit_of_off(off)) {
+                        if (rank >= r0 && rank < r1) {
+                            uint32_t b = (words[off >> 2] >> (8 * (off & 3))) & 0xffu;
+                            if (upper && b >= 'a' && b <= 'z') b -= 32;
+                            if (comp) b = s_lut[b];
+                            const int pos = rev ? (int)(r1 - 1 - rank) : (int)(rank - r0);
+                            stage[a + pos] = (uint8_t)b;
+                        }
+                        ++rank;
+                    }
+                }
+            }
+            __syncwarp();
+            // flush: aligned 16-byte words; ragged ends byte-wise
+            const int nwords = (a + nout + 15) >> 4;
+            for (int w = lane; w < nwords; w += 32) {
+                const int lo = (w == 0) ? a : 0;
+                const int hi = ((w + 1) * 16 <= a + nout) ? 16 : (a + nout - w * 16);
+                const uint4 sv = *reinterpret_cast<const uint4 *>(stage + w * 16);
+                uint8_t *gw = g0 - a + w * 16;
+                if (lo == 0 && hi == 16) {
+                    *reinterpret_cast<uint4 *>(gw) = sv;
+                } else {
+                    for (int i = lo; i < hi; ++i) gw[i] = stage[w * 16 + i];
+                }
+                if (WANT_ACGT) {
+                    const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int l = lo - 4 * q, h = hi - 4 * q;
+                        l = l < 0 ? 0 : (l > 4 ? 4 : l);
+                        h = h < 0 ? 0 : (h > 4 ? 4 : h);
+                        if (h > l) {
+                            uint32_t vb = (l == 0 && h == 4) ? 0x80808080u
+                                        : (((h == 4 ? 0xffffffffu : ((1u << (8 * h)) - 1u)) & ~((1u << (8 * l)) - 1u)) & 0x80808080u);
+                            cntA += count_letter(sw[q], 0x61616161u, vb);
+                            cntC += count_letter(sw[q], 0x63636363u, vb);
+                            cntG += count_letter(sw[q], 0x67676767u, vb);
+                            cntT += count_letter(sw[q], 0x74747474u, vb);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        done += total;
+    }
+    // fewer kept bytes than requested (malformed record): the reference returns stale buffer
+    // bytes there; we define them as 0 (documented in DESIGN.md)
+    {
+        const int64_t emitted = (done > job.skip ? (done < want_end ? done : want_end) - job.skip : 0);
+        if (emitted < job.out_len) {
+            const int64_t missing = job.out_len - emitted;
+            uint8_t *z = rev ? job.dst : job.dst + emitted;
+            for (int64_t i = lane; i < missing; i += 32) z[i] = 0;
+        }
+    }
+    if (WANT_ACGT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            cntA += __shfl_down_sync(0xffffffffu, cntA, d);
+            cntC += __shfl_down_sync(0xffffffffu, cntC, d);
+            cntG += __shfl_down_sync(0xffffffffu, cntG, d);
+            cntT += __shfl_down_sync(0xffffffffu, cntT, d);
+        }
+        if (lane == 0 && acgt_out) { acgt_out[0] = cntA; acgt_out[1] = cntC; acgt_out[2] = cntG; acgt_out[3] = cntT; }
+    }
+}
+
+// complement LUT: comp_map (src/util.c:228-237) extended to 256 entries with identity for
+// bytes >= 128 (the reference indexes a 128-entry table out of bounds there).
+__device__ __forceinline__ uint8_t complement_byte(int b) {
+    const int low = (b >= 'a' && b <= 'z') ? 32 : 0;
+    const int up = b - low;
+    int r = up;
+    switch (up) {
+    case 'A': r = 'T'; break; case 'T': r = 'A'; break; case 'U': r = 'A'; break;
+    case 'C': r = 'G'; break; case 'G': r = 'C'; break;
+    case 'M': r = 'K'; break; case 'K': r = 'M'; break;
+    case 'R': r = 'Y'; break; case 'Y': r = 'R'; break;
+    case 'V': r = 'B'; break; case 'B': r = 'V'; break;
+    case 'H': r = 'D'; break; case 'D': r = 'H'; break;
+    default: break;
+    }
+    return (uint8_t)(r + low);
+}
+
+template <bool WANT_ACGT>
+__global__ void __launch_bounds__(XTHREADS) extract_kernel(
+    const uint8_t *__restrict__ file, int64_t fsize, const fxg_fasta_row *__restrict__ rows, int64_t n_rows,
+    const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s, const int64_t *__restrict__ q_e,
+    const int32_t *__restrict__ q_flags, int64_t nq, const int64_t *__restrict__ out_off,
+    uint8_t *__restrict__ out, int64_t *__restrict__ acgt) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
+    for (int i = threadIdx.x; i < 256; i += XTHREADS) s_lut[i] = complement_byte(i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * XWARPS;
+    for (int64_t q = (int64_t)blockIdx.x * XWARPS + warp; q < nq; q += nwarps) {
+        const int64_t rid = q_row[q];
+        int64_t s = q_s[q], e = q_e[q];
+        const int flags = q_flags ? q_flags[q] : 0;
+        GatherJob job;
+        job.flags = flags & ~FXG_X_RAW;
+        job.dst = out + out_off[q];
+        job.skip = 0;
+        job.src = 0; job.src_len = 0;
+        job.out_len = e > s ? e - s : 0;
+        if (rid >= 0 && rid < n_rows && job.out_len > 0) {
+            const fxg_fasta_row r = rows[rid];
+            const int64_t bpl = r.llen - (int64_t)r.elen;
+            const bool whole = (s == 0 && e == r.slen);
+            if (r.norm && bpl > 0 && !whole) {
+                const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
+                job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
+                job.src_len = (e - s) + (be - bs) * (int64_t)r.elen;            // sequence.c:509
+            } else {
+                job.src = r.boff; job.src_len = r.blen; job.skip = s;           // sequence.c:100-102,108-110
+            }
+        }
+        if (job.out_len > 0)
+            gather_one<WANT_ACGT>(file, fsize, job, s_lut, s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
+        else if (WANT_ACGT && lane == 0) { acgt[4 * q] = acgt[4 * q + 1] = acgt[4 * q + 2] = acgt[4 * q + 3] = 0; }
+    }
+}
+
+// K5: which = 0 -> sequence line (soff), 1 -> quality line (qoff)
+__global__ void __launch_bounds__(XTHREADS) reads_kernel(
+    const uint8_t *__restrict__ file, int64_t fsize, const fxg_fastq_row *__restrict__ rows, int64_t n_rows,
+    const int64_t *__restrict__ ids, int64_t nq, int flags, const int64_t *__restrict__ out_off,
+    uint8_t *__restrict__ seq_out, uint8_t *__restrict__ qual_out) {
+    __shared__ uint8_t s_lut[256];
+    __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
+    for (int i = threadIdx.x; i < 256; i += XTHREADS) s_lut[i] = complement_byte(i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * XWARPS;
+    for (int64_t q = (int64_t)blockIdx.x * XWARPS + warp; q < nq; q += nwarps) {
+        const int64_t id = ids[q];
+        if (id < 0 || id >= n_rows) continue;
+        const fxg_fastq_row r = rows[id];
+        GatherJob job;
+        job.skip = 0; job.src_len = r.rlen; job.out_len = r.rlen;
+        if (seq_out) {
+            job.src = r.soff; job.dst = seq_out + out_off[q]; job.flags = flags | FXG_X_RAW;
+            gather_one<false>(file, fsize, job, s_lut, s_stage[warp], lane, nullptr);
+        }
+        if (qual_out) {
+            job.src = r.qoff; job.dst = qual_out + out_off[q];
+            job.flags = (flags & FXG_X_REVERSE) | FXG_X_RAW;      // qualities are never complemented
+            gather_one<false>(file, fsize, job, s_lut, s_stage[warp], lane, nullptr);
+        }
+    }
+}
+
+// ---- exclusive prefix sum of lengths (3 small kernels; < 2 % of the gather traffic) -----------
+constexpr int PS_ITEMS = 2048;   // per block
+__global__ void ps_block_sums(const int64_t *s, const int64_t *e, const fxg_fastq_row *rows, const int64_t *ids,
+                              int64_t n_rows, int64_t nq, int64_t *block_sums) {
+    __shared__ int64_t red[8];
+    const int64_t b0 = (int64_t)blockIdx.x * PS_ITEMS;
+    int64_t acc = 0;
+    for (int i = threadIdx.x; i < PS_ITEMS; i += blockDim.x) {
+        const int64_t q = b0 + i;
+        if (q < nq) {
+            int64_t len;
+            if (rows) { const int64_t id = ids[q]; len = (id >= 0 && id < n_rows) ? rows[id].rlen : 0; }
+            else { len = e[q] - s[q]; }
+            acc += len > 0 ? len : 0;
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += shfl_down_i64(acc, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        block_sums[blockIdx.x] = t;
+    }
+}
+__global__ void ps_scan_sums(int64_t *block_sums, int64_t nblocks, int64_t *total) {
+    // single block, sequential over chunks of blockDim
+    __shared__ int64_t carry;
+    __shared__ int64_t wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < nblocks; b += blockDim.x) {
+        const int64_t i = b + threadIdx.x;
+        const int64_t v = i < nblocks ? block_sums[i] : 0;
+        int64_t incl = v;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t o = shfl_i64(incl, lane >= d ? lane - d : lane);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int64_t wb = 0;
+        for (int w = 0; w < warp; ++w) wb += wsum[w];
+        const int64_t base = carry;
+        if (i < nblocks) block_sums[i] = base + wb + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = base + wb + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void ps_write_offsets(const int64_t *s, const int64_t *e, const fxg_fastq_row *rows, const int64_t *ids,
+                                 int64_t n_rows, int64_t nq, const int64_t *block_sums, int64_t *out_off) {
+    // each thread owns PS_ITEMS / blockDim consecutive items
+    __shared__ int64_t wsum[32];
+    const int per = PS_ITEMS / blockDim.x;
+    const int64_t q0 = (int64_t)blockIdx.x * PS_ITEMS + (int64_t)threadIdx.x * per;
+    int64_t loc[16];
+    int64_t acc = 0;
+    for (int i = 0; i < per; ++i) {
+        const int64_t q = q0 + i;
+        int64_t len = 0;
+        if (q < nq) {
+            if (rows) { const int64_t id = ids[q]; len = (id >= 0 && id < n_rows) ? rows[id].rlen : 0; }
+            else { len = e[q] - s[q]; }
+            if (len < 0) len = 0;
+        }
+        loc[i] = acc;
+        acc += len;
+    }
+    int64_t incl = acc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int64_t o = shfl_i64(incl, lane >= d ? lane - d : lane);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int64_t wb = 0;
+    for (int w = 0; w < warp; ++w) wb += wsum[w];
+    const int64_t base = block_sums[blockIdx.x] + wb + incl - acc;
+    for (int i = 0; i < per; ++i) {
+        const int64_t q = q0 + i;
+        if (q < nq) out_off[q] = base + loc[i];
+    }
+    if (q0 + per >= nq && q0 < nq + per) {
+        // the thread that covers index nq-1 also writes out_off[nq]
+        if (q0 <= nq - 1 && nq - 1 < q0 + per) out_off[nq] = base + acc;
+    }
+}
+
+}  // namespace fxg
+
+using namespace fxg;
+
+static int prefix_lengths(fxg_ctx *ctx, const int64_t *d_s, const int64_t *d_e, const fxg_fastq_row *rows,
+                          const int64_t *ids, int64_t n_rows, int64_t nq, int64_t *d_out_off, int64_t *total_host) {
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    if (nq == 0) {
+        FXG_CUDA(cudaMemsetAsync(d_out_off, 0, sizeof(int64_t), ctx->stream));
+        if (total_host) *total_host = 0;
+        return FXG_OK;
+    }
+    const int64_t nblocks = (nq + PS_ITEMS - 1) / PS_ITEMS;
+    int rc = ctx->plan.reserve((size_t)(nblocks + 2) * sizeof(int64_t));
+    if (rc) return rc;
+    int64_t *bs = (int64_t *)ctx->plan.ptr;
+    {
+    FxgProfScope prof(ctx, FXG_PROF_PLAN, 3);
+    ps_block_sums<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_s, d_e, rows, ids, n_rows, nq, bs);
+    ps_scan_sums<<<1, 1024, 0, ctx->stream>>>(bs, nblocks, bs + nblocks);
+    ps_write_offsets<<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_s, d_e, rows, ids, n_rows, nq, bs, d_out_off);
+    }
+    FXG_CUDA(cudaGetLastError());
+    if (total_host) {
+        FXG_CUDA(cudaMemcpyAsync(total_host, bs + nblocks, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return FXG_OK;
+}
+
+extern "C" int fxg_extract_plan_dev(fxg_ctx *ctx, const int64_t *d_s, const int64_t *d_e, int64_t nq,
+                                    int64_t *d_out_off, int64_t *total_bytes) {
+    FXG_CHECK_ARG(ctx && d_out_off && nq >= 0 && (nq == 0 || (d_s && d_e)), "bad arguments");
+    return prefix_lengths(ctx, d_s, d_e, nullptr, nullptr, 0, nq, d_out_off, total_bytes);
+}
+
+static int gather_grid(fxg_ctx *ctx, int64_t nq) {
+    int64_t blocks = (nq + XWARPS - 1) / XWARPS;
+    const int64_t maxb = (int64_t)ctx->sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" int fxg_extract_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                               const int64_t *d_row_id, const int64_t *d_s, const int64_t *d_e,
+                               const int32_t *d_flags, int64_t nq, const int64_t *d_out_off, uint8_t *d_out,
+                               int64_t *d_acgt) {
+    FXG_CHECK_ARG(ctx && f && nq >= 0, "bad arguments");
+    if (nq == 0) return FXG_OK;
+    FXG_CHECK_ARG(d_rows && d_row_id && d_s && d_e && d_out_off && d_out, "null device pointer");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    const int grid = gather_grid(ctx, nq);
+    FxgProfScope prof(ctx, FXG_PROF_GATHER);
+    if (d_acgt)
+        extract_kernel<true><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_row_id, d_s, d_e,
+                                                                d_flags, nq, d_out_off, d_out, d_acgt);
+    else
+        extract_kernel<false><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_row_id, d_s, d_e,
+                                                                 d_flags, nq, d_out_off, d_out, nullptr);
+    FXG_CUDA(cudaGetLastError());
+    return FXG_OK;
+}
+
+extern "C" int fxg_extract_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                                const int64_t *row_id, const int64_t *s, const int64_t *e, const int32_t *flags,
+                                int64_t nq, int64_t *out_off_host, uint8_t *out_host, int64_t out_cap,
+                                int64_t *acgt_host) {
+    FXG_CHECK_ARG(ctx && f && nq >= 0, "bad arguments");
+    if (nq == 0) { if (out_off_host) out_off_host[0] = 0; return FXG_OK; }
+    FXG_CHECK_ARG(row_id && s && e && out_off_host && out_host, "null host pointer");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)nq * sizeof(int64_t);
+    // device layout in ctx->misc: row_id | s | e | out_off(nq+1) | flags | acgt
+    const size_t need = qb * 3 + (size_t)(nq + 1) * 8 + (size_t)nq * 4 + 16 + (acgt_host ? (size_t)nq * 32 : 0);
+    int rc = ctx->misc.reserve(need + 64);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->misc.ptr;
+    int64_t *d_row = (int64_t *)base, *d_s = d_row + nq, *d_e = d_s + nq, *d_off = d_e + nq;
+    int32_t *d_fl = (int32_t *)(d_off + nq + 1);
+    int64_t *d_acgt = acgt_host ? (int64_t *)(((uintptr_t)(d_fl + nq) + 15) & ~(uintptr_t)15) : nullptr;
+    FXG_CUDA(cudaMemcpyAsync(d_row, row_id, qb, cudaMemcpyHostToDevice, ctx->stream));
+    FXG_CUDA(cudaMemcpyAsync(d_s, s, qb, cudaMemcpyHostToDevice, ctx->stream));
+    FXG_CUDA(cudaMemcpyAsync(d_e, e, qb, cudaMemcpyHostToDevice, ctx->stream));
+    if (flags) FXG_CUDA(cudaMemcpyAsync(d_fl, flags, (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t total = 0;
+    rc = prefix_lengths(ctx, d_s, d_e, nullptr, nullptr, 0, nq, d_off, &total);
+    if (rc) return rc;
+    if (total > out_cap) { fxg_set_error("output needs %lld bytes, capacity %lld", (long long)total, (long long)out_cap); return FXG_ECAP; }
+    if ((rc = ctx->row_tmp.reserve((size_t)total + 64))) return rc;
+    uint8_t *d_out = (uint8_t *)ctx->row_tmp.ptr;
+    rc = fxg_extract_dev(ctx, f, d_rows, n_rows, d_row, d_s, d_e, flags ? d_fl : nullptr, nq, d_off, d_out, d_acgt);
+    if (rc) return rc;
+    FXG_CUDA(cudaMemcpyAsync(out_off_host, d_off, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (total) FXG_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (acgt_host) FXG_CUDA(cudaMemcpyAsync(acgt_host, d_acgt, (size_t)nq * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}
+
+extern "C" int fxg_reads_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows,
+                             const int64_t *d_ids, int64_t nq, int32_t flags, int64_t *d_out_off,
+                             uint8_t *d_seq_out, uint8_t *d_qual_out, int64_t out_cap, int64_t *total_bytes) {
+    FXG_CHECK_ARG(ctx && f && nq >= 0 && d_out_off, "bad arguments");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    int64_t total = 0;
+    int rc = prefix_lengths(ctx, nullptr, nullptr, d_rows, d_ids, n_rows, nq, d_out_off, &total);
+    if (rc) return rc;
+    if (total_bytes) *total_bytes = total;
+    if (total > out_cap) { fxg_set_error("output needs %lld bytes, capacity %lld", (long long)total, (long long)out_cap); return FXG_ECAP; }
+    if (nq == 0 || (!d_seq_out && !d_qual_out)) return FXG_OK;
+    FxgProfScope prof(ctx, FXG_PROF_GATHER);
+    reads_kernel<<<gather_grid(ctx, nq), XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_ids, nq, flags,
+                                                                    d_out_off, d_seq_out, d_qual_out);
+    FXG_CUDA(cudaGetLastError());
+    return FXG_OK;
+}
+
+extern "C" int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows,
+                              const int64_t *ids, int64_t nq, int32_t flags, int64_t *out_off_host,
+                              uint8_t *seq_host, uint8_t *qual_host, int64_t out_cap) {
+    FXG_CHECK_ARG(ctx && f && nq >= 0 && out_off_host, "bad arguments");
+    if (nq == 0) { out_off_host[0] = 0; return FXG_OK; }
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->misc.reserve((size_t)nq * 8 + (size_t)(nq + 1) * 8 + 64);
+    if (rc) return rc;
+    int64_t *d_ids = (int64_t *)ctx->misc.ptr, *d_off = d_ids + nq;
+    FXG_CUDA(cudaMemcpyAsync(d_ids, ids, (size_t)nq * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t total = 0;
+    rc = prefix_lengths(ctx, nullptr, nullptr, d_rows, d_ids, n_rows, nq, d_off, &total);
+    if (rc) return rc;
+    if (total > out_cap) { fxg_set_error("output needs %lld bytes, capacity %lld", (long long)total, (long long)out_cap); return FXG_ECAP; }
+    if ((rc = ctx->row_tmp.reserve((size_t)total * 2 + 128))) return rc;
+    uint8_t *d_seq = (uint8_t *)ctx->row_tmp.ptr;
+    uint8_t *d_qual = d_seq + fxg_round_up(total + 16, 16);
+    ctx->launches += 1;
+    reads_kernel<<<gather_grid(ctx, nq), XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_ids, nq, flags, d_off,
+                                                                    seq_host ? d_seq : nullptr, qual_host ? d_qual : nullptr);
+    FXG_CUDA(cudaGetLastError());
+    FXG_CUDA(cudaMemcpyAsync(out_off_host, d_off, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (seq_host && total) FXG_CUDA(cudaMemcpyAsync(seq_host, d_seq, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (qual_host && total) FXG_CUDA(cudaMemcpyAsync(qual_host, d_qual, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}

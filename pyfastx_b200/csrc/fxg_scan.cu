@@ -1,0 +1,709 @@
+// fxg_scan.cu -- K1 (FASTA) and K2 (FASTQ) index-build scans for sm_100a.
+//
+// Replaces the per-line loops of pyfastx_create_index (reference src/index.c:226-361) and
+// pyfastx_fastq_create_index (src/fastq.c:84-171), both driven by ks_getuntil2
+// (src/kseq.c:59-109), with ONE pass over the file bytes resident in HBM.
+//
+// Design:
+//   * persistent CTAs claim 16 KiB tiles in file order from an atomic counter; each tile
+//     (+ a 256 B left halo) is brought into shared memory by a 1-D TMA bulk copy
+//     (cp.async.bulk -> SASS UBLKCP) through a 3-stage mbarrier ring;
+//   * phase A: every thread tests 4 x 16 B for '\n' with 3 ALU ops per 32-bit word and the
+//     warp turns the per-chunk masks into ordered newline indices with ballots/popc;
+//   * the tile publishes {#newlines, #header starts, last two newline positions} and obtains
+//     the exclusive prefix over all earlier tiles with a decoupled look-back (single pass,
+//     no second read of the file);
+//   * phase C: one thread per LINE.  Every quantity the reference carries from line to line
+//     is re-expressed as a local rule on (this line, previous line, global line index,
+//     global header ordinal):
+//       - a header line writes boff / dlen / elen / name length / its line index;
+//       - a sequence line that follows a header writes llen;
+//       - a sequence line whose length differs from the previous sequence line raises an
+//         "event" (count, min/max line index, sum of length deltas) on its record;
+//     a tiny finalize kernel then derives blen, slen, norm per record from neighbouring
+//     headers and the event summary (proof of equivalence with index.c:325-342 in DESIGN.md);
+//   * FASTQ needs no per-record state at all: line k of the file writes field k%4 of row k/4.
+#include "fxg_common.cuh"
+
+namespace fxg {
+
+constexpr int TILE    = 16384;          // bytes per tile
+constexpr int HALO    = 256;            // left halo kept in smem (previous line starts)
+constexpr int STAGES  = 3;
+constexpr int THREADS = 256;
+constexpr int NWARPS  = THREADS / 32;
+constexpr int REGION  = TILE / NWARPS;  // contiguous bytes per warp (2048)
+constexpr int CHUNKS  = REGION / 512;   // 16-byte chunks per thread (4)
+constexpr int LB      = THREADS;        // lines per phase-C batch
+constexpr int STAGE_BYTES = HALO + TILE;
+constexpr int64_t NOPOS = INT64_MIN / 4;
+
+struct __align__(16) TileDesc {   // decoupled look-back descriptor (64 B)
+    uint64_t nl;       // newlines
+    uint64_t hdr;      // header starts ('>' at a line start)
+    int64_t  p_last;   // last newline position (buffer relative)
+    int64_t  p_prev;   // the one before it
+    int32_t  k;        // how many of (p_last, p_prev) are valid: 0, 1, 2
+    uint32_t status;   // 0 = not yet, 1 = ready
+    uint64_t pad[3];
+};
+
+struct Agg {
+    uint64_t nl, hdr;
+    int64_t  p_last, p_prev;
+    int      k;
+};
+
+__device__ __forceinline__ Agg agg_identity() { return Agg{0, 0, NOPOS, NOPOS, 0}; }
+// a = earlier range, b = later range
+__device__ __forceinline__ Agg agg_combine(const Agg &a, const Agg &b) {
+    Agg r;
+    r.nl = a.nl + b.nl;
+    r.hdr = a.hdr + b.hdr;
+    if (b.k >= 2) { r.p_last = b.p_last; r.p_prev = b.p_prev; r.k = 2; }
+    else if (b.k == 1) { r.p_last = b.p_last; r.p_prev = a.p_last; r.k = min(2, 1 + a.k); }
+    else { r.p_last = a.p_last; r.p_prev = a.p_prev; r.k = a.k; }
+    return r;
+}
+__device__ __forceinline__ Agg agg_shfl_down(const Agg &a, int d) {
+    Agg r;
+    r.nl = (uint64_t)shfl_down_i64((int64_t)a.nl, d);
+    r.hdr = (uint64_t)shfl_down_i64((int64_t)a.hdr, d);
+    r.p_last = shfl_down_i64(a.p_last, d);
+    r.p_prev = shfl_down_i64(a.p_prev, d);
+    r.k = __shfl_down_sync(0xffffffffu, a.k, d);
+    return r;
+}
+__device__ __forceinline__ void desc_publish(TileDesc *d, const Agg &a) {
+    d->nl = a.nl; d->hdr = a.hdr; d->p_last = a.p_last; d->p_prev = a.p_prev; d->k = a.k;
+    __threadfence();
+    st_volatile_u32(&d->status, 1u);
+}
+__device__ __forceinline__ Agg desc_read(const TileDesc *d) {
+    Agg a;
+    a.nl = ld_cg_u64(&d->nl); a.hdr = ld_cg_u64(&d->hdr);
+    a.p_last = ld_cg_i64(&d->p_last); a.p_prev = ld_cg_i64(&d->p_prev);
+    a.k = __ldcg(&d->k);
+    return a;
+}
+
+// Exclusive prefix of tile t over tiles [0, t): warp-wide decoupled look-back.
+__device__ Agg lookback(const TileDesc *agg, const TileDesc *inc, int64_t t, int lane, const Agg &seed) {
+    Agg acc = agg_identity();
+    int64_t j0 = t - 1;
+    while (true) {
+        const int64_t j = j0 - lane;
+        Agg mine = agg_identity();
+        int st = 2;
+        if (j >= 0) {
+            while (true) {
+                if (ld_volatile_u32(&inc[j].status)) { st = 2; break; }
+                if (ld_volatile_u32(&agg[j].status)) { st = 1; break; }
+            }
+            __threadfence();
+            mine = desc_read(st == 2 ? &inc[j] : &agg[j]);
+        } else if (j == -1) {
+            mine = seed;
+        }
+        const uint32_t done = __ballot_sync(0xffffffffu, st == 2);
+        const int first = done ? (__ffs(done) - 1) : 32;
+        if (lane > first) mine = agg_identity();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            Agg o = agg_shfl_down(mine, d);
+            if (lane + d < 32) mine = agg_combine(o, mine);
+        }
+        // lane 0 now holds the ordered combination of this window
+        Agg w;
+        w.nl = (uint64_t)shfl_i64((int64_t)mine.nl, 0);
+        w.hdr = (uint64_t)shfl_i64((int64_t)mine.hdr, 0);
+        w.p_last = shfl_i64(mine.p_last, 0);
+        w.p_prev = shfl_i64(mine.p_prev, 0);
+        w.k = __shfl_sync(0xffffffffu, mine.k, 0);
+        acc = agg_combine(w, acc);
+        if (done) break;
+        j0 -= 32;
+    }
+    return acc;
+}
+
+struct __align__(16) FastaTmp {   // per header slot (slot 0 = lines before the first header)
+    int64_t  boff;       // header thread
+    int64_t  lineidx;    // header thread: buffer-local line index of the header line
+    int64_t  llen;       // first sequence line (len + 1)
+    uint64_t S;          // sum of (L - prevL) over events (wrapping)
+    uint64_t evmax;      // max line index of an event
+    uint64_t evminc;     // max of ~lineidx  (== ~min)
+    uint32_t D;          // number of events
+    int32_t  dlen;
+    int32_t  nlen;
+    uint32_t elen;
+};
+static_assert(sizeof(FastaTmp) == 64, "FastaTmp layout");
+
+struct ScanTotals {     // written by the CTA that owns the last tile (+ finalize)
+    uint64_t nl;
+    uint64_t hdr;
+    int64_t  n_eff;     // n + 1 if the last line has no '\n'
+    uint64_t sum_len;   // FASTA: sum(slen) (finalize); FASTQ: sum(rlen)
+    int64_t  lead_lines, lead_bytes, lead_llen;
+    uint64_t pad;
+};
+
+struct ScanParams {
+    const uint8_t *file;
+    int64_t   n;            // bytes
+    int64_t   capacity;     // readable bytes at file (multiple of 16)
+    int64_t   ntiles;
+    int64_t   base_offset;  // added to every file offset written to rows
+    int64_t   first_line;   // FASTQ: global index of the first line of this buffer
+    int       flags;
+    TileDesc *agg;
+    TileDesc *inc;
+    uint32_t *tile_counter;
+    ScanTotals *totals;
+    FastaTmp *tmp;          // FASTA
+    int64_t   tmp_cap;      // slots
+    fxg_fastq_row *qrows;   // FASTQ
+    int64_t   qrows_cap;
+};
+
+template <int MODE>   // 0 = FASTA, 1 = FASTQ
+__global__ void __launch_bounds__(THREADS, 2) scan_kernel(const ScanParams P) {
+    extern __shared__ __align__(128) uint8_t dyn_smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ int64_t  s_tile[STAGES];
+    __shared__ int64_t  l_pos[LB + 2];
+    __shared__ uint32_t l_flag[LB + 2];
+    __shared__ uint32_t s_wtot[NWARPS];
+    __shared__ int64_t  s_last[2];
+    __shared__ Agg      s_prefix;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t n = P.n;
+    const bool virt = (n > 0) && (P.file[n - 1] != '\n');
+    const int64_t n_eff = n + (virt ? 1 : 0);
+    const bool full_name = (P.flags & FXG_SCAN_FULL_NAME) != 0;
+    unsigned long long my_size = 0;   // FASTQ: sum of rlen seen by this thread
+
+    auto issue = [&](int st) {
+        const int64_t t = (int64_t)atomicAdd(P.tile_counter, 1u);
+        s_tile[st] = t;
+        uint8_t *buf = dyn_smem + (size_t)st * STAGE_BYTES;
+        if (t < P.ntiles) {
+            const int64_t base = t * TILE;
+            int64_t src = base - HALO, dst = 0, want = STAGE_BYTES;
+            if (t == 0) { src = 0; dst = HALO; want = TILE; }
+            int64_t avail = P.capacity - src;
+            if (avail < want) want = avail > 0 ? (avail & ~(int64_t)15) : 0;
+            if (want > 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&full_bar[st], (uint32_t)want);
+                tma_load_1d(buf + dst, P.file + src, (uint32_t)want, &full_bar[st]);
+                return;
+            }
+        }
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES; ++s) issue(s);
+
+    for (int it = 0;; ++it) {
+        const int st = it % STAGES;
+        mbar_wait(&full_bar[st], (uint32_t)((it / STAGES) & 1));
+        const int64_t t = s_tile[st];
+        if (t >= P.ntiles) break;
+        const int64_t base = t * TILE;
+        uint8_t *tb = dyn_smem + (size_t)st * STAGE_BYTES + HALO;   // tb[x] = byte base + x
+        auto byte_at = [&](int64_t x) -> uint8_t {                 // x = buffer-relative position
+            const int64_t r = x - base;
+            if (r >= -(int64_t)HALO && (t > 0 || r >= 0)) return tb[r];
+            return P.file[x];
+        };
+
+        // the tile that contains EOF: neutralise bytes past n, plant the virtual newline
+        if (base + TILE > n) {
+            for (int x = tid; x < TILE; x += THREADS)
+                if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
+            __syncthreads();
+        }
+
+        // ---------------- phase A: newline masks, ordered indices -----------------------------
+        const int roff = warp * REGION + lane * 16;
+        uint32_t c[CHUNKS], pre[CHUNKS];     // pre = exclusive (nl | hdr << 16) before this chunk, warp-local
+        uint32_t run = 0;
+#pragma unroll
+        for (int j = 0; j < CHUNKS; ++j) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(tb + roff + j * 512);
+            c[j] = chunk_eq_mask(v, 0x0a0a0a0au);
+            const uint32_t cnt = __popc(c[j]);
+            uint32_t h = 0;
+            if (MODE == 0 && cnt) {
+                uint32_t m = c[j];
+                while (m) {
+                    const int beta = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int x = roff + j * 512 + chunk_bit_to_off(beta) + 1;   // next line start
+                    if (x < TILE && base + x < n && tb[x] == '>') ++h;
+                }
+            }
+            uint32_t excl, tot;
+            if (!__any_sync(0xffffffffu, cnt > 1)) {
+                const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
+                const uint32_t bh = __ballot_sync(0xffffffffu, h != 0);
+                excl = __popc(bn & lt_mask) | (__popc(bh & lt_mask) << 16);
+                tot = __popc(bn) | (__popc(bh) << 16);
+            } else {
+                const uint32_t packed = cnt | (h << 16);
+                uint32_t incl = packed;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                excl = incl - packed;
+                tot = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            pre[j] = run + excl;
+            run += tot;
+        }
+        if (lane == 0) s_wtot[warp] = run;
+        __syncthreads();   // (1)
+        uint32_t wbase = 0, ttot = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            const uint32_t v = s_wtot[w];
+            if (w < warp) wbase += v;
+            ttot += v;
+        }
+        const int T_nl = (int)(ttot & 0xffffu);
+        const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
+        const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
+        const uint32_t T_h = (ttot >> 16) + tsh;
+
+        // ---------------- entries of batch 0 + the tile's last two newline positions -------------
+        auto write_entries = [&](int b0) {
+#pragma unroll
+            for (int j = 0; j < CHUNKS; ++j) {
+                uint32_t m = c[j];
+                if (!m) continue;
+                int idx = (int)((wbase + pre[j]) & 0xffffu);
+                uint32_t hc = tsh + ((wbase + pre[j]) >> 16);
+                // iterate set bits in increasing byte order: word w = 0..3, then byte b
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t mw = m & (0x80808080u >> w);
+                    while (mw) {
+                        const int beta = __ffs(mw) - 1;
+                        mw &= mw - 1;
+                        const int x = roff + j * 512 + chunk_bit_to_off(beta);
+                        uint32_t nh = 0;
+                        if (MODE == 0) {
+                            const int y = x + 1;
+                            nh = (y < TILE && base + y < n && tb[y] == '>') ? 1u : 0u;
+                            hc += nh;
+                        }
+                        const int rel = idx - b0;
+                        if (rel >= 0 && rel < LB) {
+                            l_pos[2 + rel] = base + x;
+                            l_flag[2 + rel] = (nh << 31) | hc;
+                        }
+                        if (b0 == 0) {
+                            if (idx == T_nl - 1) s_last[0] = base + x;
+                            if (idx == T_nl - 2) s_last[1] = base + x;
+                        }
+                        ++idx;
+                    }
+                }
+            }
+        };
+        write_entries(0);
+        __syncthreads();   // (2)
+
+        // ---------------- publish aggregate, look back, publish inclusive prefix -------------------
+        if (warp == 0) {
+            Agg mine;
+            mine.nl = (uint64_t)T_nl; mine.hdr = T_h;
+            mine.k = T_nl >= 2 ? 2 : T_nl;
+            mine.p_last = T_nl >= 1 ? s_last[0] : NOPOS;
+            mine.p_prev = T_nl >= 2 ? s_last[1] : NOPOS;
+            if (lane == 0) desc_publish(&P.agg[t], mine);
+            Agg seed = agg_identity();
+            seed.k = 1; seed.p_last = -1;          // virtual newline before byte 0
+            const Agg ex = lookback(P.agg, P.inc, t, lane, seed);
+            if (lane == 0) {
+                const Agg in = agg_combine(ex, mine);
+                desc_publish(&P.inc[t], in);
+                s_prefix = ex;
+                // carry entries: the two newlines preceding this tile
+                const int64_t pl = ex.p_last;
+                uint32_t nh1 = 0, hc1 = 0, nh2 = 0;
+                if (MODE == 0) {
+                    if (pl + 1 == base) { nh1 = tsh; hc1 = tsh; }
+                    else nh1 = (byte_at(pl + 1) == '>') ? 1u : 0u;
+                    if (ex.k >= 2) nh2 = (byte_at(ex.p_prev + 1) == '>') ? 1u : 0u;
+                }
+                l_pos[1] = pl;              l_flag[1] = (nh1 << 31) | hc1;
+                l_pos[0] = ex.k >= 2 ? ex.p_prev : NOPOS;   l_flag[0] = (nh2 << 31);
+                if (t == P.ntiles - 1) {
+                    P.totals->nl = in.nl; P.totals->hdr = in.hdr; P.totals->n_eff = n_eff;
+                }
+            }
+        }
+        __syncthreads();   // (3)
+
+        // ---------------- phase C: one thread per line ----------------------------------------------
+        const Agg ex = s_prefix;
+        for (int b0 = 0; b0 < T_nl; b0 += LB) {
+            if (b0 > 0) {
+                __syncthreads();
+                int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
+                if (tid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
+                __syncthreads();
+                if (tid == 0) { l_pos[0] = c0; l_pos[1] = c1; l_flag[0] = g0; l_flag[1] = g1; }
+                write_entries(b0);
+                __syncthreads();
+            }
+            const int idx = b0 + tid;
+            if (idx < T_nl) {
+                const int e = 2 + tid;
+                const int64_t p = l_pos[e], pm1 = l_pos[e - 1], pm2 = l_pos[e - 2];
+                const uint32_t f1 = l_flag[e - 1], f2 = l_flag[e - 2];
+                const int64_t s = pm1 + 1;
+                const int64_t L = p - pm1;                         // len + 1
+                const int64_t lineidx = (int64_t)ex.nl + idx;      // buffer-local line index
+                if (MODE == 0) {
+                    const bool is_hdr = (f1 >> 31) != 0;
+                    const int64_t slot = (int64_t)ex.hdr + (int64_t)(f1 & 0x7fffffffu);   // rec + 1
+                    if (is_hdr) {
+                        const int elen = (byte_at(p - 1) == '\r') ? 2 : 1;
+                        const int64_t dlen = L - 1 - elen;
+                        int64_t nlen = dlen;
+                        if (!full_name) {
+                            nlen = 0;
+                            while (nlen < dlen) {
+                                const uint8_t ch = byte_at(s + 1 + nlen);
+                                if (ch == ' ' || ch == '\t') break;
+                                ++nlen;
+                            }
+                        }
+                        if (slot < P.tmp_cap) {
+                            FastaTmp *r = &P.tmp[slot];
+                            r->boff = P.base_offset + p + 1;
+                            r->lineidx = lineidx;
+                            r->dlen = (int32_t)dlen;
+                            r->nlen = (int32_t)nlen;
+                            r->elen = (uint32_t)elen;
+                        }
+                    } else if (slot < P.tmp_cap) {
+                        FastaTmp *r = &P.tmp[slot];
+                        const bool prev_exists = pm1 >= 0;
+                        const bool prev_is_hdr = (f2 >> 31) != 0;
+                        if (!prev_exists || prev_is_hdr) {
+                            r->llen = L;
+                        } else {
+                            const int64_t prevL = pm1 - pm2;
+                            if (L != prevL) {
+                                atomicAdd(&r->D, 1u);
+                                atomicMax((unsigned long long *)&r->evmax, (unsigned long long)lineidx);
+                                atomicMax((unsigned long long *)&r->evminc, ~(unsigned long long)lineidx);
+                                atomicAdd((unsigned long long *)&r->S, (unsigned long long)(L - prevL));
+                            }
+                        }
+                    }
+                } else {
+                    const int64_t gline = P.first_line + lineidx;
+                    const int ph = (int)(gline & 3);
+                    const int64_t row = (gline >> 2) - (P.first_line >> 2);
+                    const int64_t len = L - 1;
+                    if (row < P.qrows_cap) {
+                        fxg_fastq_row *r = &P.qrows[row];
+                        if (ph == 0) {
+                            int64_t l = len - 1;
+                            if (l > 0 && byte_at(p - 1) == '\r') --l;
+                            if (l < 0) l = 0;
+                            int64_t k = 0;
+                            for (; k < l; ++k) {
+                                const uint8_t ch = byte_at(s + 1 + k);
+                                if (ch == 0) { k = l; break; }
+                                if (ch == ' ') break;
+                            }
+                            r->dlen = (int32_t)len;
+                            r->nlen = (int32_t)k;
+                        } else if (ph == 1) {
+                            const int64_t rlen = (len > 0 && byte_at(p - 1) == '\r') ? len - 1 : len;
+                            r->soff = P.base_offset + s;
+                            r->rlen = rlen;
+                            my_size += (unsigned long long)rlen;
+                        } else if (ph == 3) {
+                            r->qoff = P.base_offset + s;
+                        }
+                    } else if (ph == 1) {
+                        const int64_t rlen = (len > 0 && byte_at(p - 1) == '\r') ? len - 1 : len;
+                        my_size += (unsigned long long)rlen;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // all reads of this stage's smem are done
+        if (tid == 0) issue(st);
+    }
+
+    if (MODE == 1) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_size += (unsigned long long)shfl_down_i64((int64_t)my_size, d);
+        if (lane == 0 && my_size) atomicAdd((unsigned long long *)&P.totals->sum_len, my_size);
+    }
+}
+
+// ---- FASTA finalize: per-record fields from neighbouring headers + event summary ------------
+// blen  = next header start - boff (or end position)                       index.c:243,348
+// slen  = blen - n_lines * elen  (sum over lines of len - elen + 1)        index.c:335-338
+// norm  = [#lines differing from the first <= 1], from the events (DESIGN.md proof)  index.c:325-342
+__global__ void fasta_finalize_kernel(const FastaTmp *tmp, int64_t nrows, int64_t base_offset,
+                                      ScanTotals *tot, fxg_fasta_row *rows) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long slen_acc = 0;
+    if (r < nrows) {
+        const FastaTmp t = tmp[r + 1];
+        int64_t next_h, next_line;
+        if (r + 1 < nrows) {
+            const FastaTmp nx = tmp[r + 2];
+            next_h = nx.boff - (1 + nx.dlen + (int64_t)nx.elen);
+            next_line = nx.lineidx;
+        } else {
+            next_h = base_offset + tot->n_eff;
+            next_line = (int64_t)tot->nl;
+        }
+        const int64_t blen = next_h - t.boff;
+        const int64_t nlines = next_line - t.lineidx - 1;
+        const int64_t slen = blen - nlines * (int64_t)t.elen;
+        int norm;
+        if (t.D == 0) norm = 1;
+        else if (t.D == 1) norm = ((int64_t)t.evmax == t.lineidx + nlines) ? 1 : 0;
+        else if (t.D == 2) norm = ((t.evmax - (~t.evminc) == 1) && t.S == 0) ? 1 : 0;
+        else norm = 0;
+        fxg_fasta_row o;
+        o.boff = t.boff; o.blen = blen; o.slen = slen; o.llen = t.llen;
+        o.dlen = t.dlen; o.nlen = t.nlen; o.elen = (uint8_t)t.elen; o.norm = (uint8_t)norm;
+        for (int i = 0; i < 6; ++i) o.pad[i] = 0;
+        rows[r] = o;
+        slen_acc = (unsigned long long)slen;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) slen_acc += (unsigned long long)shfl_down_i64((int64_t)slen_acc, d);
+    if ((threadIdx.x & 31) == 0 && slen_acc) atomicAdd((unsigned long long *)&tot->sum_len, slen_acc);
+    if (r == 0) {
+        // lead part = lines before the first header of this buffer (multi-GPU shard merge)
+        const FastaTmp l = tmp[0];
+        tot->lead_llen = l.llen;
+        if (nrows > 0) {
+            const FastaTmp f = tmp[1];
+            tot->lead_lines = f.lineidx;
+            tot->lead_bytes = f.boff - base_offset - (1 + f.dlen + (int64_t)f.elen);
+        }
+    }
+}
+
+// ---- density sample: headers / newlines in evenly spaced windows (capacity estimate) -------
+__global__ void sample_density_kernel(const uint8_t *file, int64_t n, int64_t nwin, int64_t win,
+                                      unsigned long long *out /* [0]=newlines, [1]=header starts */) {
+    const int64_t w = blockIdx.x;
+    const int64_t start = (nwin > 1) ? (int64_t)((__int128)(n - win) * w / (nwin - 1)) : 0;
+    unsigned long long nl = 0, h = 0;
+    for (int64_t i = start + threadIdx.x; i < start + win && i < n; i += blockDim.x) {
+        if (file[i] == '\n') { ++nl; if (i + 1 < n && file[i + 1] == '>') ++h; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        nl += (unsigned long long)shfl_down_i64((int64_t)nl, d);
+        h += (unsigned long long)shfl_down_i64((int64_t)h, d);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], nl); atomicAdd(&out[1], h); }
+}
+
+// ---- plain newline count (FASTQ multi-GPU phase pass) ----------------------------------------
+__global__ void count_newlines_kernel(const uint8_t *file, int64_t n, unsigned long long *out) {
+    const int64_t nvec = n / 16;
+    unsigned long long cnt = 0;
+    const uint4 *v = reinterpret_cast<const uint4 *>(file);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
+        cnt += __popc(chunk_eq_mask(v[i], 0x0a0a0a0au));
+    if (blockIdx.x == 0)
+        for (int64_t i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) cnt += (file[i] == '\n');
+    for (int d = 16; d > 0; d >>= 1) cnt += (unsigned long long)shfl_down_i64((int64_t)cnt, d);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
+}  // namespace fxg
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace fxg;
+
+static int scan_launch_config(fxg_ctx *ctx, int mode, int *grid, size_t *smem) {
+    *smem = (size_t)STAGES * STAGE_BYTES;
+    int per_sm = 0;
+    if (mode == 0) {
+        FXG_CUDA(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<0>, THREADS, *smem));
+    } else {
+        FXG_CUDA(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<1>, THREADS, *smem));
+    }
+    if (per_sm < 1) per_sm = 1;
+    *grid = ctx->sm_count * per_sm;
+    return FXG_OK;
+}
+
+// estimate (#newlines, #headers) of the whole buffer from 256 evenly spaced 16 KiB windows
+static int sample_density(fxg_ctx *ctx, const fxg_file *f, double *nl_per_byte, double *hdr_per_byte) {
+    const int64_t n = f->size;
+    const int64_t win = 16384;
+    int64_t nwin = n / win;
+    if (nwin > 256) nwin = 256;
+    if (nwin < 1) nwin = 1;
+    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
+    ctx->launches += 1;
+    sample_density_kernel<<<(unsigned)nwin, 256, 0, ctx->stream>>>(f->d, n, nwin, win < n ? win : n,
+                                                                  (unsigned long long *)ctx->counters.ptr);
+    FXG_CUDA(cudaGetLastError());
+    unsigned long long h[2];
+    FXG_CUDA(cudaMemcpyAsync(h, ctx->counters.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double sampled = (double)nwin * (double)(win < n ? win : n);
+    *nl_per_byte = sampled > 0 ? (double)h[0] / sampled : 0;
+    *hdr_per_byte = sampled > 0 ? (double)h[1] / sampled : 0;
+    return FXG_OK;
+}
+
+static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offset, int64_t first_line, int flags,
+                    void **d_rows_out, fxg_scan_stats *stats) {
+    FXG_CHECK_ARG(ctx && f && stats, "null ctx/file/stats");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    memset(stats, 0, sizeof(*stats));
+    const int64_t n = f->size;
+    if (d_rows_out) *d_rows_out = nullptr;
+    if (n == 0) return FXG_OK;
+    const int64_t ntiles = (n + 1 + TILE - 1) / TILE;   // room for a virtual newline at n
+    int rc;
+    if ((rc = ctx->counters.reserve(256))) return rc;
+    if ((rc = ctx->tile_desc.reserve((size_t)ntiles * 2 * sizeof(TileDesc)))) return rc;
+
+    double nlpb = 0, hpb = 0;
+    if ((rc = sample_density(ctx, f, &nlpb, &hpb))) return rc;
+    int64_t cap;
+    if (mode == 0) cap = (int64_t)(hpb * (double)n * 1.5) + 4096;
+    else cap = (int64_t)(nlpb * (double)n * 1.25 / 4.0) + 4096;
+
+    int grid = 0; size_t smem = 0;
+    if ((rc = scan_launch_config(ctx, mode, &grid, &smem))) return rc;
+    if ((int64_t)grid > ntiles) grid = (int)ntiles;
+
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (mode == 0) {
+            if ((rc = ctx->row_tmp.reserve((size_t)(cap + 2) * sizeof(FastaTmp)))) return rc;
+            FXG_CUDA(cudaMemsetAsync(ctx->row_tmp.ptr, 0, (size_t)(cap + 2) * sizeof(FastaTmp), ctx->stream));
+        } else {
+            if ((rc = ctx->rows.reserve((size_t)(cap + 2) * sizeof(fxg_fastq_row)))) return rc;
+            // rows are fully overwritten except partially-owned boundary rows
+            FXG_CUDA(cudaMemsetAsync(ctx->rows.ptr, 0, sizeof(fxg_fastq_row), ctx->stream));
+        }
+        FXG_CUDA(cudaMemsetAsync(ctx->tile_desc.ptr, 0, (size_t)ntiles * 2 * sizeof(TileDesc), ctx->stream));
+        FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
+
+        ScanParams P;
+        memset(&P, 0, sizeof(P));
+        P.file = f->d; P.n = n; P.capacity = f->capacity & ~(int64_t)15; P.ntiles = ntiles;
+        P.base_offset = base_offset; P.first_line = first_line; P.flags = flags;
+        P.agg = (TileDesc *)ctx->tile_desc.ptr; P.inc = P.agg + ntiles;
+        P.tile_counter = (uint32_t *)ctx->counters.ptr;
+        P.totals = (ScanTotals *)((uint8_t *)ctx->counters.ptr + 64);
+        P.tmp = (FastaTmp *)ctx->row_tmp.ptr; P.tmp_cap = cap + 1;
+        P.qrows = (fxg_fastq_row *)ctx->rows.ptr; P.qrows_cap = cap;
+
+        {
+            FxgProfScope prof(ctx, FXG_PROF_SCAN);
+            if (mode == 0) scan_kernel<0><<<grid, THREADS, smem, ctx->stream>>>(P);
+            else scan_kernel<1><<<grid, THREADS, smem, ctx->stream>>>(P);
+        }
+        FXG_CUDA(cudaGetLastError());
+
+        ScanTotals tot;
+        FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+        FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+
+        const int64_t nrows = mode == 0 ? (int64_t)tot.hdr
+                                        : (int64_t)((first_line + (int64_t)tot.nl + 3) / 4 - first_line / 4);
+        if (nrows > cap) { cap = nrows + 16; continue; }   // estimate too small: exact rerun
+
+        stats->n_lines = (int64_t)tot.nl;
+        stats->end_position = tot.n_eff;
+        if (mode == 0) {
+            stats->n_rows = nrows;
+            if ((rc = ctx->rows.reserve((size_t)(nrows + 1) * sizeof(fxg_fasta_row)))) return rc;
+            const int64_t work = nrows > 0 ? nrows : 1;
+            {
+                FxgProfScope prof(ctx, FXG_PROF_FINALIZE);
+                fasta_finalize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(
+                    P.tmp, nrows, base_offset, P.totals, (fxg_fasta_row *)ctx->rows.ptr);
+            }
+            FXG_CUDA(cudaGetLastError());
+            FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+            FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+            stats->total_len = (int64_t)tot.sum_len;
+            stats->lead_llen = tot.lead_llen;
+            if (nrows > 0) { stats->lead_lines = tot.lead_lines; stats->lead_bytes = tot.lead_bytes; }
+            else { stats->lead_lines = (int64_t)tot.nl; stats->lead_bytes = n; }
+        } else {
+            // complete reads only (fastq.c:132-146,159); rows owned partially by this buffer are
+            // still present in the array for the shard merge
+            stats->n_rows = (first_line + (int64_t)tot.nl) / 4 - first_line / 4;
+            stats->total_len = (int64_t)tot.sum_len;
+        }
+        if (d_rows_out) *d_rows_out = ctx->rows.ptr;
+        return FXG_OK;
+    }
+    fxg_set_error("scan: row capacity estimate failed to converge");
+    return FXG_ECUDA;
+}
+
+extern "C" int fxg_fasta_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int flags,
+                              fxg_fasta_row **d_rows_out, fxg_scan_stats *stats) {
+    return run_scan(ctx, f, 0, base_offset, 0, flags, (void **)d_rows_out, stats);
+}
+
+extern "C" int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int64_t first_line,
+                              fxg_fastq_row **d_rows_out, fxg_scan_stats *stats) {
+    FXG_CHECK_ARG(first_line >= 0, "first_line < 0");
+    return run_scan(ctx, f, 1, base_offset, first_line, 0, (void **)d_rows_out, stats);
+}
+
+extern "C" int fxg_count_lines(fxg_ctx *ctx, const fxg_file *f, int64_t *n_newlines, int *ends_with_newline) {
+    FXG_CHECK_ARG(ctx && f && n_newlines, "null argument");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ctx->counters.reserve(256))) return rc;
+    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
+    unsigned long long h = 0;
+    uint8_t last = '\n';
+    if (f->size > 0) {
+        ctx->launches += 1;
+        count_newlines_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f->d, f->size,
+                                                                         (unsigned long long *)ctx->counters.ptr);
+        FXG_CUDA(cudaGetLastError());
+        FXG_CUDA(cudaMemcpyAsync(&last, f->d + f->size - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FXG_CUDA(cudaMemcpyAsync(&h, ctx->counters.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_newlines = (int64_t)h;
+    if (ends_with_newline) *ends_with_newline = (last == '\n');
+    return FXG_OK;
+}

@@ -1,0 +1,241 @@
+"""numpy-facing wrapper over the C-ABI (one Engine per process and GPU).
+
+Everything here runs on the GPU through libfxg.so; nothing falls back to the CPU.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import FASTA_ROW, FASTQ_ROW, ScanStats, check, lib, ptr
+
+_engines = {}
+_lock = threading.Lock()
+
+
+def default_device():
+    d = os.environ.get("PYFASTX_B200_DEVICE")
+    if d is not None:
+        return int(d)
+    lr = os.environ.get("LOCAL_RANK")
+    return int(lr) if lr is not None else 0
+
+
+def get_engine(device=None):
+    if device is None:
+        device = default_device()
+    with _lock:
+        e = _engines.get(device)
+        if e is None:
+            e = _engines[device] = Engine(device)
+        return e
+
+
+class DeviceFile:
+    """A FASTA/FASTQ byte stream resident in HBM (fxg_file)."""
+
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self.handle = handle
+
+    @property
+    def size(self):
+        return lib().fxg_file_size(self.handle)
+
+    @property
+    def devptr(self):
+        return lib().fxg_file_devptr(self.handle)
+
+    def download(self, offset=0, nbytes=None):
+        n = self.size - offset if nbytes is None else nbytes
+        out = np.empty(max(n, 0), dtype=np.uint8)
+        if n > 0:
+            check(lib().fxg_file_download(self.engine.ctx, self.handle, offset, out.ctypes.data, n))
+        return out
+
+    def free(self):
+        if self.handle:
+            lib().fxg_file_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceRows:
+    """Index rows resident in HBM (own allocation, independent of the scan scratch)."""
+
+    def __init__(self, engine, devptr, n_rows, dtype):
+        self.engine, self.devptr, self.n_rows, self.dtype = engine, devptr, n_rows, dtype
+
+    def free(self):
+        if self.devptr:
+            lib().fxg_dev_free(self.devptr)
+            self.devptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _stats_dict(st):
+    return {k: getattr(st, k) for k, _ in ScanStats._fields_ if k != "reserved"}
+
+
+class Engine:
+    def __init__(self, device=0):
+        L = lib()
+        h = C.c_void_p()
+        check(L.fxg_ctx_create(device, C.byref(h)))
+        self.ctx = h
+        self.device = device
+        self.sm_count = L.fxg_ctx_sm_count(h)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            lib().fxg_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def set_stream(self, cuda_stream):
+        check(lib().fxg_ctx_set_stream(self.ctx, cuda_stream))
+
+    def sync(self):
+        check(lib().fxg_ctx_sync(self.ctx))
+
+    # ---- staging --------------------------------------------------------------------------
+    def stage_bytes(self, data):
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        h = C.c_void_p()
+        check(lib().fxg_file_from_host(self.ctx, a.ctypes.data if a.size else None, a.size, C.byref(h)))
+        self.sync()
+        return DeviceFile(self, h)
+
+    def stage_path(self, path):
+        h = C.c_void_p()
+        check(lib().fxg_file_from_path(self.ctx, os.fsencode(path), C.byref(h)))
+        return DeviceFile(self, h)
+
+    def alloc_file(self, nbytes):
+        h = C.c_void_p()
+        check(lib().fxg_file_alloc(self.ctx, nbytes, C.byref(h)))
+        return DeviceFile(self, h)
+
+    def wrap_file(self, devptr, nbytes, capacity):
+        h = C.c_void_p()
+        check(lib().fxg_file_wrap(self.ctx, devptr, nbytes, capacity, C.byref(h)))
+        return DeviceFile(self, h)
+
+    # ---- index scans ------------------------------------------------------------------------
+    def fasta_scan_dev(self, dfile, full_name=False, base_offset=0):
+        """-> (device pointer to rows in the context scratch, stats dict)"""
+        st = ScanStats()
+        d_rows = C.c_void_p()
+        check(lib().fxg_fasta_scan(self.ctx, dfile.handle, base_offset, _cabi.SCAN_FULL_NAME if full_name else 0,
+                                   C.byref(d_rows), C.byref(st)))
+        return d_rows.value, _stats_dict(st)
+
+    def fasta_scan(self, dfile, full_name=False, base_offset=0, keep_device_rows=False):
+        d_rows, st = self.fasta_scan_dev(dfile, full_name, base_offset)
+        rows = np.zeros(st["n_rows"], dtype=FASTA_ROW)
+        if st["n_rows"]:
+            check(lib().fxg_rows_download(self.ctx, d_rows, st["n_rows"], FASTA_ROW.itemsize, rows.ctypes.data))
+        if keep_device_rows:
+            return rows, st, self.upload_rows(rows)
+        return rows, st
+
+    def fastq_scan_dev(self, dfile, base_offset=0, first_line=0):
+        st = ScanStats()
+        d_rows = C.c_void_p()
+        check(lib().fxg_fastq_scan(self.ctx, dfile.handle, base_offset, first_line, C.byref(d_rows), C.byref(st)))
+        return d_rows.value, _stats_dict(st)
+
+    def fastq_scan(self, dfile, base_offset=0, first_line=0, keep_device_rows=False, include_partial=False):
+        d_rows, st = self.fastq_scan_dev(dfile, base_offset, first_line)
+        n = st["n_rows"]
+        if include_partial:
+            n = (first_line + st["n_lines"] + 3) // 4 - first_line // 4
+        rows = np.zeros(n, dtype=FASTQ_ROW)
+        if n:
+            check(lib().fxg_rows_download(self.ctx, d_rows, n, FASTQ_ROW.itemsize, rows.ctypes.data))
+        if keep_device_rows:
+            return rows, st, self.upload_rows(rows)
+        return rows, st
+
+    def count_lines(self, dfile):
+        n = C.c_int64(0)
+        e = C.c_int(0)
+        check(lib().fxg_count_lines(self.ctx, dfile.handle, C.byref(n), C.byref(e)))
+        return n.value, bool(e.value)
+
+    def upload_rows(self, rows):
+        rows = np.ascontiguousarray(rows)
+        d = C.c_void_p()
+        check(lib().fxg_rows_upload(self.ctx, rows.ctypes.data if rows.size else None, rows.size,
+                                    rows.dtype.itemsize, C.byref(d)))
+        return DeviceRows(self, d.value, rows.size, rows.dtype)
+
+    def fasta_build_index_host(self, data, full_name=False):
+        """End-to-end host-buffer form: H2D staging + scan + D2H rows in one C call."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        cap = max(1024, a.size // 64)
+        while True:
+            rows = np.zeros(cap, dtype=FASTA_ROW)
+            st = ScanStats()
+            rc = lib().fxg_fasta_build_index_host(self.ctx, a.ctypes.data if a.size else None, a.size,
+                                                  _cabi.SCAN_FULL_NAME if full_name else 0,
+                                                  rows.ctypes.data, cap, C.byref(st))
+            if rc == _cabi.FXG_ECAP:
+                cap = st.n_rows
+                continue
+            check(rc)
+            return rows[:st.n_rows], _stats_dict(st)
+
+    def fastq_build_index_host(self, data):
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        cap = max(1024, a.size // 64)
+        while True:
+            rows = np.zeros(cap, dtype=FASTQ_ROW)
+            st = ScanStats()
+            rc = lib().fxg_fastq_build_index_host(self.ctx, a.ctypes.data if a.size else None, a.size,
+                                                  rows.ctypes.data, cap, C.byref(st))
+            if rc == _cabi.FXG_ECAP:
+                cap = st.n_rows
+                continue
+            check(rc)
+            return rows[:st.n_rows], _stats_dict(st)
+
+    # ---- extraction -------------------------------------------------------------------------
+    def extract(self, dfile, drows, row_id, s, e, flags=None, want_acgt=False):
+        """Batched (row, s, e, flags) -> (out uint8[total], out_off int64[nq+1], acgt int64[nq,4] | None)"""
+        row_id = np.ascontiguousarray(row_id, dtype=np.int64)
+        s = np.ascontiguousarray(s, dtype=np.int64)
+        e = np.ascontiguousarray(e, dtype=np.int64)
+        nq = row_id.size
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.int32)
+        total = int(np.maximum(e - s, 0).sum())
+        out = np.empty(max(total, 1), dtype=np.uint8)
+        off = np.zeros(nq + 1, dtype=np.int64)
+        acgt = np.zeros((nq, 4), dtype=np.int64) if want_acgt else None
+        check(lib().fxg_extract_host(self.ctx, dfile.handle, drows.devptr, drows.n_rows, ptr(row_id), ptr(s), ptr(e),
+                                     ptr(fl), nq, ptr(off), ptr(out), out.size, ptr(acgt)))
+        return out[:total], off, acgt
+
+    def reads(self, dfile, drows, ids, flags=0, want_seq=True, want_qual=True, rlens=None):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        nq = ids.size
+        if rlens is None:
+            raise ValueError("rlens (host copy of the rows' rlen for these ids) is required to size the output")
+        total = int(np.asarray(rlens, dtype=np.int64).sum())
+        seq = np.empty(max(total, 1), dtype=np.uint8) if want_seq else None
+        qual = np.empty(max(total, 1), dtype=np.uint8) if want_qual else None
+        off = np.zeros(nq + 1, dtype=np.int64)
+        check(lib().fxg_reads_host(self.ctx, dfile.handle, drows.devptr, drows.n_rows, ptr(ids), nq, flags,
+                                   ptr(off), ptr(seq), ptr(qual), max(total, 1)))
+        return (seq[:total] if want_seq else None), (qual[:total] if want_qual else None), off
