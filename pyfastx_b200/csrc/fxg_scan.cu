@@ -29,7 +29,7 @@ namespace fxg {
 
 constexpr int TILE    = 16384;          // bytes per tile
 constexpr int HALO    = 256;            // left halo kept in smem (previous line starts)
-constexpr int STAGES  = 3;
+constexpr int STAGES  = 3;          // tile i-1 (phase C) | tile i (phase A) | tile i+1 (loading)
 constexpr int THREADS = 256;
 constexpr int NWARPS  = THREADS / 32;
 constexpr int REGION  = TILE / NWARPS;  // contiguous bytes per warp (2048)
@@ -38,93 +38,78 @@ constexpr int LB      = THREADS;        // lines per phase-C batch
 constexpr int STAGE_BYTES = HALO + TILE;
 constexpr int64_t NOPOS = INT64_MIN / 4;
 
-struct __align__(16) TileDesc {   // decoupled look-back descriptor (64 B)
-    uint64_t nl;       // newlines
-    uint64_t hdr;      // header starts ('>' at a line start)
-    int64_t  p_last;   // last newline position (buffer relative)
-    int64_t  p_prev;   // the one before it
-    int32_t  k;        // how many of (p_last, p_prev) are valid: 0, 1, 2
-    uint32_t status;   // 0 = not yet, 1 = ready
-    uint64_t pad[3];
-};
+// ---- decoupled look-back state ---------------------------------------------------------------
+// Two 16-byte entries per tile, every 64-bit word self-validating (0 = not written yet), so no
+// fence / flag ordering is needed and a reader costs ONE L2 round trip:
+//   cnt[t] = { st<<62 | newlines , st<<62 | header starts }   st 1 = tile aggregate, 2 = inclusive prefix
+//   pos[t] = { p_last + 2 , p_prev + 2 }  positions of the tile's last two newlines; 1 = none
+constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
 
-struct Agg {
+struct Agg {          // exclusive prefix handed to phase C
     uint64_t nl, hdr;
     int64_t  p_last, p_prev;
     int      k;
 };
 
-__device__ __forceinline__ Agg agg_identity() { return Agg{0, 0, NOPOS, NOPOS, 0}; }
-// a = earlier range, b = later range
-__device__ __forceinline__ Agg agg_combine(const Agg &a, const Agg &b) {
-    Agg r;
-    r.nl = a.nl + b.nl;
-    r.hdr = a.hdr + b.hdr;
-    if (b.k >= 2) { r.p_last = b.p_last; r.p_prev = b.p_prev; r.k = 2; }
-    else if (b.k == 1) { r.p_last = b.p_last; r.p_prev = a.p_last; r.k = min(2, 1 + a.k); }
-    else { r.p_last = a.p_last; r.p_prev = a.p_prev; r.k = a.k; }
-    return r;
+__device__ __forceinline__ ulonglong2 ld_desc(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ Agg agg_shfl_down(const Agg &a, int d) {
-    Agg r;
-    r.nl = (uint64_t)shfl_down_i64((int64_t)a.nl, d);
-    r.hdr = (uint64_t)shfl_down_i64((int64_t)a.hdr, d);
-    r.p_last = shfl_down_i64(a.p_last, d);
-    r.p_prev = shfl_down_i64(a.p_prev, d);
-    r.k = __shfl_down_sync(0xffffffffu, a.k, d);
-    return r;
+__device__ __forceinline__ void st_desc(ulonglong2 *p, uint64_t x, uint64_t y) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
 }
-__device__ __forceinline__ void desc_publish(TileDesc *d, const Agg &a) {
-    d->nl = a.nl; d->hdr = a.hdr; d->p_last = a.p_last; d->p_prev = a.p_prev; d->k = a.k;
-    __threadfence();
-    st_volatile_u32(&d->status, 1u);
-}
-__device__ __forceinline__ Agg desc_read(const TileDesc *d) {
-    Agg a;
-    a.nl = ld_cg_u64(&d->nl); a.hdr = ld_cg_u64(&d->hdr);
-    a.p_last = ld_cg_i64(&d->p_last); a.p_prev = ld_cg_i64(&d->p_prev);
-    a.k = __ldcg(&d->k);
-    return a;
-}
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return (uint64_t)shfl_i64((int64_t)v, src); }
 
-// Exclusive prefix of tile t over tiles [0, t): warp-wide decoupled look-back.
-__device__ Agg lookback(const TileDesc *agg, const TileDesc *inc, int64_t t, int lane, const Agg &seed) {
-    Agg acc = agg_identity();
+// Exclusive (newline, header) counts of tile t: warp-wide look-back over windows of 128 tiles
+// (4 independent 16-byte loads per lane in flight).  Sums are commutative, so a window reduces
+// with two REDUX instructions plus one shuffle of the (large) inclusive value it ends on.
+__device__ void lookback_counts(const ulonglong2 *cnt, int64_t t, int lane, uint64_t &ex_nl, uint64_t &ex_hdr) {
+    uint64_t snl = 0, shdr = 0;
     int64_t j0 = t - 1;
     while (true) {
-        const int64_t j = j0 - lane;
-        Agg mine = agg_identity();
-        int st = 2;
-        if (j >= 0) {
-            while (true) {
-                if (ld_volatile_u32(&inc[j].status)) { st = 2; break; }
-                if (ld_volatile_u32(&agg[j].status)) { st = 1; break; }
-            }
-            __threadfence();
-            mine = desc_read(st == 2 ? &inc[j] : &agg[j]);
-        } else if (j == -1) {
-            mine = seed;
-        }
-        const uint32_t done = __ballot_sync(0xffffffffu, st == 2);
-        const int first = done ? (__ffs(done) - 1) : 32;
-        if (lane > first) mine = agg_identity();
+        ulonglong2 v[4];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            Agg o = agg_shfl_down(mine, d);
-            if (lane + d < 32) mine = agg_combine(o, mine);
+        for (int m = 0; m < 4; ++m) {
+            const int64_t j = j0 - lane - 32 * m;
+            v[m] = (j >= 0) ? ld_desc(cnt + j) : make_ulonglong2(ST_INC, ST_INC);   // before tile 0: prefix 0
         }
-        // lane 0 now holds the ordered combination of this window
-        Agg w;
-        w.nl = (uint64_t)shfl_i64((int64_t)mine.nl, 0);
-        w.hdr = (uint64_t)shfl_i64((int64_t)mine.hdr, 0);
-        w.p_last = shfl_i64(mine.p_last, 0);
-        w.p_prev = shfl_i64(mine.p_prev, 0);
-        w.k = __shfl_sync(0xffffffffu, mine.k, 0);
-        acc = agg_combine(w, acc);
-        if (done) break;
-        j0 -= 32;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int64_t j = j0 - lane - 32 * m;
+            while ((v[m].x & ST_MASK) == 0 || ((v[m].x ^ v[m].y) & ST_MASK) != 0) v[m] = ld_desc(cnt + j);
+            const bool inc = (v[m].x & ST_MASK) == ST_INC;
+            const uint32_t ball = __ballot_sync(0xffffffffu, inc);
+            const int first = ball ? (__ffs(ball) - 1) : 32;
+            const uint32_t a = lane < first ? (uint32_t)(v[m].x & ~ST_MASK) : 0u;   // tile aggregates are < 2^15
+            const uint32_t b = lane < first ? (uint32_t)(v[m].y & ~ST_MASK) : 0u;
+            snl += __reduce_add_sync(0xffffffffu, a);
+            shdr += __reduce_add_sync(0xffffffffu, b);
+            if (ball) {
+                snl += shfl_u64(v[m].x & ~ST_MASK, first);
+                shdr += shfl_u64(v[m].y & ~ST_MASK, first);
+                ex_nl = snl; ex_hdr = shdr;
+                return;
+            }
+        }
+        j0 -= 128;
     }
-    return acc;
+}
+
+// The two newlines preceding tile t (buffer-relative); -1 is the virtual newline before byte 0.
+__device__ void lookback_positions(const ulonglong2 *pos, int64_t t, int64_t &p_last, int64_t &p_prev, int &k) {
+    int64_t got[2] = {NOPOS, NOPOS};
+    int n = 0;
+    for (int64_t j = t - 1; n < 2; --j) {
+        if (j < 0) { got[n++] = -1; break; }
+        ulonglong2 pv;
+        do { pv = ld_desc(pos + j); } while (pv.x == 0 || pv.y == 0);
+        if (pv.x != 1) {
+            got[n++] = (int64_t)pv.x - 2;
+            if (n < 2 && pv.y != 1) got[n++] = (int64_t)pv.y - 2;
+        }
+    }
+    p_last = got[0]; p_prev = got[1]; k = n;
 }
 
 struct __align__(16) FastaTmp {   // per header slot (slot 0 = lines before the first header)
@@ -158,8 +143,8 @@ struct ScanParams {
     int64_t   base_offset;  // added to every file offset written to rows
     int64_t   first_line;   // FASTQ: global index of the first line of this buffer
     int       flags;
-    TileDesc *agg;
-    TileDesc *inc;
+    ulonglong2 *cnt;        // look-back: counts (aggregate -> inclusive, in place)
+    ulonglong2 *pos;        // look-back: last two newline positions per tile
     uint32_t *tile_counter;
     ScanTotals *totals;
     FastaTmp *tmp;          // FASTA
@@ -168,16 +153,43 @@ struct ScanParams {
     int64_t   qrows_cap;
 };
 
+// Per-CTA roles (warp specialisation):
+//   warps 0..7  "workers": phase A of tile i (as soon as its TMA load lands) then phase C of
+//               tile i-1.  They never spin on other CTAs.
+//   warp  8     "prefix warp": takes each tile's aggregate from a mailbox, publishes it, runs the
+//               decoupled look-back and hands the exclusive prefix (+ the two preceding newline
+//               positions) back.  Its waiting overlaps phase A of the next tile, and -- crucially --
+//               a tile's aggregate is published a fixed, short time after the tile was claimed,
+//               never behind another tile's look-back.
+constexpr int WORKERS = THREADS;            // 256 worker threads
+constexpr int CTA_THREADS = THREADS + 32;   // + prefix warp
+
+struct Mail {           // workers -> prefix warp (per pipeline slot)
+    int64_t  t;         // tile id, -1 = no more tiles
+    int64_t  last0, last1;
+    uint32_t T_nl, T_h, tsh, pad;
+};
+struct Pref {           // prefix warp -> workers
+    uint64_t ex_nl, ex_hdr;
+};
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int MODE>   // 0 = FASTA, 1 = FASTQ
-__global__ void __launch_bounds__(THREADS, 2) scan_kernel(const ScanParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t mail_bar[2];
+    __shared__ __align__(8) uint64_t pref_bar[2];
     __shared__ int64_t  s_tile[STAGES];
-    __shared__ int64_t  l_pos[LB + 2];
-    __shared__ uint32_t l_flag[LB + 2];
+    __shared__ int64_t  l_pos[2][LB + 2];
+    __shared__ uint32_t l_flag[2][LB + 2];
     __shared__ uint32_t s_wtot[NWARPS];
-    __shared__ int64_t  s_last[2];
-    __shared__ Agg      s_prefix;
+    __shared__ Mail     s_mail[2];
+    __shared__ Pref     s_pref[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -185,6 +197,65 @@ __global__ void __launch_bounds__(THREADS, 2) scan_kernel(const ScanParams P) {
     const bool virt = (n > 0) && (P.file[n - 1] != '\n');
     const int64_t n_eff = n + (virt ? 1 : 0);
     const bool full_name = (P.flags & FXG_SCAN_FULL_NAME) != 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&mail_bar[s], 1); mbar_init(&pref_bar[s], 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto stage_ptr = [&](int it) -> uint8_t * { return dyn_smem + (size_t)(it % STAGES) * STAGE_BYTES + HALO; };
+    // byte at buffer-relative position x, given the tile (id t, base) whose stage is tb
+    auto byte_at = [&](const uint8_t *tb, int64_t t, int64_t base, int64_t x) -> uint8_t {
+        const int64_t r = x - base;
+        if (r >= -(int64_t)HALO && (t > 0 || r >= 0)) return tb[r];
+        return P.file[x];
+    };
+
+    // =========================================================================================
+    // prefix warp
+    // =========================================================================================
+    if (warp == NWARPS) {
+        for (int it = 0;; ++it) {
+            const int q = it & 1;
+            mbar_wait(&mail_bar[q], (uint32_t)((it >> 1) & 1));
+            const Mail m = s_mail[q];
+            if (m.t < 0) break;
+            const int64_t t = m.t, base = t * TILE;
+            const uint8_t *tb = stage_ptr(it);
+            if (lane == 0) {
+                st_desc(&P.cnt[t], ST_AGG | (uint64_t)m.T_nl, ST_AGG | (uint64_t)m.T_h);
+                st_desc(&P.pos[t], m.T_nl >= 1 ? (uint64_t)(m.last0 + 2) : 1ull, m.T_nl >= 2 ? (uint64_t)(m.last1 + 2) : 1ull);
+            }
+            uint64_t ex_nl = 0, ex_hdr = 0;
+            lookback_counts(P.cnt, t, lane, ex_nl, ex_hdr);
+            if (lane == 0) {
+                st_desc(&P.cnt[t], ST_INC | (ex_nl + (uint64_t)m.T_nl), ST_INC | (ex_hdr + (uint64_t)m.T_h));
+                if (t == P.ntiles - 1) {
+                    P.totals->nl = ex_nl + (uint64_t)m.T_nl; P.totals->hdr = ex_hdr + (uint64_t)m.T_h; P.totals->n_eff = n_eff;
+                }
+                int64_t pl, pp; int k;
+                lookback_positions(P.pos, t, pl, pp, k);
+                uint32_t nh1 = 0, hc1 = 0, nh2 = 0;
+                if (MODE == 0) {
+                    if (pl + 1 == base) { nh1 = m.tsh; hc1 = m.tsh; }
+                    else nh1 = (byte_at(tb, t, base, pl + 1) == '>') ? 1u : 0u;
+                    if (k >= 2) nh2 = (byte_at(tb, t, base, pp + 1) == '>') ? 1u : 0u;
+                }
+                l_pos[q][1] = pl;                    l_flag[q][1] = (nh1 << 31) | hc1;
+                l_pos[q][0] = k >= 2 ? pp : NOPOS;   l_flag[q][0] = (nh2 << 31);
+                s_pref[q].ex_nl = ex_nl; s_pref[q].ex_hdr = ex_hdr;
+                mbar_arrive(&pref_bar[q]);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // =========================================================================================
+    // workers
+    // =========================================================================================
     unsigned long long my_size = 0;   // FASTQ: sum of rlen seen by this thread
 
     auto issue = [&](int st) {
@@ -204,192 +275,88 @@ __global__ void __launch_bounds__(THREADS, 2) scan_kernel(const ScanParams P) {
                 return;
             }
         }
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[st])) : "memory");
+        mbar_arrive(&full_bar[st]);
     };
 
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0)
-        for (int s = 0; s < STAGES; ++s) issue(s);
+    // state of the tile whose phase A has run and whose phase C is still pending
+    struct TileState {
+        int64_t t, base;
+        uint32_t c[CHUNKS], pre[CHUNKS], wbase, tsh;
+        int T_nl;
+    } cur, prev;
+    prev.t = -1; prev.base = 0; prev.T_nl = 0; prev.wbase = 0; prev.tsh = 0;
+    for (int j = 0; j < CHUNKS; ++j) { prev.c[j] = 0; prev.pre[j] = 0; }
+    cur = prev;
+    const int roff = warp * REGION + lane * 16;
 
-    for (int it = 0;; ++it) {
-        const int st = it % STAGES;
-        mbar_wait(&full_bar[st], (uint32_t)((it / STAGES) & 1));
-        const int64_t t = s_tile[st];
-        if (t >= P.ntiles) break;
-        const int64_t base = t * TILE;
-        uint8_t *tb = dyn_smem + (size_t)st * STAGE_BYTES + HALO;   // tb[x] = byte base + x
-        auto byte_at = [&](int64_t x) -> uint8_t {                 // x = buffer-relative position
-            const int64_t r = x - base;
-            if (r >= -(int64_t)HALO && (t > 0 || r >= 0)) return tb[r];
-            return P.file[x];
-        };
-
-        // the tile that contains EOF: neutralise bytes past n, plant the virtual newline
-        if (base + TILE > n) {
-            for (int x = tid; x < TILE; x += THREADS)
-                if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
-            __syncthreads();
-        }
-
-        // ---------------- phase A: newline masks, ordered indices -----------------------------
-        const int roff = warp * REGION + lane * 16;
-        uint32_t c[CHUNKS], pre[CHUNKS];     // pre = exclusive (nl | hdr << 16) before this chunk, warp-local
-        uint32_t run = 0;
+    // entries [b0, b0+LB) of tile S's newline list -> list slot q
+    auto write_entries = [&](const TileState &S, const uint8_t *tb, int q, int b0, int64_t *last) {
 #pragma unroll
         for (int j = 0; j < CHUNKS; ++j) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(tb + roff + j * 512);
-            c[j] = chunk_eq_mask(v, 0x0a0a0a0au);
-            const uint32_t cnt = __popc(c[j]);
-            uint32_t h = 0;
-            if (MODE == 0 && cnt) {
-                uint32_t m = c[j];
-                while (m) {
-                    const int beta = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int x = roff + j * 512 + chunk_bit_to_off(beta) + 1;   // next line start
-                    if (x < TILE && base + x < n && tb[x] == '>') ++h;
-                }
-            }
-            uint32_t excl, tot;
-            if (!__any_sync(0xffffffffu, cnt > 1)) {
-                const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
-                const uint32_t bh = __ballot_sync(0xffffffffu, h != 0);
-                excl = __popc(bn & lt_mask) | (__popc(bh & lt_mask) << 16);
-                tot = __popc(bn) | (__popc(bh) << 16);
-            } else {
-                const uint32_t packed = cnt | (h << 16);
-                uint32_t incl = packed;
+            uint32_t m = S.c[j];
+            if (!m) continue;
+            int idx = (int)((S.wbase + S.pre[j]) & 0xffffu);
+            uint32_t hc = S.tsh + ((S.wbase + S.pre[j]) >> 16);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                excl = incl - packed;
-                tot = __shfl_sync(0xffffffffu, incl, 31);
-            }
-            pre[j] = run + excl;
-            run += tot;
-        }
-        if (lane == 0) s_wtot[warp] = run;
-        __syncthreads();   // (1)
-        uint32_t wbase = 0, ttot = 0;
-#pragma unroll
-        for (int w = 0; w < NWARPS; ++w) {
-            const uint32_t v = s_wtot[w];
-            if (w < warp) wbase += v;
-            ttot += v;
-        }
-        const int T_nl = (int)(ttot & 0xffffu);
-        const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
-        const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
-        const uint32_t T_h = (ttot >> 16) + tsh;
-
-        // ---------------- entries of batch 0 + the tile's last two newline positions -------------
-        auto write_entries = [&](int b0) {
-#pragma unroll
-            for (int j = 0; j < CHUNKS; ++j) {
-                uint32_t m = c[j];
-                if (!m) continue;
-                int idx = (int)((wbase + pre[j]) & 0xffffu);
-                uint32_t hc = tsh + ((wbase + pre[j]) >> 16);
-                // iterate set bits in increasing byte order: word w = 0..3, then byte b
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    uint32_t mw = m & (0x80808080u >> w);
-                    while (mw) {
-                        const int beta = __ffs(mw) - 1;
-                        mw &= mw - 1;
-                        const int x = roff + j * 512 + chunk_bit_to_off(beta);
-                        uint32_t nh = 0;
-                        if (MODE == 0) {
-                            const int y = x + 1;
-                            nh = (y < TILE && base + y < n && tb[y] == '>') ? 1u : 0u;
-                            hc += nh;
-                        }
-                        const int rel = idx - b0;
-                        if (rel >= 0 && rel < LB) {
-                            l_pos[2 + rel] = base + x;
-                            l_flag[2 + rel] = (nh << 31) | hc;
-                        }
-                        if (b0 == 0) {
-                            if (idx == T_nl - 1) s_last[0] = base + x;
-                            if (idx == T_nl - 2) s_last[1] = base + x;
-                        }
-                        ++idx;
+            for (int w = 0; w < 4; ++w) {                     // increasing byte order: word, then byte
+                uint32_t mw = m & (0x80808080u >> w);
+                while (mw) {
+                    const int beta = __ffs(mw) - 1;
+                    mw &= mw - 1;
+                    const int x = roff + j * 512 + chunk_bit_to_off(beta);
+                    uint32_t nh = 0;
+                    if (MODE == 0) {
+                        const int y = x + 1;
+                        nh = (y < TILE && S.base + y < n && tb[y] == '>') ? 1u : 0u;
+                        hc += nh;
                     }
-                }
-            }
-        };
-        write_entries(0);
-        __syncthreads();   // (2)
-
-        // ---------------- publish aggregate, look back, publish inclusive prefix -------------------
-        if (warp == 0) {
-            Agg mine;
-            mine.nl = (uint64_t)T_nl; mine.hdr = T_h;
-            mine.k = T_nl >= 2 ? 2 : T_nl;
-            mine.p_last = T_nl >= 1 ? s_last[0] : NOPOS;
-            mine.p_prev = T_nl >= 2 ? s_last[1] : NOPOS;
-            if (lane == 0) desc_publish(&P.agg[t], mine);
-            Agg seed = agg_identity();
-            seed.k = 1; seed.p_last = -1;          // virtual newline before byte 0
-            const Agg ex = lookback(P.agg, P.inc, t, lane, seed);
-            if (lane == 0) {
-                const Agg in = agg_combine(ex, mine);
-                desc_publish(&P.inc[t], in);
-                s_prefix = ex;
-                // carry entries: the two newlines preceding this tile
-                const int64_t pl = ex.p_last;
-                uint32_t nh1 = 0, hc1 = 0, nh2 = 0;
-                if (MODE == 0) {
-                    if (pl + 1 == base) { nh1 = tsh; hc1 = tsh; }
-                    else nh1 = (byte_at(pl + 1) == '>') ? 1u : 0u;
-                    if (ex.k >= 2) nh2 = (byte_at(ex.p_prev + 1) == '>') ? 1u : 0u;
-                }
-                l_pos[1] = pl;              l_flag[1] = (nh1 << 31) | hc1;
-                l_pos[0] = ex.k >= 2 ? ex.p_prev : NOPOS;   l_flag[0] = (nh2 << 31);
-                if (t == P.ntiles - 1) {
-                    P.totals->nl = in.nl; P.totals->hdr = in.hdr; P.totals->n_eff = n_eff;
+                    const int rel = idx - b0;
+                    if (rel >= 0 && rel < LB) {
+                        l_pos[q][2 + rel] = S.base + x;
+                        l_flag[q][2 + rel] = (nh << 31) | hc;
+                    }
+                    if (last) {
+                        if (idx == S.T_nl - 1) last[0] = S.base + x;
+                        if (idx == S.T_nl - 2) last[1] = S.base + x;
+                    }
+                    ++idx;
                 }
             }
         }
-        __syncthreads();   // (3)
+    };
 
-        // ---------------- phase C: one thread per line ----------------------------------------------
-        const Agg ex = s_prefix;
-        for (int b0 = 0; b0 < T_nl; b0 += LB) {
+    // ---- phase C of tile S (its list for batch 0 is already in slot q) ---------------------------
+    auto phase_c = [&](const TileState &S, const uint8_t *tb, int q) {
+        const uint64_t ex_nl = s_pref[q].ex_nl, ex_hdr = s_pref[q].ex_hdr;
+        for (int b0 = 0; b0 < S.T_nl; b0 += LB) {
             if (b0 > 0) {
-                __syncthreads();
+                worker_bar();
                 int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
-                if (tid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
-                __syncthreads();
-                if (tid == 0) { l_pos[0] = c0; l_pos[1] = c1; l_flag[0] = g0; l_flag[1] = g1; }
-                write_entries(b0);
-                __syncthreads();
+                if (tid == 0) { c0 = l_pos[q][LB]; c1 = l_pos[q][LB + 1]; g0 = l_flag[q][LB]; g1 = l_flag[q][LB + 1]; }
+                worker_bar();
+                if (tid == 0) { l_pos[q][0] = c0; l_pos[q][1] = c1; l_flag[q][0] = g0; l_flag[q][1] = g1; }
+                write_entries(S, tb, q, b0, nullptr);
+                worker_bar();
             }
             const int idx = b0 + tid;
-            if (idx < T_nl) {
+            if (idx < S.T_nl) {
                 const int e = 2 + tid;
-                const int64_t p = l_pos[e], pm1 = l_pos[e - 1], pm2 = l_pos[e - 2];
-                const uint32_t f1 = l_flag[e - 1], f2 = l_flag[e - 2];
+                const int64_t p = l_pos[q][e], pm1 = l_pos[q][e - 1], pm2 = l_pos[q][e - 2];
+                const uint32_t f1 = l_flag[q][e - 1], f2 = l_flag[q][e - 2];
                 const int64_t s = pm1 + 1;
                 const int64_t L = p - pm1;                         // len + 1
-                const int64_t lineidx = (int64_t)ex.nl + idx;      // buffer-local line index
+                const int64_t lineidx = (int64_t)ex_nl + idx;      // buffer-local line index
                 if (MODE == 0) {
                     const bool is_hdr = (f1 >> 31) != 0;
-                    const int64_t slot = (int64_t)ex.hdr + (int64_t)(f1 & 0x7fffffffu);   // rec + 1
+                    const int64_t slot = (int64_t)ex_hdr + (int64_t)(f1 & 0x7fffffffu);   // rec + 1
                     if (is_hdr) {
-                        const int elen = (byte_at(p - 1) == '\r') ? 2 : 1;
+                        const int elen = (byte_at(tb, S.t, S.base, p - 1) == '\r') ? 2 : 1;
                         const int64_t dlen = L - 1 - elen;
                         int64_t nlen = dlen;
                         if (!full_name) {
                             nlen = 0;
                             while (nlen < dlen) {
-                                const uint8_t ch = byte_at(s + 1 + nlen);
+                                const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + nlen);
                                 if (ch == ' ' || ch == '\t') break;
                                 ++nlen;
                             }
@@ -423,39 +390,127 @@ __global__ void __launch_bounds__(THREADS, 2) scan_kernel(const ScanParams P) {
                     const int ph = (int)(gline & 3);
                     const int64_t row = (gline >> 2) - (P.first_line >> 2);
                     const int64_t len = L - 1;
-                    if (row < P.qrows_cap) {
+                    if (ph == 1) {
+                        const int64_t rlen = (len > 0 && byte_at(tb, S.t, S.base, p - 1) == '\r') ? len - 1 : len;
+                        my_size += (unsigned long long)rlen;
+                        if (row < P.qrows_cap) { P.qrows[row].soff = P.base_offset + s; P.qrows[row].rlen = rlen; }
+                    } else if (row < P.qrows_cap) {
                         fxg_fastq_row *r = &P.qrows[row];
                         if (ph == 0) {
                             int64_t l = len - 1;
-                            if (l > 0 && byte_at(p - 1) == '\r') --l;
+                            if (l > 0 && byte_at(tb, S.t, S.base, p - 1) == '\r') --l;
                             if (l < 0) l = 0;
                             int64_t k = 0;
                             for (; k < l; ++k) {
-                                const uint8_t ch = byte_at(s + 1 + k);
+                                const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + k);
                                 if (ch == 0) { k = l; break; }
                                 if (ch == ' ') break;
                             }
                             r->dlen = (int32_t)len;
                             r->nlen = (int32_t)k;
-                        } else if (ph == 1) {
-                            const int64_t rlen = (len > 0 && byte_at(p - 1) == '\r') ? len - 1 : len;
-                            r->soff = P.base_offset + s;
-                            r->rlen = rlen;
-                            my_size += (unsigned long long)rlen;
                         } else if (ph == 3) {
                             r->qoff = P.base_offset + s;
                         }
-                    } else if (ph == 1) {
-                        const int64_t rlen = (len > 0 && byte_at(p - 1) == '\r') ? len - 1 : len;
-                        my_size += (unsigned long long)rlen;
                     }
                 }
             }
         }
-        __syncthreads();   // all reads of this stage's smem are done
-        if (tid == 0) issue(st);
-    }
+    };
 
+    if (tid == 0) issue(0);
+    __shared__ int64_t s_lastpos[2];
+
+    for (int it = 0;; ++it) {
+        const int st = it % STAGES, q = it & 1;
+        mbar_wait(&full_bar[st], (uint32_t)((it / STAGES) & 1));
+        const int64_t t = s_tile[st];
+        const bool have = t < P.ntiles;
+        uint8_t *tb = stage_ptr(it);
+        if (have) {
+            // claim + prefetch the next tile: stage (it+1)%3 held tile it-2, whose phase C ended
+            // (worker barrier) in iteration it-1
+            if (tid == 0) issue((it + 1) % STAGES);
+            const int64_t base = t * TILE;
+            // the tile that contains EOF: neutralise bytes past n, plant the virtual newline
+            if (base + TILE > n) {
+                for (int x = tid; x < TILE; x += WORKERS)
+                    if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
+                worker_bar();
+            }
+            // ---------------- phase A: newline masks, ordered indices -----------------------------
+            cur.t = t; cur.base = base;
+            uint32_t run = 0;
+#pragma unroll
+            for (int j = 0; j < CHUNKS; ++j) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(tb + roff + j * 512);
+                cur.c[j] = chunk_eq_mask(v, 0x0a0a0a0au);
+                const uint32_t cnt = __popc(cur.c[j]);
+                uint32_t h = 0;
+                if (MODE == 0 && cnt) {
+                    uint32_t m = cur.c[j];
+                    while (m) {
+                        const int beta = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int x = roff + j * 512 + chunk_bit_to_off(beta) + 1;   // next line start
+                        if (x < TILE && base + x < n && tb[x] == '>') ++h;
+                    }
+                }
+                uint32_t excl, tot;
+                if (!__any_sync(0xffffffffu, cnt > 1)) {
+                    const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
+                    const uint32_t bh = __ballot_sync(0xffffffffu, h != 0);
+                    excl = __popc(bn & lt_mask) | (__popc(bh & lt_mask) << 16);
+                    tot = __popc(bn) | (__popc(bh) << 16);
+                } else {
+                    const uint32_t packed = cnt | (h << 16);
+                    uint32_t incl = packed;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    excl = incl - packed;
+                    tot = __shfl_sync(0xffffffffu, incl, 31);
+                }
+                cur.pre[j] = run + excl;
+                run += tot;
+            }
+            if (lane == 0) s_wtot[warp] = run;
+            worker_bar();   // (1)
+            uint32_t wbase = 0, ttot = 0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) {
+                const uint32_t v = s_wtot[w];
+                if (w < warp) wbase += v;
+                ttot += v;
+            }
+            cur.wbase = wbase;
+            cur.T_nl = (int)(ttot & 0xffffu);
+            const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
+            cur.tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
+            const uint32_t T_h = (ttot >> 16) + cur.tsh;
+            write_entries(cur, tb, q, 0, s_lastpos);
+            worker_bar();   // (2) entries + last positions visible
+            if (tid == 0) {
+                s_mail[q].t = t; s_mail[q].T_nl = (uint32_t)cur.T_nl; s_mail[q].T_h = T_h; s_mail[q].tsh = cur.tsh;
+                s_mail[q].last0 = s_lastpos[0]; s_mail[q].last1 = s_lastpos[1];
+                mbar_arrive(&mail_bar[q]);
+            }
+        }
+        if (!have && tid == 0) {          // no more tiles: release the prefix warp
+            s_mail[q].t = -1;
+            mbar_arrive(&mail_bar[q]);
+        }
+        // ---------------- phase C of the previous tile (its look-back ran during our phase A) ------
+        if (it > 0 && prev.t >= 0) {
+            const int pq = q ^ 1;
+            mbar_wait(&pref_bar[pq], (uint32_t)(((it - 1) >> 1) & 1));
+            phase_c(prev, stage_ptr(it - 1), pq);
+        }
+        worker_bar();   // (3) stage it-1 and list slot q^1 are free again
+        if (!have) break;
+        prev = cur;
+    }
     if (MODE == 1) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) my_size += (unsigned long long)shfl_down_i64((int64_t)my_size, d);
@@ -553,10 +608,10 @@ static int scan_launch_config(fxg_ctx *ctx, int mode, int *grid, size_t *smem) {
     int per_sm = 0;
     if (mode == 0) {
         FXG_CUDA(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<0>, THREADS, *smem));
+        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<0>, CTA_THREADS, *smem));
     } else {
         FXG_CUDA(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<1>, THREADS, *smem));
+        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<1>, CTA_THREADS, *smem));
     }
     if (per_sm < 1) per_sm = 1;
     *grid = ctx->sm_count * per_sm;
@@ -595,7 +650,7 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
     const int64_t ntiles = (n + 1 + TILE - 1) / TILE;   // room for a virtual newline at n
     int rc;
     if ((rc = ctx->counters.reserve(256))) return rc;
-    if ((rc = ctx->tile_desc.reserve((size_t)ntiles * 2 * sizeof(TileDesc)))) return rc;
+    if ((rc = ctx->tile_desc.reserve((size_t)ntiles * 2 * sizeof(ulonglong2)))) return rc;
 
     double nlpb = 0, hpb = 0;
     if ((rc = sample_density(ctx, f, &nlpb, &hpb))) return rc;
@@ -616,14 +671,14 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
             // rows are fully overwritten except partially-owned boundary rows
             FXG_CUDA(cudaMemsetAsync(ctx->rows.ptr, 0, sizeof(fxg_fastq_row), ctx->stream));
         }
-        FXG_CUDA(cudaMemsetAsync(ctx->tile_desc.ptr, 0, (size_t)ntiles * 2 * sizeof(TileDesc), ctx->stream));
+        FXG_CUDA(cudaMemsetAsync(ctx->tile_desc.ptr, 0, (size_t)ntiles * 2 * sizeof(ulonglong2), ctx->stream));
         FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
 
         ScanParams P;
         memset(&P, 0, sizeof(P));
         P.file = f->d; P.n = n; P.capacity = f->capacity & ~(int64_t)15; P.ntiles = ntiles;
         P.base_offset = base_offset; P.first_line = first_line; P.flags = flags;
-        P.agg = (TileDesc *)ctx->tile_desc.ptr; P.inc = P.agg + ntiles;
+        P.cnt = (ulonglong2 *)ctx->tile_desc.ptr; P.pos = P.cnt + ntiles;
         P.tile_counter = (uint32_t *)ctx->counters.ptr;
         P.totals = (ScanTotals *)((uint8_t *)ctx->counters.ptr + 64);
         P.tmp = (FastaTmp *)ctx->row_tmp.ptr; P.tmp_cap = cap + 1;
@@ -631,8 +686,8 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
 
         {
             FxgProfScope prof(ctx, FXG_PROF_SCAN);
-            if (mode == 0) scan_kernel<0><<<grid, THREADS, smem, ctx->stream>>>(P);
-            else scan_kernel<1><<<grid, THREADS, smem, ctx->stream>>>(P);
+            if (mode == 0) scan_kernel<0><<<grid, CTA_THREADS, smem, ctx->stream>>>(P);
+            else scan_kernel<1><<<grid, CTA_THREADS, smem, ctx->stream>>>(P);
         }
         FXG_CUDA(cudaGetLastError());
 
