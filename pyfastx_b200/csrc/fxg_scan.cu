@@ -24,17 +24,22 @@
 //     headers and the event summary (proof of equivalence with index.c:325-342 in DESIGN.md);
 //   * FASTQ needs no per-record state at all: line k of the file writes field k%4 of row k/4.
 #include "fxg_common.cuh"
+#include <stdlib.h>
 
 namespace fxg {
 
 constexpr int TILE    = 16384;          // bytes per tile
 constexpr int HALO    = 256;            // left halo kept in smem (previous line starts)
-constexpr int STAGES  = 3;          // tile i-1 (phase C) | tile i (phase A) | tile i+1 (loading)
-constexpr int THREADS = 256;
+constexpr int LAG     = 2;          // phase C of tile i-LAG runs after phase A of tile i
+constexpr int STAGES  = LAG + 2;    // tiles i-LAG..i-1 (awaiting phase C) | tile i (phase A) | tile i+1 (loading)
+constexpr int NSLOT   = LAG + 1;    // line-list / mailbox slots
+constexpr int THREADS = 512;          // worker threads (16 warps) + one prefix warp
 constexpr int NWARPS  = THREADS / 32;
 constexpr int REGION  = TILE / NWARPS;  // contiguous bytes per warp (2048)
-constexpr int CHUNKS  = REGION / 512;   // 16-byte chunks per thread (4)
-constexpr int LB      = THREADS;        // lines per phase-C batch
+constexpr int BPT     = TILE / THREADS; // contiguous bytes per worker thread (32)
+constexpr int NCH     = BPT / 16;       // 16-byte chunks per thread (2)
+constexpr int LB      = 512;            // line-list capacity of a regular tile (lines >= 32 B on average)
+constexpr int SEGCAP  = 64;             // per-warp entry segment (2 KiB region: lines >= 21 B on average)
 constexpr int STAGE_BYTES = HALO + TILE;
 constexpr int64_t NOPOS = INT64_MIN / 4;
 
@@ -64,11 +69,13 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return (uint
 // Exclusive (newline, header) counts of tile t: warp-wide look-back over windows of 128 tiles
 // (4 independent 16-byte loads per lane in flight).  Sums are commutative, so a window reduces
 // with two REDUX instructions plus one shuffle of the (large) inclusive value it ends on.
-__device__ void lookback_counts(const ulonglong2 *cnt, int64_t t, int lane, uint64_t &ex_nl, uint64_t &ex_hdr) {
+__device__ void lookback_counts(const ulonglong2 *cnt, int64_t t, int lane, uint64_t &ex_nl, uint64_t &ex_hdr, int &nwin) {
     uint64_t snl = 0, shdr = 0;
+    nwin = 0;
     int64_t j0 = t - 1;
     while (true) {
         ulonglong2 v[4];
+        ++nwin;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int64_t j = j0 - lane - 32 * m;
@@ -151,6 +158,7 @@ struct ScanParams {
     int64_t   tmp_cap;      // slots
     fxg_fastq_row *qrows;   // FASTQ
     int64_t   qrows_cap;
+    unsigned long long *dbg; // optional cycle counters (FXG_SCAN_DEBUG=1)
 };
 
 // Per-CTA roles (warp specialisation):
@@ -166,11 +174,20 @@ constexpr int CTA_THREADS = THREADS + 32;   // + prefix warp
 
 struct Mail {           // workers -> prefix warp (per pipeline slot)
     int64_t  t;         // tile id, -1 = no more tiles
-    int64_t  last0, last1;
-    uint32_t T_nl, T_h, tsh, pad;
+    uint32_t tsh, pad;
 };
 struct Pref {           // prefix warp -> workers
     uint64_t ex_nl, ex_hdr;
+    int64_t  cpos[2];   // the two newlines preceding the tile: [1] = nearest, [0] = the one before (NOPOS if none)
+    uint32_t cflag[2];  // bit31: the line starting after that newline begins with '>' ; low bits: header count (only [1])
+    uint32_t pad[2];
+};
+struct Slot {           // everything phase C needs about a tile whose phase A has run
+    uint16_t seg_pos[NWARPS][SEGCAP];    // per-warp newline positions (tile relative), file order
+    uint16_t seg_flag[NWARPS][SEGCAP];   // bit15: next line starts with '>', low bits: warp-local inclusive header count
+    uint32_t wcnt[NWARPS];               // per warp: newlines | header starts << 16
+    Mail     mail;
+    Pref     pref;
 };
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
@@ -182,14 +199,13 @@ template <int MODE>   // 0 = FASTA, 1 = FASTQ
 __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ __align__(8) uint64_t mail_bar[2];
-    __shared__ __align__(8) uint64_t pref_bar[2];
+    __shared__ __align__(8) uint64_t mail_bar[NSLOT];
+    __shared__ __align__(8) uint64_t pref_bar[NSLOT];
     __shared__ int64_t  s_tile[STAGES];
-    __shared__ int64_t  l_pos[2][LB + 2];
-    __shared__ uint32_t l_flag[2][LB + 2];
-    __shared__ uint32_t s_wtot[NWARPS];
-    __shared__ Mail     s_mail[2];
-    __shared__ Pref     s_pref[2];
+    __shared__ __align__(16) Slot slots[NSLOT];
+    __shared__ int64_t  l_pos[LB + 2];       // compacted line list of the tile in phase C ([0],[1] = carry)
+    __shared__ uint32_t l_flag[LB + 2];
+    __shared__ uint32_t s_scan[NWARPS];      // dense path block scan
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&mail_bar[s], 1); mbar_init(&pref_bar[s], 1); }
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&mail_bar[s], 1); mbar_init(&pref_bar[s], 1); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -214,27 +230,28 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
     };
 
     // =========================================================================================
-    // prefix warp
+    // prefix warp: decoupled look-back for one tile after the other
     // =========================================================================================
     if (warp == NWARPS) {
         for (int it = 0;; ++it) {
-            const int q = it & 1;
-            mbar_wait(&mail_bar[q], (uint32_t)((it >> 1) & 1));
-            const Mail m = s_mail[q];
+            const int q = it % NSLOT;
+            const long long tm0 = clock64();
+            mbar_wait(&mail_bar[q], (uint32_t)((it / NSLOT) & 1));
+            if (P.dbg && lane == 0) atomicAdd(&P.dbg[7], (unsigned long long)(clock64() - tm0));
+            const Mail m = slots[q].mail;
             if (m.t < 0) break;
             const int64_t t = m.t, base = t * TILE;
             const uint8_t *tb = stage_ptr(it);
-            if (lane == 0) {
-                st_desc(&P.cnt[t], ST_AGG | (uint64_t)m.T_nl, ST_AGG | (uint64_t)m.T_h);
-                st_desc(&P.pos[t], m.T_nl >= 1 ? (uint64_t)(m.last0 + 2) : 1ull, m.T_nl >= 2 ? (uint64_t)(m.last1 + 2) : 1ull);
-            }
             uint64_t ex_nl = 0, ex_hdr = 0;
-            lookback_counts(P.cnt, t, lane, ex_nl, ex_hdr);
+            int nwin = 0;
+            const long long tl0 = clock64();
+            lookback_counts(P.cnt, t, lane, ex_nl, ex_hdr, nwin);
+            if (P.dbg && lane == 0) { atomicAdd(&P.dbg[4], (unsigned long long)(clock64() - tl0)); atomicAdd(&P.dbg[5], (unsigned long long)nwin); atomicAdd(&P.dbg[6], 1ull); }
             if (lane == 0) {
-                st_desc(&P.cnt[t], ST_INC | (ex_nl + (uint64_t)m.T_nl), ST_INC | (ex_hdr + (uint64_t)m.T_h));
-                if (t == P.ntiles - 1) {
-                    P.totals->nl = ex_nl + (uint64_t)m.T_nl; P.totals->hdr = ex_hdr + (uint64_t)m.T_h; P.totals->n_eff = n_eff;
-                }
+                const ulonglong2 own = ld_desc(&P.cnt[t]);
+                const uint64_t in_nl = ex_nl + (own.x & ~ST_MASK), in_hdr = ex_hdr + (own.y & ~ST_MASK);
+                st_desc(&P.cnt[t], ST_INC | in_nl, ST_INC | in_hdr);
+                if (t == P.ntiles - 1) { P.totals->nl = in_nl; P.totals->hdr = in_hdr; P.totals->n_eff = n_eff; }
                 int64_t pl, pp; int k;
                 lookback_positions(P.pos, t, pl, pp, k);
                 uint32_t nh1 = 0, hc1 = 0, nh2 = 0;
@@ -243,9 +260,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                     else nh1 = (byte_at(tb, t, base, pl + 1) == '>') ? 1u : 0u;
                     if (k >= 2) nh2 = (byte_at(tb, t, base, pp + 1) == '>') ? 1u : 0u;
                 }
-                l_pos[q][1] = pl;                    l_flag[q][1] = (nh1 << 31) | hc1;
-                l_pos[q][0] = k >= 2 ? pp : NOPOS;   l_flag[q][0] = (nh2 << 31);
-                s_pref[q].ex_nl = ex_nl; s_pref[q].ex_hdr = ex_hdr;
+                Pref &pr = slots[q].pref;
+                pr.ex_nl = ex_nl; pr.ex_hdr = ex_hdr;
+                pr.cpos[1] = pl;                    pr.cflag[1] = (nh1 << 31) | hc1;
+                pr.cpos[0] = k >= 2 ? pp : NOPOS;   pr.cflag[0] = (nh2 << 31);
                 mbar_arrive(&pref_bar[q]);
             }
             __syncwarp();
@@ -278,157 +296,186 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
         mbar_arrive(&full_bar[st]);
     };
 
-    // state of the tile whose phase A has run and whose phase C is still pending
-    struct TileState {
-        int64_t t, base;
-        uint32_t c[CHUNKS], pre[CHUNKS], wbase, tsh;
-        int T_nl;
-    } cur, prev;
-    prev.t = -1; prev.base = 0; prev.T_nl = 0; prev.wbase = 0; prev.tsh = 0;
-    for (int j = 0; j < CHUNKS; ++j) { prev.c[j] = 0; prev.pre[j] = 0; }
-    cur = prev;
-    const int roff = warp * REGION + lane * 16;
+    struct TileState { int64_t t, base; int T_nl; };
+    const int lbase = warp * REGION + lane * BPT;              // this thread's BPT contiguous bytes
+    const int rot = (lane / (8 / NCH)) % NCH;                  // chunk rotation: conflict-free LDS.128
 
-    // entries [b0, b0+LB) of tile S's newline list -> list slot q
-    auto write_entries = [&](const TileState &S, const uint8_t *tb, int q, int b0, int64_t *last) {
+    // ---- one line: list entry e (>= 2) of the tile in phase C ---------------------------------------
+    auto do_line = [&](const TileState &S, const uint8_t *tb, const Pref &pr, int e, int idx) {
+        const int64_t p = l_pos[e], pm1 = l_pos[e - 1], pm2 = l_pos[e - 2];
+        const uint32_t f1 = l_flag[e - 1], f2 = l_flag[e - 2];
+        const int64_t s = pm1 + 1;
+        const int64_t L = p - pm1;                            // len + 1
+        const int64_t lineidx = (int64_t)pr.ex_nl + idx;      // buffer-local line index
+        const int rp = (int)(p - S.base);                     // newline, tile relative (>= 0)
+        const bool near = (s - S.base) >= -(int64_t)HALO && (S.t > 0 || s >= S.base);   // line start inside smem window
+        const int rs = (int)(s - S.base);
+        if (MODE == 0) {
+            const bool is_hdr = (f1 >> 31) != 0;
+            const int64_t slot = (int64_t)pr.ex_hdr + (int64_t)(f1 & 0x7fffffffu);   // rec + 1
+            if (is_hdr) {
+                const uint8_t before = (rp >= 1 || S.t > 0) ? tb[rp - 1] : P.file[p - 1];
+                const int elen = (before == '\r') ? 2 : 1;
+                const int64_t dlen = L - 1 - elen;
+                int64_t nlen = dlen;
+                if (!full_name) {
+                    nlen = 0;
+                    if (near) {
+                        const uint8_t *h = tb + rs + 1;
+                        while (nlen < dlen) { const uint8_t ch = h[nlen]; if (ch == ' ' || ch == '\t') break; ++nlen; }
+                    } else {
+                        while (nlen < dlen) {
+                            const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + nlen);
+                            if (ch == ' ' || ch == '\t') break;
+                            ++nlen;
+                        }
+                    }
+                }
+                if (slot < P.tmp_cap) {
+                    FastaTmp *r = &P.tmp[slot];
+                    r->boff = P.base_offset + p + 1;
+                    r->lineidx = lineidx;
+                    r->dlen = (int32_t)dlen;
+                    r->nlen = (int32_t)nlen;
+                    r->elen = (uint32_t)elen;
+                }
+            } else if (slot < P.tmp_cap) {
+                const bool prev_exists = pm1 >= 0;
+                const bool prev_is_hdr = (f2 >> 31) != 0;
+                if (!prev_exists || prev_is_hdr) {
+                    P.tmp[slot].llen = L;
+                } else {
+                    const int64_t prevL = pm1 - pm2;
+                    if (L != prevL) {
+                        FastaTmp *r = &P.tmp[slot];
+                        atomicAdd(&r->D, 1u);
+                        atomicMax((unsigned long long *)&r->evmax, (unsigned long long)lineidx);
+                        atomicMax((unsigned long long *)&r->evminc, ~(unsigned long long)lineidx);
+                        atomicAdd((unsigned long long *)&r->S, (unsigned long long)(L - prevL));
+                    }
+                }
+            }
+        } else {
+            const int64_t gline = P.first_line + lineidx;
+            const int ph = (int)(gline & 3);
+            const int64_t row = (gline >> 2) - (P.first_line >> 2);
+            const int64_t len = L - 1;
+            if (ph == 1) {
+                const uint8_t before = (rp >= 1 || S.t > 0) ? tb[rp - 1] : (p >= 1 ? P.file[p - 1] : (uint8_t)0);
+                const int64_t rlen = (len > 0 && before == '\r') ? len - 1 : len;
+                my_size += (unsigned long long)rlen;
+                if (row < P.qrows_cap) { P.qrows[row].soff = P.base_offset + s; P.qrows[row].rlen = rlen; }
+            } else if (row < P.qrows_cap) {
+                if (ph == 0) {
+                    const uint8_t before = (rp >= 1 || S.t > 0) ? tb[rp - 1] : (p >= 1 ? P.file[p - 1] : (uint8_t)0);
+                    int64_t l = len - 1;
+                    if (l > 0 && before == '\r') --l;
+                    if (l < 0) l = 0;
+                    int64_t k = 0;
+                    if (near) {
+                        const uint8_t *h = tb + rs + 1;
+                        for (; k < l; ++k) { const uint8_t ch = h[k]; if (ch == 0) { k = l; break; } if (ch == ' ') break; }
+                    } else {
+                        for (; k < l; ++k) {
+                            const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + k);
+                            if (ch == 0) { k = l; break; }
+                            if (ch == ' ') break;
+                        }
+                    }
+                    *reinterpret_cast<int2 *>(&P.qrows[row].dlen) = make_int2((int)len, (int)k);
+                } else if (ph == 3) {
+                    P.qrows[row].qoff = P.base_offset + s;
+                }
+            }
+        }
+    };
+
+    // ---- phase C of a regular tile: compact the warp segments into the line list, then one
+    //      thread per line (two rounds when the tile has more than 256 lines) ------------------------
+    auto phase_c = [&](const TileState &S, const uint8_t *tb, const Slot &sl) {
+        // compaction: warp w copies its own segment to its tile-level position
+        uint32_t wb = 0;
 #pragma unroll
-        for (int j = 0; j < CHUNKS; ++j) {
-            uint32_t m = S.c[j];
-            if (!m) continue;
-            int idx = (int)((S.wbase + S.pre[j]) & 0xffffu);
-            uint32_t hc = S.tsh + ((S.wbase + S.pre[j]) >> 16);
+        for (int w = 0; w < NWARPS; ++w) if (w < warp) wb += sl.wcnt[w];
+        const int wn = (int)(sl.wcnt[warp] & 0xffffu), wb_nl = (int)(wb & 0xffffu);
+        const uint32_t wb_h = sl.mail.tsh + (wb >> 16);
+        for (int k = lane; k < wn; k += 32) {
+            const uint32_t f = sl.seg_flag[warp][k];
+            l_pos[2 + wb_nl + k] = S.base + sl.seg_pos[warp][k];
+            l_flag[2 + wb_nl + k] = ((f >> 15) << 31) | (wb_h + (f & 0x7fffu));
+        }
+        if (tid < 2) { l_pos[tid] = sl.pref.cpos[tid]; l_flag[tid] = sl.pref.cflag[tid]; }
+        worker_bar();
+        for (int idx = tid; idx < S.T_nl; idx += WORKERS) do_line(S, tb, sl.pref, 2 + idx, idx);
+    };
+
+    // ---- dense tile (more than LB lines, or a warp region with more than SEGCAP): rebuild the
+    //      newline list byte-wise in batches of LB lines; slow but fully general ----------------------
+    auto dense_tile = [&](const TileState &S, const uint8_t *tb, const Slot &sl, uint32_t my_cnt /* nl | h<<16 */) {
+        // exclusive block prefix of per-thread (newline, header) counts in thread order == file order
+        uint32_t incl = my_cnt;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {                     // increasing byte order: word, then byte
-                uint32_t mw = m & (0x80808080u >> w);
-                while (mw) {
-                    const int beta = __ffs(mw) - 1;
-                    mw &= mw - 1;
-                    const int x = roff + j * 512 + chunk_bit_to_off(beta);
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        worker_bar();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_scan[w];
+        const uint32_t excl = wb + incl - my_cnt;
+        for (int b0 = 0; b0 < S.T_nl; b0 += LB) {
+            worker_bar();                                   // previous batch fully consumed
+            int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
+            if (b0 > 0 && tid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
+            worker_bar();
+            if (tid == 0) {
+                if (b0 == 0) { l_pos[0] = sl.pref.cpos[0]; l_pos[1] = sl.pref.cpos[1]; l_flag[0] = sl.pref.cflag[0]; l_flag[1] = sl.pref.cflag[1]; }
+                else { l_pos[0] = c0; l_pos[1] = c1; l_flag[0] = g0; l_flag[1] = g1; }
+            }
+            int idx = (int)(excl & 0xffffu);
+            uint32_t hc = sl.mail.tsh + (excl >> 16);
+            if ((my_cnt & 0xffffu) && idx < b0 + LB && idx + (int)(my_cnt & 0xffffu) > b0) {
+                for (int b = 0; b < BPT; ++b) {
+                    const int x = lbase + b;
+                    if (tb[x] != '\n') continue;
                     uint32_t nh = 0;
-                    if (MODE == 0) {
-                        const int y = x + 1;
-                        nh = (y < TILE && S.base + y < n && tb[y] == '>') ? 1u : 0u;
-                        hc += nh;
-                    }
+                    if (MODE == 0) { nh = (x + 1 < TILE && S.base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
                     const int rel = idx - b0;
-                    if (rel >= 0 && rel < LB) {
-                        l_pos[q][2 + rel] = S.base + x;
-                        l_flag[q][2 + rel] = (nh << 31) | hc;
-                    }
-                    if (last) {
-                        if (idx == S.T_nl - 1) last[0] = S.base + x;
-                        if (idx == S.T_nl - 2) last[1] = S.base + x;
-                    }
+                    if (rel >= 0 && rel < LB) { l_pos[2 + rel] = S.base + x; l_flag[2 + rel] = (nh << 31) | hc; }
                     ++idx;
                 }
             }
+            worker_bar();
+            const int nb = S.T_nl - b0 < LB ? S.T_nl - b0 : LB;
+            for (int i = tid; i < nb; i += WORKERS) do_line(S, tb, sl.pref, 2 + i, b0 + i);
         }
-    };
-
-    // ---- phase C of tile S (its list for batch 0 is already in slot q) ---------------------------
-    auto phase_c = [&](const TileState &S, const uint8_t *tb, int q) {
-        const uint64_t ex_nl = s_pref[q].ex_nl, ex_hdr = s_pref[q].ex_hdr;
-        for (int b0 = 0; b0 < S.T_nl; b0 += LB) {
-            if (b0 > 0) {
-                worker_bar();
-                int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
-                if (tid == 0) { c0 = l_pos[q][LB]; c1 = l_pos[q][LB + 1]; g0 = l_flag[q][LB]; g1 = l_flag[q][LB + 1]; }
-                worker_bar();
-                if (tid == 0) { l_pos[q][0] = c0; l_pos[q][1] = c1; l_flag[q][0] = g0; l_flag[q][1] = g1; }
-                write_entries(S, tb, q, b0, nullptr);
-                worker_bar();
-            }
-            const int idx = b0 + tid;
-            if (idx < S.T_nl) {
-                const int e = 2 + tid;
-                const int64_t p = l_pos[q][e], pm1 = l_pos[q][e - 1], pm2 = l_pos[q][e - 2];
-                const uint32_t f1 = l_flag[q][e - 1], f2 = l_flag[q][e - 2];
-                const int64_t s = pm1 + 1;
-                const int64_t L = p - pm1;                         // len + 1
-                const int64_t lineidx = (int64_t)ex_nl + idx;      // buffer-local line index
-                if (MODE == 0) {
-                    const bool is_hdr = (f1 >> 31) != 0;
-                    const int64_t slot = (int64_t)ex_hdr + (int64_t)(f1 & 0x7fffffffu);   // rec + 1
-                    if (is_hdr) {
-                        const int elen = (byte_at(tb, S.t, S.base, p - 1) == '\r') ? 2 : 1;
-                        const int64_t dlen = L - 1 - elen;
-                        int64_t nlen = dlen;
-                        if (!full_name) {
-                            nlen = 0;
-                            while (nlen < dlen) {
-                                const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + nlen);
-                                if (ch == ' ' || ch == '\t') break;
-                                ++nlen;
-                            }
-                        }
-                        if (slot < P.tmp_cap) {
-                            FastaTmp *r = &P.tmp[slot];
-                            r->boff = P.base_offset + p + 1;
-                            r->lineidx = lineidx;
-                            r->dlen = (int32_t)dlen;
-                            r->nlen = (int32_t)nlen;
-                            r->elen = (uint32_t)elen;
-                        }
-                    } else if (slot < P.tmp_cap) {
-                        FastaTmp *r = &P.tmp[slot];
-                        const bool prev_exists = pm1 >= 0;
-                        const bool prev_is_hdr = (f2 >> 31) != 0;
-                        if (!prev_exists || prev_is_hdr) {
-                            r->llen = L;
-                        } else {
-                            const int64_t prevL = pm1 - pm2;
-                            if (L != prevL) {
-                                atomicAdd(&r->D, 1u);
-                                atomicMax((unsigned long long *)&r->evmax, (unsigned long long)lineidx);
-                                atomicMax((unsigned long long *)&r->evminc, ~(unsigned long long)lineidx);
-                                atomicAdd((unsigned long long *)&r->S, (unsigned long long)(L - prevL));
-                            }
-                        }
-                    }
-                } else {
-                    const int64_t gline = P.first_line + lineidx;
-                    const int ph = (int)(gline & 3);
-                    const int64_t row = (gline >> 2) - (P.first_line >> 2);
-                    const int64_t len = L - 1;
-                    if (ph == 1) {
-                        const int64_t rlen = (len > 0 && byte_at(tb, S.t, S.base, p - 1) == '\r') ? len - 1 : len;
-                        my_size += (unsigned long long)rlen;
-                        if (row < P.qrows_cap) { P.qrows[row].soff = P.base_offset + s; P.qrows[row].rlen = rlen; }
-                    } else if (row < P.qrows_cap) {
-                        fxg_fastq_row *r = &P.qrows[row];
-                        if (ph == 0) {
-                            int64_t l = len - 1;
-                            if (l > 0 && byte_at(tb, S.t, S.base, p - 1) == '\r') --l;
-                            if (l < 0) l = 0;
-                            int64_t k = 0;
-                            for (; k < l; ++k) {
-                                const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + k);
-                                if (ch == 0) { k = l; break; }
-                                if (ch == ' ') break;
-                            }
-                            r->dlen = (int32_t)len;
-                            r->nlen = (int32_t)k;
-                        } else if (ph == 3) {
-                            r->qoff = P.base_offset + s;
-                        }
-                    }
-                }
-            }
-        }
+        worker_bar();   // the line list is shared with phase C of the pending tile
     };
 
     if (tid == 0) issue(0);
-    __shared__ int64_t s_lastpos[2];
 
+    TileState pend[LAG];
+    for (int i = 0; i < LAG; ++i) { pend[i].t = -1; pend[i].base = 0; pend[i].T_nl = 0; }
+    bool draining = false;
     for (int it = 0;; ++it) {
-        const int st = it % STAGES, q = it & 1;
-        mbar_wait(&full_bar[st], (uint32_t)((it / STAGES) & 1));
-        const int64_t t = s_tile[st];
+        const int st = it % STAGES, q = it % NSLOT;
+        int64_t t = P.ntiles;
+        const long long tw0 = clock64();
+        if (!draining) {
+            mbar_wait(&full_bar[st], (uint32_t)((it / STAGES) & 1));
+            t = s_tile[st];
+        }
+        const long long tw1 = clock64();
+        if (P.dbg && tid == 0) atomicAdd(&P.dbg[0], (unsigned long long)(tw1 - tw0));
         const bool have = t < P.ntiles;
         uint8_t *tb = stage_ptr(it);
+        Slot &sl = slots[q];
+        TileState cur;
+        cur.t = -1; cur.base = 0; cur.T_nl = 0;
         if (have) {
-            // claim + prefetch the next tile: stage (it+1)%3 held tile it-2, whose phase C ended
-            // (worker barrier) in iteration it-1
+            // claim + prefetch the next tile: stage (it+1)%STAGES held tile it-LAG-1, whose phase C
+            // ended (worker barrier) in iteration it-1
             if (tid == 0) issue((it + 1) % STAGES);
             const int64_t base = t * TILE;
             // the tile that contains EOF: neutralise bytes past n, plant the virtual newline
@@ -437,79 +484,188 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                     if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
                 worker_bar();
             }
-            // ---------------- phase A: newline masks, ordered indices -----------------------------
-            cur.t = t; cur.base = base;
-            uint32_t run = 0;
+            // ---------------- phase A ------------------------------------------------------------------
+            // each thread owns 64 contiguous bytes (4 x LDS.128 in a lane-rotated chunk order, so the
+            // loads are bank-conflict free); lines are normally longer than that, so a thread holds at
+            // most one newline and ONE ballot ranks all newlines of the warp's 2 KiB region.
+            uint4 v[NCH];
 #pragma unroll
-            for (int j = 0; j < CHUNKS; ++j) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(tb + roff + j * 512);
-                cur.c[j] = chunk_eq_mask(v, 0x0a0a0a0au);
-                const uint32_t cnt = __popc(cur.c[j]);
+            for (int j = 0; j < NCH; ++j) v[j] = *reinterpret_cast<const uint4 *>(tb + lbase + 16 * ((j + rot) % NCH));
+            uint32_t m[NCH];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) { m[j] = chunk_eq_mask(v[j], 0x0a0a0a0au); cnt += __popc(m[j]); }
+            uint32_t my_cnt;      // newlines | header starts << 16 of this thread
+            uint32_t run;         // same, whole warp
+            if (!__any_sync(0xffffffffu, cnt > 1)) {
+                int x = 0;
+                uint32_t nh = 0;
+                if (cnt) {
+                    int j = 0;
+                    uint32_t mm = 0;
+#pragma unroll
+                    for (int jj = NCH - 1; jj >= 0; --jj) if (m[jj]) { j = jj; mm = m[jj]; }
+                    x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
+                    if (MODE == 0) nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u;
+                }
+                const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
+                const uint32_t bh = (MODE == 0) ? __ballot_sync(0xffffffffu, nh != 0) : 0u;
+                if (cnt) {
+                    const int wi = __popc(bn & lt_mask);
+                    sl.seg_pos[warp][wi] = (uint16_t)x;
+                    sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | (__popc(bh & lt_mask) + nh));
+                }
+                my_cnt = cnt | (nh << 16);
+                run = __popc(bn) | (__popc(bh) << 16);
+            } else if (!__any_sync(0xffffffffu, cnt > 2)) {
+                // at most two newlines per thread (e.g. a header line inside the 64 bytes): two ballots
+                int xa = 0x7fffffff, xb = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    if (m[j]) {
+                        const int qoff = lbase + 16 * ((j + rot) % NCH);
+                        const int x1 = qoff + chunk_bit_to_off(__ffs(m[j]) - 1);
+                        if (x1 < xa) { xb = xa; xa = x1; } else if (x1 < xb) xb = x1;
+                        const uint32_t m2 = m[j] & (m[j] - 1);
+                        if (m2) {
+                            const int x2 = qoff + chunk_bit_to_off(__ffs(m2) - 1);
+                            if (x2 < xa) { xb = xa; xa = x2; } else if (x2 < xb) xb = x2;
+                        }
+                    }
+                }
+                uint32_t nha = 0, nhb = 0;
+                if (MODE == 0) {
+                    if (cnt >= 1) nha = (xa + 1 < TILE && base + xa + 1 < n && tb[xa + 1] == '>') ? 1u : 0u;
+                    if (cnt >= 2) nhb = (xb + 1 < TILE && base + xb + 1 < n && tb[xb + 1] == '>') ? 1u : 0u;
+                }
+                const uint32_t bn1 = __ballot_sync(0xffffffffu, cnt >= 1), bn2 = __ballot_sync(0xffffffffu, cnt >= 2);
+                const uint32_t bh1 = (MODE == 0) ? __ballot_sync(0xffffffffu, nha != 0) : 0u;
+                const uint32_t bh2 = (MODE == 0) ? __ballot_sync(0xffffffffu, nhb != 0) : 0u;
+                const int wi = __popc(bn1 & lt_mask) + __popc(bn2 & lt_mask);
+                const uint32_t hcb = __popc(bh1 & lt_mask) + __popc(bh2 & lt_mask);
+                if (cnt >= 1) { sl.seg_pos[warp][wi] = (uint16_t)xa; sl.seg_flag[warp][wi] = (uint16_t)((nha << 15) | (hcb + nha)); }
+                if (cnt >= 2) { sl.seg_pos[warp][wi + 1] = (uint16_t)xb; sl.seg_flag[warp][wi + 1] = (uint16_t)((nhb << 15) | (hcb + nha + nhb)); }
+                my_cnt = cnt | ((nha + nhb) << 16);
+                run = (__popc(bn1) + __popc(bn2)) | ((__popc(bh1) + __popc(bh2)) << 16);
+            } else {
+                // short lines (three or more newlines in some thread's 64 bytes): shuffle scan + ordered
+                // iteration over the masks
                 uint32_t h = 0;
-                if (MODE == 0 && cnt) {
-                    uint32_t m = cur.c[j];
-                    while (m) {
-                        const int beta = __ffs(m) - 1;
-                        m &= m - 1;
-                        const int x = roff + j * 512 + chunk_bit_to_off(beta) + 1;   // next line start
-                        if (x < TILE && base + x < n && tb[x] == '>') ++h;
-                    }
-                }
-                uint32_t excl, tot;
-                if (!__any_sync(0xffffffffu, cnt > 1)) {
-                    const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
-                    const uint32_t bh = __ballot_sync(0xffffffffu, h != 0);
-                    excl = __popc(bn & lt_mask) | (__popc(bh & lt_mask) << 16);
-                    tot = __popc(bn) | (__popc(bh) << 16);
-                } else {
-                    const uint32_t packed = cnt | (h << 16);
-                    uint32_t incl = packed;
+                if (MODE == 0) {
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += o;
+                    for (int j = 0; j < NCH; ++j) {
+                        uint32_t mm = m[j];
+                        while (mm) {
+                            const int x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
+                            mm &= mm - 1;
+                            if (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ++h;
+                        }
                     }
-                    excl = incl - packed;
-                    tot = __shfl_sync(0xffffffffu, incl, 31);
                 }
-                cur.pre[j] = run + excl;
-                run += tot;
+                my_cnt = cnt | (h << 16);
+                uint32_t incl = my_cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                run = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t wi = (incl - my_cnt) & 0xffffu, hc = (incl - my_cnt) >> 16;
+                if (cnt && (run & 0xffffu) <= (uint32_t)SEGCAP) {
+#pragma unroll 1
+                    for (int qc = 0; qc < NCH; ++qc) {
+                        const int j = (qc - rot + NCH) % NCH;
+                        uint32_t mq = 0;
+#pragma unroll
+                        for (int jj = 0; jj < NCH; ++jj) if (jj == j) mq = m[jj];
+#pragma unroll 1
+                        for (int w = 0; w < 4; ++w) {                 // byte order: word, then byte
+                            uint32_t mw = mq & (0x80808080u >> w);
+                            while (mw) {
+                                const int x = lbase + 16 * qc + chunk_bit_to_off(__ffs(mw) - 1);
+                                mw &= mw - 1;
+                                uint32_t nh = 0;
+                                if (MODE == 0) { nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
+                                sl.seg_pos[warp][wi] = (uint16_t)x;
+                                sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | hc);
+                                ++wi;
+                            }
+                        }
+                    }
+                }
             }
-            if (lane == 0) s_wtot[warp] = run;
-            worker_bar();   // (1)
-            uint32_t wbase = 0, ttot = 0;
+            if (lane == 0) sl.wcnt[warp] = run;
+            worker_bar();   // (1) segments + per-warp counts visible
+            uint32_t ttot = 0;
+            bool dense = false;
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) {
-                const uint32_t v = s_wtot[w];
-                if (w < warp) wbase += v;
-                ttot += v;
+                const uint32_t c = sl.wcnt[w];
+                dense |= (c & 0xffffu) > (uint32_t)SEGCAP;
+                ttot += c;
             }
-            cur.wbase = wbase;
+            cur.t = t; cur.base = base;
             cur.T_nl = (int)(ttot & 0xffffu);
-            const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
-            cur.tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
-            const uint32_t T_h = (ttot >> 16) + cur.tsh;
-            write_entries(cur, tb, q, 0, s_lastpos);
-            worker_bar();   // (2) entries + last positions visible
+            dense |= cur.T_nl > LB;
             if (tid == 0) {
-                s_mail[q].t = t; s_mail[q].T_nl = (uint32_t)cur.T_nl; s_mail[q].T_h = T_h; s_mail[q].tsh = cur.tsh;
-                s_mail[q].last0 = s_lastpos[0]; s_mail[q].last1 = s_lastpos[1];
+                const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
+                const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
+                const uint32_t T_h = (ttot >> 16) + tsh;
+                // the tile's last two newline positions
+                int64_t l0 = NOPOS, l1 = NOPOS;
+                if (!dense) {
+                    int found = 0;
+                    for (int w = NWARPS - 1; w >= 0 && found < 2; --w) {
+                        const int c = (int)(sl.wcnt[w] & 0xffffu);
+                        for (int k = c - 1; k >= 0 && found < 2; --k) {
+                            const int64_t pp = base + sl.seg_pos[w][k];
+                            if (found == 0) l0 = pp; else l1 = pp;
+                            ++found;
+                        }
+                    }
+                } else {
+                    int found = 0;
+                    for (int x = TILE - 1; x >= 0 && found < 2; --x)
+                        if (tb[x] == '\n') { if (found == 0) l0 = base + x; else l1 = base + x; ++found; }
+                }
+                // publish the tile aggregate NOW (not from the prefix warp, whose look-backs are
+                // sequential): every tile becomes visible a fixed, short time after it was claimed
+                st_desc(&P.cnt[t], ST_AGG | (uint64_t)cur.T_nl, ST_AGG | (uint64_t)T_h);
+                st_desc(&P.pos[t], cur.T_nl >= 1 ? (uint64_t)(l0 + 2) : 1ull, cur.T_nl >= 2 ? (uint64_t)(l1 + 2) : 1ull);
+                sl.mail.t = t; sl.mail.tsh = tsh;
                 mbar_arrive(&mail_bar[q]);
             }
+            if (dense) {
+                // not pipelined: wait for our own prefix and finish the tile now
+                mbar_wait(&pref_bar[q], (uint32_t)((it / NSLOT) & 1));
+                dense_tile(cur, tb, sl, my_cnt);
+                cur.t = -1;   // nothing pending
+            }
         }
-        if (!have && tid == 0) {          // no more tiles: release the prefix warp
-            s_mail[q].t = -1;
+        if (!have && !draining && tid == 0) {   // no more tiles: release the prefix warp
+            sl.mail.t = -1;
             mbar_arrive(&mail_bar[q]);
         }
-        // ---------------- phase C of the previous tile (its look-back ran during our phase A) ------
-        if (it > 0 && prev.t >= 0) {
-            const int pq = q ^ 1;
-            mbar_wait(&pref_bar[pq], (uint32_t)(((it - 1) >> 1) & 1));
-            phase_c(prev, stage_ptr(it - 1), pq);
+        if (!have) draining = true;
+        const long long tw2 = clock64();
+        if (P.dbg && tid == 0) atomicAdd(&P.dbg[1], (unsigned long long)(tw2 - tw1));
+        // ---------------- phase C of tile it-LAG (its look-back had LAG iterations to finish) --------
+        if (pend[0].t >= 0) {
+            const int pit = it - LAG, pq = pit % NSLOT;
+            mbar_wait(&pref_bar[pq], (uint32_t)((pit / NSLOT) & 1));
+            const long long tw3 = clock64();
+            if (P.dbg && tid == 0) atomicAdd(&P.dbg[2], (unsigned long long)(tw3 - tw2));
+            phase_c(pend[0], stage_ptr(pit), slots[pq]);
+            if (P.dbg && tid == 0) atomicAdd(&P.dbg[3], (unsigned long long)(clock64() - tw3));
         }
-        worker_bar();   // (3) stage it-1 and list slot q^1 are free again
-        if (!have) break;
-        prev = cur;
+        worker_bar();   // (3) stage, slot and line list are free again
+#pragma unroll
+        for (int i = 0; i + 1 < LAG; ++i) pend[i] = pend[i + 1];
+        pend[LAG - 1] = cur;
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < LAG; ++i) any |= pend[i].t >= 0;
+        if (draining && !any) break;
     }
     if (MODE == 1) {
 #pragma unroll
@@ -683,6 +839,8 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
         P.totals = (ScanTotals *)((uint8_t *)ctx->counters.ptr + 64);
         P.tmp = (FastaTmp *)ctx->row_tmp.ptr; P.tmp_cap = cap + 1;
         P.qrows = (fxg_fastq_row *)ctx->rows.ptr; P.qrows_cap = cap;
+        const bool dbg = getenv("FXG_SCAN_DEBUG") != nullptr;
+        P.dbg = dbg ? (unsigned long long *)((uint8_t *)ctx->counters.ptr + 128) : nullptr;
 
         {
             FxgProfScope prof(ctx, FXG_PROF_SCAN);
@@ -695,6 +853,13 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
         FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
         FXG_CUDA(cudaStreamSynchronize(ctx->stream));
 
+        if (dbg) {
+            unsigned long long h[8];
+            cudaMemcpy(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[fxg scan dbg] grid=%d tiles=%lld | worker cycles/tile: wait_data=%.0f phaseA=%.0f wait_pref=%.0f phaseC=%.0f | prefix warp: lookback=%.0f cyc/tile, windows=%.2f/tile, wait_mail=%.0f\n",
+                    grid, (long long)ntiles, (double)h[0] / ntiles, (double)h[1] / ntiles, (double)h[2] / ntiles, (double)h[3] / ntiles,
+                    (double)h[4] / (h[6] ? h[6] : 1), (double)h[5] / (h[6] ? h[6] : 1), (double)h[7] / (h[6] ? h[6] : 1));
+        }
         const int64_t nrows = mode == 0 ? (int64_t)tot.hdr
                                         : (int64_t)((first_line + (int64_t)tot.nl + 3) / 4 - first_line / 4);
         if (nrows > cap) { cap = nrows + 16; continue; }   // estimate too small: exact rerun
