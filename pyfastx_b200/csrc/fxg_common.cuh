@@ -122,7 +122,16 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// 0x80 in every byte of w that equals `c` (c < 0x80).  Exact, 3 ALU ops.
+// 0x80 in every byte of w that equals `c` (c < 0x80).  Exact, 3 ALU ops when the constants
+// live in registers (one LOP3 per boolean step):
+//   u = (w ^ c4) & 0x7f7f7f7f ; t = u + 0x7f7f7f7f ; r = ~(t | w) & 0x80808080
+__device__ __forceinline__ uint32_t byte_eq_mask_r(uint32_t w, uint32_t c4, uint32_t k7f, uint32_t k80) {
+    uint32_t u, r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(u) : "r"(w), "r"(c4), "r"(k7f));   // (a ^ b) & c
+    const uint32_t t = u + k7f;
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(r) : "r"(t), "r"(w), "r"(k80));    // ~(a | b) & c
+    return r;
+}
 __device__ __forceinline__ uint32_t byte_eq_mask(uint32_t w, uint32_t c4) {
     uint32_t u = (w ^ c4) & 0x7f7f7f7fu;
     uint32_t t = u + 0x7f7f7f7fu;
@@ -132,6 +141,17 @@ __device__ __forceinline__ uint32_t byte_eq_mask(uint32_t w, uint32_t c4) {
 __device__ __forceinline__ uint32_t chunk_eq_mask(const uint4 &v, uint32_t c4) {
     return byte_eq_mask(v.x, c4) | (byte_eq_mask(v.y, c4) >> 1) | (byte_eq_mask(v.z, c4) >> 2) |
            (byte_eq_mask(v.w, c4) >> 3);
+}
+// same with the three constants held in registers by the caller (hot loops)
+__device__ __forceinline__ uint32_t chunk_eq_mask_r(const uint4 &v, uint32_t c4, uint32_t k7f, uint32_t k80) {
+    return byte_eq_mask_r(v.x, c4, k7f, k80) | (byte_eq_mask_r(v.y, c4, k7f, k80) >> 1) |
+           (byte_eq_mask_r(v.z, c4, k7f, k80) >> 2) | (byte_eq_mask_r(v.w, c4, k7f, k80) >> 3);
+}
+// keeps a constant in a register (defeats immediate folding)
+__device__ __forceinline__ uint32_t reg_const(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 // byte offset (0..15) of combined-mask bit beta
 __device__ __forceinline__ int chunk_bit_to_off(int beta) { return ((7 - (beta & 7)) << 2) + (beta >> 3); }

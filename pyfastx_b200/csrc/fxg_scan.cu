@@ -28,6 +28,12 @@
 
 namespace fxg {
 
+#ifdef FXG_SCAN_PROFILE
+#define FXG_DBG(x) x
+#else
+#define FXG_DBG(x)
+#endif
+
 constexpr int TILE    = 16384;          // bytes per tile
 constexpr int HALO    = 256;            // left halo kept in smem (previous line starts)
 constexpr int LAG     = 2;          // phase C of tile i-LAG runs after phase A of tile i
@@ -39,8 +45,10 @@ constexpr int REGION  = TILE / NWARPS;  // contiguous bytes per warp (2048)
 constexpr int BPT     = TILE / THREADS; // contiguous bytes per worker thread (32)
 constexpr int NCH     = BPT / 16;       // 16-byte chunks per thread (2)
 constexpr int LB      = 512;            // line-list capacity of a regular tile (lines >= 32 B on average)
-constexpr int SEGCAP  = 64;             // per-warp entry segment (2 KiB region: lines >= 21 B on average)
+constexpr int SEGCAP  = 32;             // per-warp entry segment (2 KiB region: lines >= 21 B on average)
 constexpr int STAGE_BYTES = HALO + TILE;
+static_assert(SEGCAP * (THREADS / 32) <= LB, "a tile without segment overflow must fit the line list");
+
 constexpr int64_t NOPOS = INT64_MIN / 4;
 
 // ---- decoupled look-back state ---------------------------------------------------------------
@@ -186,11 +194,19 @@ struct Slot {           // everything phase C needs about a tile whose phase A h
     uint16_t seg_pos[NWARPS][SEGCAP];    // per-warp newline positions (tile relative), file order
     uint16_t seg_flag[NWARPS][SEGCAP];   // bit15: next line starts with '>', low bits: warp-local inclusive header count
     uint32_t wcnt[NWARPS];               // per warp: newlines | header starts << 16
+    uint32_t wstart[NWARPS];             // exclusive prefix of wcnt (filled by warp 0 in phase A)
+    int      T_nl, pad0;                 // newlines in the tile
     Mail     mail;
     Pref     pref;
 };
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
+// worker barrier that also ORs a predicate over all workers (bar.red)
+__device__ __forceinline__ bool worker_bar_or(bool p) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.or.pred q, 1, %2, p;\n\tselp.b32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"((int)p), "n"(WORKERS) : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -233,20 +249,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
     // prefix warp: decoupled look-back for one tile after the other
     // =========================================================================================
     if (warp == NWARPS) {
+        int q = 0;
+        uint32_t qpar = 0;
         for (int it = 0;; ++it) {
-            const int q = it % NSLOT;
-            const long long tm0 = clock64();
-            mbar_wait(&mail_bar[q], (uint32_t)((it / NSLOT) & 1));
-            if (P.dbg && lane == 0) atomicAdd(&P.dbg[7], (unsigned long long)(clock64() - tm0));
+            FXG_DBG(const long long tm0 = clock64();)
+            mbar_wait(&mail_bar[q], qpar);
+            FXG_DBG(if (P.dbg && lane == 0) atomicAdd(&P.dbg[7], (unsigned long long)(clock64() - tm0));)
             const Mail m = slots[q].mail;
             if (m.t < 0) break;
             const int64_t t = m.t, base = t * TILE;
             const uint8_t *tb = stage_ptr(it);
             uint64_t ex_nl = 0, ex_hdr = 0;
             int nwin = 0;
-            const long long tl0 = clock64();
+            FXG_DBG(const long long tl0 = clock64();)
             lookback_counts(P.cnt, t, lane, ex_nl, ex_hdr, nwin);
-            if (P.dbg && lane == 0) { atomicAdd(&P.dbg[4], (unsigned long long)(clock64() - tl0)); atomicAdd(&P.dbg[5], (unsigned long long)nwin); atomicAdd(&P.dbg[6], 1ull); }
+            FXG_DBG(if (P.dbg && lane == 0) { atomicAdd(&P.dbg[4], (unsigned long long)(clock64() - tl0)); atomicAdd(&P.dbg[5], (unsigned long long)nwin); atomicAdd(&P.dbg[6], 1ull); })
             if (lane == 0) {
                 const ulonglong2 own = ld_desc(&P.cnt[t]);
                 const uint64_t in_nl = ex_nl + (own.x & ~ST_MASK), in_hdr = ex_hdr + (own.y & ~ST_MASK);
@@ -267,6 +284,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                 mbar_arrive(&pref_bar[q]);
             }
             __syncwarp();
+            if (++q == NSLOT) { q = 0; qpar ^= 1u; }
         }
         return;
     }
@@ -296,7 +314,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
         mbar_arrive(&full_bar[st]);
     };
 
-    struct TileState { int64_t t, base; int T_nl; };
+    struct TileState { int64_t t, base; };
     const int lbase = warp * REGION + lane * BPT;              // this thread's BPT contiguous bytes
     const int rot = (lane / (8 / NCH)) % NCH;                  // chunk rotation: conflict-free LDS.128
 
@@ -394,9 +412,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
     //      thread per line (two rounds when the tile has more than 256 lines) ------------------------
     auto phase_c = [&](const TileState &S, const uint8_t *tb, const Slot &sl) {
         // compaction: warp w copies its own segment to its tile-level position
-        uint32_t wb = 0;
-#pragma unroll
-        for (int w = 0; w < NWARPS; ++w) if (w < warp) wb += sl.wcnt[w];
+        const uint32_t wb = sl.wstart[warp];
         const int wn = (int)(sl.wcnt[warp] & 0xffffu), wb_nl = (int)(wb & 0xffffu);
         const uint32_t wb_h = sl.mail.tsh + (wb >> 16);
         for (int k = lane; k < wn; k += 32) {
@@ -406,7 +422,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
         }
         if (tid < 2) { l_pos[tid] = sl.pref.cpos[tid]; l_flag[tid] = sl.pref.cflag[tid]; }
         worker_bar();
-        for (int idx = tid; idx < S.T_nl; idx += WORKERS) do_line(S, tb, sl.pref, 2 + idx, idx);
+        const int T_nl = sl.T_nl;
+        for (int idx = tid; idx < T_nl; idx += WORKERS) do_line(S, tb, sl.pref, 2 + idx, idx);
     };
 
     // ---- dense tile (more than LB lines, or a warp region with more than SEGCAP): rebuild the
@@ -424,7 +441,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
         uint32_t wb = 0;
         for (int w = 0; w < warp; ++w) wb += s_scan[w];
         const uint32_t excl = wb + incl - my_cnt;
-        for (int b0 = 0; b0 < S.T_nl; b0 += LB) {
+        const int T_nl = sl.T_nl;
+        for (int b0 = 0; b0 < T_nl; b0 += LB) {
             worker_bar();                                   // previous batch fully consumed
             int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
             if (b0 > 0 && tid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
@@ -447,7 +465,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                 }
             }
             worker_bar();
-            const int nb = S.T_nl - b0 < LB ? S.T_nl - b0 : LB;
+            const int nb = T_nl - b0 < LB ? T_nl - b0 : LB;
             for (int i = tid; i < nb; i += WORKERS) do_line(S, tb, sl.pref, 2 + i, b0 + i);
         }
         worker_bar();   // the line list is shared with phase C of the pending tile
@@ -455,28 +473,31 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
 
     if (tid == 0) issue(0);
 
+    static_assert(STAGES == 4, "stage ring indexing assumes 4 stages");
+    const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
     TileState pend[LAG];
-    for (int i = 0; i < LAG; ++i) { pend[i].t = -1; pend[i].base = 0; pend[i].T_nl = 0; }
+    for (int i = 0; i < LAG; ++i) { pend[i].t = -1; pend[i].base = 0; }
     bool draining = false;
+    int q = 0, pq = 0;                 // slot of the tile in phase A / of the tile in phase C
+    uint32_t qpar = 0, pqpar = 0;
     for (int it = 0;; ++it) {
-        const int st = it % STAGES, q = it % NSLOT;
+        const int st = it & (STAGES - 1);
         int64_t t = P.ntiles;
-        const long long tw0 = clock64();
+        FXG_DBG(const long long tw0 = clock64();)
         if (!draining) {
-            mbar_wait(&full_bar[st], (uint32_t)((it / STAGES) & 1));
+            mbar_wait(&full_bar[st], (uint32_t)((it >> 2) & 1));
             t = s_tile[st];
         }
-        const long long tw1 = clock64();
-        if (P.dbg && tid == 0) atomicAdd(&P.dbg[0], (unsigned long long)(tw1 - tw0));
+        FXG_DBG(const long long tw1 = clock64(); if (P.dbg && tid == 0) atomicAdd(&P.dbg[0], (unsigned long long)(tw1 - tw0));)
         const bool have = t < P.ntiles;
         uint8_t *tb = stage_ptr(it);
         Slot &sl = slots[q];
         TileState cur;
-        cur.t = -1; cur.base = 0; cur.T_nl = 0;
+        cur.t = -1; cur.base = 0;
         if (have) {
             // claim + prefetch the next tile: stage (it+1)%STAGES held tile it-LAG-1, whose phase C
             // ended (worker barrier) in iteration it-1
-            if (tid == 0) issue((it + 1) % STAGES);
+            if (tid == 0) issue((it + 1) & (STAGES - 1));
             const int64_t base = t * TILE;
             // the tile that contains EOF: neutralise bytes past n, plant the virtual newline
             if (base + TILE > n) {
@@ -494,7 +515,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
             uint32_t m[NCH];
             uint32_t cnt = 0;
 #pragma unroll
-            for (int j = 0; j < NCH; ++j) { m[j] = chunk_eq_mask(v[j], 0x0a0a0a0au); cnt += __popc(m[j]); }
+            for (int j = 0; j < NCH; ++j) { m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80); cnt += __popc(m[j]); }
             uint32_t my_cnt;      // newlines | header starts << 16 of this thread
             uint32_t run;         // same, whole warp
             if (!__any_sync(0xffffffffu, cnt > 1)) {
@@ -595,49 +616,54 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                 }
             }
             if (lane == 0) sl.wcnt[warp] = run;
-            worker_bar();   // (1) segments + per-warp counts visible
-            uint32_t ttot = 0;
-            bool dense = false;
-#pragma unroll
-            for (int w = 0; w < NWARPS; ++w) {
-                const uint32_t c = sl.wcnt[w];
-                dense |= (c & 0xffffu) > (uint32_t)SEGCAP;
-                ttot += c;
-            }
+            // (1) segments + per-warp counts visible; OR-reduce "some warp overflowed its segment".
+            // SEGCAP * NWARPS == LB, so a tile without overflow always fits the line list.
+            const bool dense = worker_bar_or((run & 0xffffu) > (uint32_t)SEGCAP);
             cur.t = t; cur.base = base;
-            cur.T_nl = (int)(ttot & 0xffffu);
-            dense |= cur.T_nl > LB;
-            if (tid == 0) {
-                const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
-                const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
-                const uint32_t T_h = (ttot >> 16) + tsh;
-                // the tile's last two newline positions
-                int64_t l0 = NOPOS, l1 = NOPOS;
-                if (!dense) {
-                    int found = 0;
-                    for (int w = NWARPS - 1; w >= 0 && found < 2; --w) {
-                        const int c = (int)(sl.wcnt[w] & 0xffffu);
-                        for (int k = c - 1; k >= 0 && found < 2; --k) {
-                            const int64_t pp = base + sl.seg_pos[w][k];
-                            if (found == 0) l0 = pp; else l1 = pp;
-                            ++found;
-                        }
-                    }
-                } else {
-                    int found = 0;
-                    for (int x = TILE - 1; x >= 0 && found < 2; --x)
-                        if (tb[x] == '\n') { if (found == 0) l0 = base + x; else l1 = base + x; ++found; }
+            if (warp == 0) {
+                // warp 0: prefix over the per-warp counts, tile totals, last two newline positions, publish
+                const uint32_t c = lane < NWARPS ? sl.wcnt[lane] : 0u;
+                uint32_t incl = c;
+#pragma unroll
+                for (int d = 1; d < NWARPS; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
                 }
-                // publish the tile aggregate NOW (not from the prefix warp, whose look-backs are
-                // sequential): every tile becomes visible a fixed, short time after it was claimed
-                st_desc(&P.cnt[t], ST_AGG | (uint64_t)cur.T_nl, ST_AGG | (uint64_t)T_h);
-                st_desc(&P.pos[t], cur.T_nl >= 1 ? (uint64_t)(l0 + 2) : 1ull, cur.T_nl >= 2 ? (uint64_t)(l1 + 2) : 1ull);
-                sl.mail.t = t; sl.mail.tsh = tsh;
-                mbar_arrive(&mail_bar[q]);
+                if (lane < NWARPS) sl.wstart[lane] = incl - c;
+                const uint32_t ttot = __shfl_sync(0xffffffffu, incl, NWARPS - 1);
+                const int T_nl = (int)(ttot & 0xffffu);
+                if (lane == 0) {
+                    const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
+                    const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
+                    const uint32_t T_h = (ttot >> 16) + tsh;
+                    int64_t l0 = NOPOS, l1 = NOPOS;
+                    if (!dense) {
+                        int found = 0;
+                        for (int w = NWARPS - 1; w >= 0 && found < 2; --w) {
+                            const int cw = (int)(sl.wcnt[w] & 0xffffu);
+                            for (int k = cw - 1; k >= 0 && found < 2; --k) {
+                                const int64_t pp = base + sl.seg_pos[w][k];
+                                if (found == 0) l0 = pp; else l1 = pp;
+                                ++found;
+                            }
+                        }
+                    } else {
+                        int found = 0;
+                        for (int x = TILE - 1; x >= 0 && found < 2; --x)
+                            if (tb[x] == '\n') { if (found == 0) l0 = base + x; else l1 = base + x; ++found; }
+                    }
+                    // publish the tile aggregate NOW (not from the prefix warp, whose look-backs are
+                    // sequential): every tile becomes visible a fixed, short time after it was claimed
+                    st_desc(&P.cnt[t], ST_AGG | (uint64_t)T_nl, ST_AGG | (uint64_t)T_h);
+                    st_desc(&P.pos[t], T_nl >= 1 ? (uint64_t)(l0 + 2) : 1ull, T_nl >= 2 ? (uint64_t)(l1 + 2) : 1ull);
+                    sl.T_nl = T_nl;
+                    sl.mail.t = t; sl.mail.tsh = tsh;
+                    mbar_arrive(&mail_bar[q]);
+                }
             }
             if (dense) {
-                // not pipelined: wait for our own prefix and finish the tile now
-                mbar_wait(&pref_bar[q], (uint32_t)((it / NSLOT) & 1));
+                // not pipelined: wait for our own prefix (also orders warp 0's slot writes) and finish now
+                mbar_wait(&pref_bar[q], qpar);
                 dense_tile(cur, tb, sl, my_cnt);
                 cur.t = -1;   // nothing pending
             }
@@ -647,18 +673,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
             mbar_arrive(&mail_bar[q]);
         }
         if (!have) draining = true;
-        const long long tw2 = clock64();
-        if (P.dbg && tid == 0) atomicAdd(&P.dbg[1], (unsigned long long)(tw2 - tw1));
+        FXG_DBG(const long long tw2 = clock64(); if (P.dbg && tid == 0) atomicAdd(&P.dbg[1], (unsigned long long)(tw2 - tw1));)
         // ---------------- phase C of tile it-LAG (its look-back had LAG iterations to finish) --------
         if (pend[0].t >= 0) {
-            const int pit = it - LAG, pq = pit % NSLOT;
-            mbar_wait(&pref_bar[pq], (uint32_t)((pit / NSLOT) & 1));
-            const long long tw3 = clock64();
-            if (P.dbg && tid == 0) atomicAdd(&P.dbg[2], (unsigned long long)(tw3 - tw2));
-            phase_c(pend[0], stage_ptr(pit), slots[pq]);
-            if (P.dbg && tid == 0) atomicAdd(&P.dbg[3], (unsigned long long)(clock64() - tw3));
+            mbar_wait(&pref_bar[pq], pqpar);
+            FXG_DBG(const long long tw3 = clock64(); if (P.dbg && tid == 0) atomicAdd(&P.dbg[2], (unsigned long long)(tw3 - tw2));)
+            phase_c(pend[0], stage_ptr(it - LAG), slots[pq]);
+            FXG_DBG(if (P.dbg && tid == 0) atomicAdd(&P.dbg[3], (unsigned long long)(clock64() - tw3));)
         }
         worker_bar();   // (3) stage, slot and line list are free again
+        if (++q == NSLOT) { q = 0; qpar ^= 1u; }
+        if (it >= LAG && ++pq == NSLOT) { pq = 0; pqpar ^= 1u; }
 #pragma unroll
         for (int i = 0; i + 1 < LAG; ++i) pend[i] = pend[i + 1];
         pend[LAG - 1] = cur;
