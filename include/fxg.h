@@ -51,7 +51,8 @@ typedef struct fxg_fasta_row {
     int32_t nlen;     /* chrom name length                        index.c:282-301  */
     uint8_t elen;     /* 1 = "\n", 2 = "\r\n" (from the header)   index.c:267-269  */
     uint8_t norm;     /* <= 1 line differing from the first       index.c:237,342  */
-    uint8_t pad[6];
+    uint8_t pad[6];   /* pad[0] bit 0 (device rows only, not part of the .fxi): every line of the
+                       * record except possibly the last has the same length                       */
 } fxg_fasta_row;
 
 /* One `read` table row (DDL: src/fastq.c:29-37).  32 bytes.
@@ -87,7 +88,10 @@ enum {
     FXG_X_UPPER      = 1,   /* Fasta(uppercase=True): remove_space_uppercase  util.c:181-194 */
     FXG_X_REVERSE    = 2,   /* Sequence.reverse                               util.c:251-260 */
     FXG_X_COMPLEMENT = 4,   /* Sequence.complement (both = antisense)         util.c:239-269 */
-    FXG_X_RAW        = 8    /* no whitespace stripping (FASTQ reads)          read.c:37-45   */
+    FXG_X_RAW        = 8,   /* no whitespace stripping (FASTQ reads)          read.c:37-45   */
+    FXG_X_WHOLE      = 16   /* Fasta.fetch semantics: index into the WHOLE stripped record (fasta.c:454-508)
+                             * instead of the slice -> byte-range formula; rows whose lines are uniform
+                             * (pad[0] bit 0, set by the scan) still take the formula, which is then exact */
 };
 
 typedef struct fxg_ctx  fxg_ctx;    /* one per (process, GPU)                    */
@@ -187,6 +191,13 @@ int fxg_extract_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_row
                      const int64_t *row_id, const int64_t *s, const int64_t *e, const int32_t *flags,
                      int64_t nq, int64_t *out_off_host, uint8_t *out_host, int64_t out_cap,
                      int64_t *acgt_host /* nq*4 or NULL */);
+
+/* K4 (full form): per-query byte histogram of the extracted bytes -- the counting loop of
+ * pyfastx_sequence_composition (src/sequence.c:727-747) and, summed over records, of the
+ * full-index composition scan (src/fasta.c:901-927).  hist_host receives nq x 256 int64. */
+int fxg_composition_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                         const int64_t *row_id, const int64_t *s, const int64_t *e, const int32_t *flags,
+                         int64_t nq, int64_t *hist_host);
 
 /* ---- K5: batched FASTQ read fetch ----------------------------------------------------------
  * Replaces pyfastx_read_random_reader + the seq/qual getters (src/read.c:37-45,152-167,

@@ -220,7 +220,7 @@ int64_t fxo_subseq(const uint8_t *buf, int64_t n, const fxo_fasta_row *row,
     int64_t want = e - s, off, bytes, got, skip = 0;
     uint8_t *tmp;
     if (want <= 0) return 0;
-    if (row->norm && row->llen > row->elen && !(s == 0 && e == row->slen)) {
+    if (row->norm && row->llen > row->elen && !(s == 0 && e == row->slen) && !(flags & FXO_WHOLE)) {
         fxo_slice_range(row, s, e, &off, &bytes);
     } else {
         off = row->boff; bytes = row->blen; skip = s;

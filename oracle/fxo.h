@@ -45,7 +45,8 @@ typedef struct fxo_fastq_row {
 enum {
     FXO_UPPER      = 1,  /* Fasta(uppercase=True): remove_space_uppercase (util.c:181)  */
     FXO_REVERSE    = 2,  /* Sequence.reverse (sequence.c:353)                           */
-    FXO_COMPLEMENT = 4   /* Sequence.complement (sequence.c:369); both = antisense      */
+    FXO_COMPLEMENT = 4,  /* Sequence.complement (sequence.c:369); both = antisense      */
+    FXO_WHOLE      = 16  /* Fasta.fetch: index into the whole stripped record (fasta.c:454-508) */
 };
 
 /* index-build scans ------------------------------------------------------------------ */

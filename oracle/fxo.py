@@ -18,7 +18,7 @@ FASTQ_ROW = np.dtype([("soff", "<i8"), ("qoff", "<i8"), ("rlen", "<i8"),
                       ("dlen", "<i4"), ("nlen", "<i4")])
 assert FASTA_ROW.itemsize == 48 and FASTQ_ROW.itemsize == 32
 
-UPPER, REVERSE, COMPLEMENT = 1, 2, 4
+UPPER, REVERSE, COMPLEMENT, WHOLE = 1, 2, 4, 16
 
 
 def build():

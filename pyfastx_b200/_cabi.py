@@ -21,7 +21,7 @@ FASTQ_ROW = np.dtype([("soff", "<i8"), ("qoff", "<i8"), ("rlen", "<i8"),
 
 FXG_OK, FXG_ENODEV, FXG_ECUDA, FXG_EINVAL, FXG_ENOMEM, FXG_ECAP, FXG_EIO, FXG_EFORMAT = 0, -1, -2, -3, -4, -5, -6, -7
 SCAN_FULL_NAME = 1
-X_UPPER, X_REVERSE, X_COMPLEMENT, X_RAW = 1, 2, 4, 8
+X_UPPER, X_REVERSE, X_COMPLEMENT, X_RAW, X_WHOLE = 1, 2, 4, 8, 16
 
 
 class ScanStats(C.Structure):
@@ -78,6 +78,7 @@ SIGNATURES = {
     "fxg_extract_plan_dev": (i32, [vp, vp, vp, i64, vp, P(i64)]),
     "fxg_extract_dev": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp]),
     "fxg_extract_host": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, i64, vp]),
+    "fxg_composition_host": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
     "fxg_reads_dev": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64, P(i64)]),
     "fxg_reads_host": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64]),
     "fxg_synth_fasta_dev": (i32, [vp, u64, vp, vp, i64, i64, i32, vp]),

@@ -1,0 +1,676 @@
+"""pyfastx-compatible object API (Fasta / Fastq / Sequence / Read) on top of the B200 engine.
+
+Mirrors the reference's Python surface for the hot path -- same class names, constructor
+arguments, indexing/slicing semantics (0-based half-open slices, 1-based inclusive `fetch`),
+strand getters and error types (reference src/fasta.c, src/sequence.c, src/fastq.c, src/read.c)
+-- and adds batched entry points (`fetch_many`, `reads_many`) that feed the GPU gather kernel
+with thousands to millions of queries per call.
+
+Every byte that is returned comes from the CUDA kernels in libfxg.so (a single query is a batch
+of one); there is no CPU extraction path.  The file stays resident in HBM for the lifetime of
+the object.
+"""
+import gzip as _gzip
+import mmap
+import os
+
+import numpy as np
+
+from . import _cabi, fxi
+from .engine import get_engine
+
+__all__ = ["Fasta", "Fastq", "Sequence", "Read", "version", "gzip_check", "reverse_complement"]
+
+VERSION = "2.3.1+b200.1"     # tracks the reference version whose behaviour is reproduced
+
+_RC = _cabi.X_REVERSE | _cabi.X_COMPLEMENT
+
+
+def version(debug=False):
+    if debug:
+        return "pyfastx_b200: %s; libfxg ABI: %d; sqlite: %s" % (VERSION, _cabi.lib().fxg_abi_version(),
+                                                                 fxi.sqlite3.sqlite_version)
+    return VERSION
+
+
+def gzip_check(file_name):
+    """reference src/util.c:307-325: gzip magic number check"""
+    with open(file_name, "rb") as f:
+        return f.read(2) == b"\x1f\x8b"
+
+
+def reverse_complement(seq):
+    """reference src/module.c:37-59 -> reverse_complement_seq (src/util.c:239-249), on the GPU gather
+    kernel: the string is staged as one raw record and fetched with REVERSE|COMPLEMENT|RAW."""
+    data = seq.encode("latin-1") if isinstance(seq, str) else bytes(seq)
+    if not data:
+        return ""
+    eng = get_engine()
+    f = eng.stage_bytes(data)
+    row = np.zeros(1, dtype=_cabi.FASTA_ROW)
+    row["blen"] = row["slen"] = len(data)
+    row["llen"] = len(data) + 1
+    row["elen"] = row["norm"] = 1
+    drows = eng.upload_rows(row)
+    out, _, _ = eng.extract(f, drows, [0], [0], [len(data)], [_RC | _cabi.X_RAW])
+    f.free()
+    drows.free()
+    return out.tobytes().decode("latin-1")
+
+
+def _read_host_bytes(path):
+    """(host bytes-like, is_gzip).  gzip members are inflated on the host before staging
+    (the GPU inflate of BGZF members is the K6 row of SURVEY.md section 8f, not built yet)."""
+    if gzip_check(path):
+        with _gzip.open(path, "rb") as g:
+            return g.read(), True
+    return None, False
+
+
+class _Staged:
+    """file bytes resident in HBM + a cheap host view for header text"""
+
+    def __init__(self, path):
+        self.engine = get_engine()
+        host, self.is_gzip = _read_host_bytes(path)
+        if self.is_gzip:
+            self.host = memoryview(host)
+            self.dfile = self.engine.stage_bytes(np.frombuffer(host, dtype=np.uint8))
+            self._mm = None
+        else:
+            self.dfile = self.engine.stage_path(path)
+            self._fh = open(path, "rb")
+            size = os.fstat(self._fh.fileno()).st_size
+            self._mm = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ) if size else None
+            self.host = memoryview(self._mm) if self._mm is not None else memoryview(b"")
+
+    def first_non_space(self):
+        for i in range(min(len(self.host), 1 << 20)):
+            c = self.host[i]
+            if c not in (9, 10, 11, 12, 13, 32):
+                return c
+        return None
+
+    def close(self):
+        try:
+            self.dfile.free()
+        except Exception:
+            pass
+
+
+# =================================================================================================
+# FASTA
+# =================================================================================================
+class Fasta:
+    """Fasta(file_name, index_file=None, uppercase=False, build_index=True, full_index=False,
+             full_name=False, memory_index=False, key_func=None)      (reference src/fasta.c:39-129)"""
+
+    def __init__(self, file_name, index_file=None, uppercase=False, build_index=True, full_index=False,
+                 full_name=False, memory_index=False, key_func=None):
+        if key_func is not None and not callable(key_func):
+            raise TypeError("key_func must be a callable function")
+        file_name = os.fspath(file_name)
+        if not os.path.exists(file_name):
+            raise FileExistsError("the input fasta file %s does not exists" % file_name)
+        self.file_name = file_name
+        self.uppercase = bool(uppercase)
+        self.full_name = bool(full_name)
+        self.key_func = key_func
+        self._st = _Staged(file_name)
+        self.is_gzip = self._st.is_gzip
+        if self._st.first_non_space() != ord(">"):
+            raise RuntimeError("%s is not plain or gzip compressed fasta formatted file" % file_name)
+        self.index_file = ":memory:" if memory_index else (os.fspath(index_file) if index_file else file_name + ".fxi")
+        self._rows = None
+        self._names = None
+        self._name2id = None
+        self._drows = None
+        self._con = None
+        self._comp_cache = None
+        if build_index:
+            self.build_index()
+            if full_index:
+                _ = self.composition
+
+    # ---- index ---------------------------------------------------------------------------------
+    def build_index(self):
+        """load the .fxi if it exists, else scan on the GPU and write it (src/index.c:418-429)"""
+        if self._rows is not None:
+            return
+        if self.index_file != ":memory:" and os.path.exists(self.index_file):
+            self._con, self._rows, self._names, stat = fxi.load_fasta_index(self.index_file)
+            self._total = int(stat[1]) if stat else int(self._rows["slen"].sum())
+            self.index_matches_file = self._verify_loaded_index()
+        else:
+            eng = self._st.engine
+            rows, st = eng.fasta_scan(self._st.dfile, full_name=self.full_name)
+            host = self._st.host
+            if self.key_func is None:
+                names = [bytes(host[int(r["boff"]) - int(r["elen"]) - int(r["dlen"]):][:int(r["nlen"])]) for r in rows]
+            else:
+                # key_func receives the header text after '>' exactly as the reference passes it
+                # (NUL-terminated line, i.e. including a trailing '\r'), src/index.c:304-318
+                names = []
+                for r in rows:
+                    a = int(r["boff"]) - int(r["elen"]) - int(r["dlen"])
+                    hdr = bytes(host[a:a + int(r["dlen"]) + int(r["elen"]) - 1]).decode("latin-1")
+                    names.append(str(self.key_func(hdr)).encode("utf-8"))
+            self._rows, self._total = rows, int(st["total_len"])
+            self._con = fxi.write_fasta_index(self.index_file, rows, names, self._total)
+            self._names = [fxi._text(b) for b in names]
+        self._name2id = {}
+        for i, nm in enumerate(self._names):
+            self._name2id.setdefault(nm, i)
+        self._drows = self._st.engine.upload_rows(self._rows)
+
+    def _verify_loaded_index(self):
+        """A loaded .fxi carries no line-uniformity bits; one GPU scan (milliseconds) recovers them
+        and doubles as a staleness check of the index against the file."""
+        rows, _ = self._st.engine.fasta_scan(self._st.dfile, full_name=self.full_name)
+        same = len(rows) == len(self._rows) and all(
+            np.array_equal(rows[f], self._rows[f]) for f in ("boff", "blen", "slen", "llen", "elen", "norm", "dlen"))
+        if same:
+            self._rows["pad"] = rows["pad"]
+        return same
+
+    def _need_index(self):
+        if self._rows is None:
+            self.build_index()
+
+    # ---- container protocol -----------------------------------------------------------------------
+    def __len__(self):
+        self._need_index()
+        return len(self._rows)
+
+    @property
+    def size(self):
+        self._need_index()
+        return self._total
+
+    def __contains__(self, name):
+        self._need_index()
+        return name in self._name2id
+
+    def keys(self):
+        self._need_index()
+        return list(self._names)
+
+    def _row_id(self, key):
+        self._need_index()
+        if isinstance(key, (int, np.integer)):
+            i = int(key)
+            if i < 0:
+                i += len(self._rows)
+            if i < 0 or i >= len(self._rows):
+                raise IndexError("index out of range")
+            return i
+        if isinstance(key, str):
+            i = self._name2id.get(key)
+            if i is None:
+                raise KeyError("%s does not exist in fasta file" % key)
+            return i
+        raise KeyError("the key must be index number or sequence name")
+
+    def __getitem__(self, key):
+        i = self._row_id(key)
+        return Sequence(self, i, 0, int(self._rows["slen"][i]), True)
+
+    def __iter__(self):
+        self._need_index()
+        for i in range(len(self._rows)):
+            yield Sequence(self, i, 0, int(self._rows["slen"][i]), True)
+
+    def __repr__(self):
+        return "<Fasta> %s contains %d seqs" % (self.file_name, len(self))
+
+    # ---- batched extraction (additive API feeding K3) -----------------------------------------------
+    def _flags(self, extra=0):
+        return (_cabi.X_UPPER if self.uppercase else 0) | extra
+
+    def extract(self, row_id, start, end, strand_minus=None, want_acgt=False, whole_record=False):
+        """Batched 0-based half-open queries -> (packed uint8 array, offsets[nq+1], acgt[nq,4] | None).
+        whole_record=True gives Fasta.fetch semantics (index into the whole stripped record)."""
+        self._need_index()
+        row_id = np.asarray(row_id, dtype=np.int64)
+        s = np.asarray(start, dtype=np.int64)
+        e = np.asarray(end, dtype=np.int64)
+        slen = self._rows["slen"][row_id]
+        s = np.clip(s, 0, slen)
+        e = np.clip(e, s, slen)
+        flags = np.full(row_id.size, self._flags(_cabi.X_WHOLE if whole_record else 0), dtype=np.int32)
+        if strand_minus is not None:
+            flags |= np.where(np.asarray(strand_minus, dtype=bool), _RC, 0).astype(np.int32)
+        return self._st.engine.extract(self._st.dfile, self._drows, row_id, s, e, flags, want_acgt=want_acgt)
+
+    def fetch_many(self, names, starts, ends, strands=None):
+        """Batched form of fetch(): 1-based inclusive (start, end) per query, strand '+'/'-'.
+        Returns a list of str."""
+        self._need_index()
+        try:
+            rid = np.fromiter((self._name2id[n] if isinstance(n, str) else self._row_id(n) for n in names), dtype=np.int64)
+        except KeyError as ex:
+            raise NameError("Sequence %s does not exists" % ex.args[0])
+        s = np.asarray(starts, dtype=np.int64)
+        e = np.asarray(ends, dtype=np.int64)
+        if (s > e).any():
+            raise ValueError("start position should less than end position")
+        minus = None if strands is None else np.array([c == "-" for c in strands], dtype=bool)
+        out, off, _ = self.extract(rid, s - 1, e, minus, whole_record=True)
+        buf = out.tobytes()
+        return [buf[off[i]:off[i + 1]].decode("latin-1") for i in range(rid.size)]
+
+    def _one(self, i, s, e, extra=0):
+        out, _, _ = self._st.engine.extract(self._st.dfile, self._drows, [i], [s], [e], [self._flags(extra)])
+        return out.tobytes().decode("latin-1")
+
+    # ---- reference methods -------------------------------------------------------------------------
+    def fetch(self, chrom, intervals, strand="+"):
+        """1-based inclusive interval(s) of `chrom`; '-' = reverse complement of the concatenation
+        (reference src/fasta.c:384-515)."""
+        if not isinstance(intervals, (list, tuple)):
+            raise ValueError("intervals must be list or tuple")
+        self._need_index()
+        i = self._name2id.get(chrom)
+        if i is None:
+            raise NameError("Sequence %s does not exists" % chrom)
+        if intervals and isinstance(intervals[0], (int, np.integer)):
+            if len(intervals) != 2:
+                raise ValueError("list or tuple should include only start and end")
+            ivs = [(int(intervals[0]), int(intervals[1]))]
+        else:
+            ivs = [(int(a), int(b)) for a, b in intervals]
+        for a, b in ivs:
+            if a > b:
+                raise ValueError("start position should less than end position")
+        minus = strand == "-"
+        if minus:
+            ivs = ivs[::-1]            # RC(concat(a, b)) == RC(b) + RC(a)
+        rid = np.full(len(ivs), i, dtype=np.int64)
+        s = np.array([a - 1 for a, _ in ivs], dtype=np.int64)
+        e = np.array([b for _, b in ivs], dtype=np.int64)
+        out, _, _ = self.extract(rid, s, e, np.full(len(ivs), minus), whole_record=True)
+        return out.tobytes().decode("latin-1")
+
+    def flank(self, chrom, start, end, flank_length=50, use_cache=False):
+        """(left, right) flanks of the 1-based inclusive interval (reference src/fasta.c:322-382)."""
+        if flank_length < 0:
+            raise ValueError("Flank length must be non-negative")
+        self._need_index()
+        i = self._name2id.get(chrom)
+        if i is None:
+            raise NameError("sequence %s does not exists" % chrom)
+        slen = int(self._rows["slen"][i])
+        ls, le = max(0, start - flank_length - 1), max(0, start - 1)
+        rs, re = min(end, slen), min(end + flank_length, slen)
+        out, off, _ = self.extract([i, i], [ls, rs], [le, re])
+        buf = out.tobytes().decode("latin-1")
+        return buf[off[0]:off[1]], buf[off[1]:off[2]]
+
+    # ---- statistics ------------------------------------------------------------------------------------
+    def _lengths(self):
+        self._need_index()
+        return self._rows["slen"]
+
+    @property
+    def longest(self):
+        i = int(np.argmax(self._lengths()))
+        return self[i]
+
+    @property
+    def shortest(self):
+        i = int(np.argmin(self._lengths()))
+        return self[i]
+
+    @property
+    def mean(self):
+        return float(self.size) / len(self)
+
+    @property
+    def median(self):
+        return float(np.median(self._lengths()))
+
+    def count(self, n):
+        return int((self._lengths() >= n).sum())
+
+    def nl(self, p=50):
+        """(N, L) statistics, e.g. nl(50) = (N50, L50) (reference src/fasta.c:599-683)."""
+        if p < 0 or p > 100:
+            raise ValueError("the value must between 0 and 100")
+        lens = np.sort(self._lengths())[::-1]
+        half = p / 100.0 * self.size
+        csum = np.cumsum(lens)
+        k = int(np.searchsorted(csum, half, side="left"))
+        k = min(k, len(lens) - 1)
+        return int(lens[k]), k + 1
+
+    def _whole_file_hist(self):
+        if self._comp_cache is None:
+            self._need_index()
+            eng = self._st.engine
+            n = len(self._rows)
+            hist = np.zeros(256, dtype=np.int64)
+            step = 65536
+            for a in range(0, n, step):
+                rid = np.arange(a, min(n, a + step), dtype=np.int64)
+                h = np.zeros((rid.size, 256), dtype=np.int64)
+                fl = np.full(rid.size, self._flags(), dtype=np.int32)
+                zs = np.zeros(rid.size, dtype=np.int64)
+                es = np.ascontiguousarray(self._rows["slen"][rid], dtype=np.int64)
+                _cabi.check(_cabi.lib().fxg_composition_host(
+                    eng.ctx, self._st.dfile.handle, self._drows.devptr, n, rid.ctypes.data,
+                    zs.ctypes.data, es.ctypes.data, fl.ctypes.data, rid.size, h.ctypes.data))
+                hist += h.sum(axis=0)
+            self._comp_cache = hist
+        return self._comp_cache
+
+    @property
+    def composition(self):
+        h = self._whole_file_hist()
+        return {chr(i): int(h[i]) for i in range(32, 127) if h[i] > 0}
+
+    @property
+    def gc_content(self):
+        h = self._whole_file_hist()
+        a, c, g, t = (int(h[ord(x)] + h[ord(x.lower())]) for x in "ACGT")
+        return float(np.float32(g + c) / np.float32(a + c + g + t) * np.float32(100))
+
+    @property
+    def gc_skew(self):
+        h = self._whole_file_hist()
+        c, g = (int(h[ord(x)] + h[ord(x.lower())]) for x in "CG")
+        return float(np.float32(g - c) / np.float32(g + c))
+
+    @property
+    def type(self):
+        """DNA / RNA / protein guess from the composition (reference src/fasta.c:1080-1154)."""
+        comp = {k.upper() for k in self.composition}
+        if comp <= set("ACGTN"):
+            return "DNA"
+        if comp <= set("ACGUN"):
+            return "RNA"
+        if comp <= set("ACGTUNRYKMSWBDHV"):
+            return "DNA" if "U" not in comp else "RNA"
+        return "protein"
+
+
+class Sequence:
+    """A record or a slice of one (reference src/sequence.c).  start/end are 1-based inclusive."""
+
+    def __init__(self, fasta, row_id, s, e, complete):
+        self._fa, self.id = fasta, row_id + 1
+        self._i, self._s, self._e = row_id, s, e
+        self._complete = complete
+        self.name = fasta._names[row_id]
+        self.start, self.end = s + 1, e
+
+    def __len__(self):
+        return self._e - self._s
+
+    def _get(self, extra=0):
+        if self._e <= self._s:
+            return ""
+        return self._fa._one(self._i, self._s, self._e, extra)
+
+    @property
+    def seq(self):
+        return self._get()
+
+    @property
+    def reverse(self):
+        return self._get(_cabi.X_REVERSE)
+
+    @property
+    def complement(self):
+        return self._get(_cabi.X_COMPLEMENT)
+
+    @property
+    def antisense(self):
+        return self._get(_RC)
+
+    def __str__(self):
+        return self.seq
+
+    def __repr__(self):
+        if self._complete:
+            return "<Sequence> %s with length of %d" % (self.name, len(self))
+        return "<Sequence> %s from %d to %d" % (self.name, self.start, self.end)
+
+    def __getitem__(self, item):
+        n = len(self)
+        if isinstance(item, slice):
+            a, b, step = item.indices(n)
+            if step != 1:
+                raise ValueError("slice step cannot > 1" if step else "slice step cannot be zero")
+            b = max(a, b)
+            return Sequence(self._fa, self._i, self._s + a, self._s + b, self._complete and (b - a) == n)
+        i = int(item)
+        if i < 0:
+            i += n
+        if i < 0 or i >= n:
+            raise IndexError("index out of range")
+        return self._fa._one(self._i, self._s + i, self._s + i + 1)
+
+    def __contains__(self, sub):
+        return sub in self.seq
+
+    def __iter__(self):
+        """sequence lines of a complete record (reference src/sequence.c:162-263)"""
+        if not self._complete:
+            raise RuntimeError("sliced subsequence cannot be read line by line")
+        r = self._fa._rows[self._i]
+        raw = bytes(self._fa._st.dfile.download(int(r["boff"]), min(int(r["blen"]), self._fa._st.dfile.size - int(r["boff"]))))
+        for line in raw.split(b"\n"):
+            line = line.rstrip(b"\r")
+            if line:
+                yield line.decode("latin-1")
+
+    @property
+    def description(self):
+        r = self._fa._rows[self._i]
+        a = int(r["boff"]) - int(r["elen"]) - int(r["dlen"])
+        return bytes(self._fa._st.dfile.download(a, int(r["dlen"]))).decode("latin-1")
+
+    @property
+    def raw(self):
+        r = self._fa._rows[self._i]
+        if self._complete:
+            a = int(r["boff"]) - int(r["elen"]) - int(r["dlen"]) - 1
+            n = min(int(r["boff"]) + int(r["blen"]), self._fa._st.dfile.size) - a
+        else:
+            bpl = int(r["llen"]) - int(r["elen"])
+            a = int(r["boff"]) + self._s + int(r["elen"]) * (self._s // bpl)
+            n = (self._e - self._s) + (self._e // bpl - self._s // bpl) * int(r["elen"])
+        return bytes(self._fa._st.dfile.download(a, n)).decode("latin-1")
+
+    def _acgt(self):
+        _, _, acgt = self._fa.extract([self._i], [self._s], [self._e], want_acgt=True)
+        return [int(x) for x in acgt[0]]
+
+    @property
+    def gc_content(self):
+        a, c, g, t = self._acgt()
+        return float(np.float32(g + c) / np.float32(a + c + g + t) * np.float32(100))
+
+    @property
+    def gc_skew(self):
+        _, c, g, _ = self._acgt()
+        return float(np.float32(g - c) / np.float32(g + c))
+
+    @property
+    def composition(self):
+        fa = self._fa
+        h = np.zeros((1, 256), dtype=np.int64)
+        one = lambda v: np.array([v], dtype=np.int64)
+        rid, s, e = one(self._i), one(self._s), one(self._e)
+        fl = np.array([fa._flags()], dtype=np.int32)
+        _cabi.check(_cabi.lib().fxg_composition_host(fa._st.engine.ctx, fa._st.dfile.handle, fa._drows.devptr,
+                                                    len(fa._rows), rid.ctypes.data, s.ctypes.data, e.ctypes.data,
+                                                    fl.ctypes.data, 1, h.ctypes.data))
+        return {chr(i): int(h[0, i]) for i in range(32, 127) if h[0, i] > 0}
+
+    def search(self, subseq, strand="+"):
+        """1-based position of the first match or None (reference src/sequence.c:519-560)"""
+        q = subseq if strand == "+" else reverse_complement(subseq)
+        k = self.seq.find(q)
+        return k + 1 if k >= 0 else None
+
+
+# =================================================================================================
+# FASTQ
+# =================================================================================================
+class Fastq:
+    """Fastq(file_name, index_file=None, phred=0, build_index=True, full_index=False, full_name=False)
+    (reference src/fastq.c:257-376)"""
+
+    def __init__(self, file_name, index_file=None, phred=0, build_index=True, full_index=False, full_name=False):
+        file_name = os.fspath(file_name)
+        if not os.path.exists(file_name):
+            raise FileExistsError("input fastq file %s does not exists" % file_name)
+        self.file_name = file_name
+        self._st = _Staged(file_name)
+        self.is_gzip = self._st.is_gzip
+        if self._st.first_non_space() != ord("@"):
+            raise RuntimeError("%s is not plain or gzip compressed fastq formatted file" % file_name)
+        self.index_file = os.fspath(index_file) if index_file else file_name + ".fxi"
+        self._phred = phred
+        self._rows = None
+        if build_index:
+            self.build_index()
+
+    def build_index(self):
+        if self._rows is not None:
+            return True
+        if os.path.exists(self.index_file):
+            self._con, self._rows, self._names, stat = fxi.load_fastq_index(self.index_file)
+            self._counts, self.size, self.avglen = int(stat[0]), int(stat[1]), stat[2]
+        else:
+            eng = self._st.engine
+            rows, st = eng.fastq_scan(self._st.dfile)
+            host = self._st.host
+            names = [bytes(host[int(r["soff"]) - int(r["dlen"]):][:int(r["nlen"])]) for r in rows]
+            self._rows = rows
+            self._counts = st["n_lines"] // 4
+            self.size = int(st["total_len"])
+            self.avglen = self.size * 1.0 / self._counts if self._counts else float("nan")
+            self._con = fxi.write_fastq_index(self.index_file, rows, names, st["n_lines"], self.size)
+            self._names = [fxi._text(b) for b in names]
+        self._name2id = {}
+        for i, nm in enumerate(self._names):
+            self._name2id.setdefault(nm, i)
+        self._drows = self._st.engine.upload_rows(self._rows)
+        return True
+
+    def __len__(self):
+        self.build_index()
+        return self._counts
+
+    def __contains__(self, name):
+        self.build_index()
+        return name in self._name2id
+
+    def keys(self):
+        self.build_index()
+        return list(self._names)
+
+    def _row_id(self, key):
+        self.build_index()
+        if isinstance(key, (int, np.integer)):
+            i = int(key)
+            if i < 0:
+                i += len(self._rows)
+            if i < 0 or i >= len(self._rows):
+                raise IndexError("index out of range")
+            return i
+        if isinstance(key, str):
+            i = self._name2id.get(key)
+            if i is None:
+                raise KeyError("%s does not exist in fastq file" % key)
+            return i
+        raise KeyError("the key must be index number or read name")
+
+    def __getitem__(self, key):
+        return Read(self, self._row_id(key))
+
+    def __iter__(self):
+        self.build_index()
+        for i in range(len(self._rows)):
+            yield Read(self, i)
+
+    def __repr__(self):
+        return "<Fastq> %s contains %d reads" % (self.file_name, len(self))
+
+    def reads_many(self, ids, want_qual=True, strand_minus=False):
+        """Batched read fetch -> (seq packed uint8, qual packed uint8 | None, offsets[n+1])"""
+        self.build_index()
+        ids = np.asarray(ids, dtype=np.int64)
+        flags = _RC if strand_minus else 0
+        return self._st.engine.reads(self._st.dfile, self._drows, ids, flags=flags, want_qual=want_qual,
+                                     rlens=self._rows["rlen"][ids])
+
+    @property
+    def phred(self):
+        return self._phred or 33
+
+
+class Read:
+    """one FASTQ record (reference src/read.c)"""
+
+    def __init__(self, fq, i):
+        self._fq, self._i = fq, i
+        self.id = i + 1
+        self.name = fq._names[i]
+
+    def __len__(self):
+        return int(self._fq._rows["rlen"][self._i])
+
+    def _fetch(self, flags=0, qual=False):
+        fq = self._fq
+        seq, ql, _ = fq._st.engine.reads(fq._st.dfile, fq._drows, [self._i], flags=flags, want_seq=not qual,
+                                         want_qual=qual, rlens=[len(self)])
+        return (ql if qual else seq).tobytes().decode("latin-1")
+
+    @property
+    def seq(self):
+        return self._fetch()
+
+    @property
+    def qual(self):
+        return self._fetch(qual=True)
+
+    @property
+    def quali(self):
+        p = self._fq.phred
+        return [c - p for c in self._fetch(qual=True).encode("latin-1")]
+
+    @property
+    def reverse(self):
+        return self._fetch(_cabi.X_REVERSE)
+
+    @property
+    def complement(self):
+        return self._fetch(_cabi.X_COMPLEMENT)
+
+    @property
+    def antisense(self):
+        return self._fetch(_RC)
+
+    @property
+    def description(self):
+        r = self._fq._rows[self._i]
+        raw = bytes(self._fq._st.dfile.download(int(r["soff"]) - int(r["dlen"]) - 1, int(r["dlen"])))
+        return raw.rstrip(b"\r").decode("latin-1")
+
+    @property
+    def raw(self):
+        r = self._fq._rows[self._i]
+        a = int(r["soff"]) - int(r["dlen"]) - 1
+        end = min(int(r["qoff"]) + int(r["rlen"]) + 2, self._fq._st.dfile.size)
+        raw = bytes(self._fq._st.dfile.download(a, end - a))
+        k = raw.find(b"\n", int(r["qoff"]) - a)
+        return raw[:k + 1 if k >= 0 else len(raw)].decode("latin-1")
+
+    def __str__(self):
+        return self.seq
+
+    def __repr__(self):
+        return "<Read> %s with length of %d" % (self.name, len(self))

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(XTHREADS) extract_kernel(
         int64_t s = q_s[q], e = q_e[q];
         const int flags = q_flags ? q_flags[q] : 0;
         GatherJob job;
-        job.flags = flags & ~FXG_X_RAW;
+        job.flags = flags;
         job.dst = out + out_off[q];
         job.skip = 0;
         job.src = 0; job.src_len = 0;
@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(XTHREADS) extract_kernel(
             const fxg_fasta_row r = rows[rid];
             const int64_t bpl = r.llen - (int64_t)r.elen;
             const bool whole = (s == 0 && e == r.slen);
-            if (r.norm && bpl > 0 && !whole) {
+            const bool formula_ok = !(flags & FXG_X_WHOLE) || (r.pad[0] & 1);
+            if (r.norm && bpl > 0 && !whole && formula_ok) {
                 const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
                 job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
                 job.src_len = (e - s) + (be - bs) * (int64_t)r.elen;            // sequence.c:509
@@ -353,6 +354,18 @@ __global__ void ps_write_offsets(const int64_t *s, const int64_t *e, const fxg_f
         // the thread that covers index nq-1 also writes out_off[nq]
         if (q0 <= nq - 1 && nq - 1 < q0 + per) out_off[nq] = base + acc;
     }
+}
+
+// per-query 256-bin histogram of the packed output (one CTA per query, 64-bit shared bins)
+__global__ void hist_kernel(const uint8_t *__restrict__ out, const int64_t *__restrict__ out_off, int64_t *__restrict__ hist) {
+    __shared__ unsigned long long bins[256];
+    const int64_t q = blockIdx.x;
+    bins[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t b = out_off[q], e = out_off[q + 1];
+    for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) atomicAdd(&bins[out[i]], 1ull);
+    __syncthreads();
+    hist[q * 256 + threadIdx.x] = (int64_t)bins[threadIdx.x];
 }
 
 }  // namespace fxg
@@ -497,6 +510,38 @@ extern "C" int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_r
     FXG_CUDA(cudaMemcpyAsync(out_off_host, d_off, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (seq_host && total) FXG_CUDA(cudaMemcpyAsync(seq_host, d_seq, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     if (qual_host && total) FXG_CUDA(cudaMemcpyAsync(qual_host, d_qual, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}
+
+extern "C" int fxg_composition_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                                    const int64_t *row_id, const int64_t *s, const int64_t *e, const int32_t *flags,
+                                    int64_t nq, int64_t *hist_host) {
+    FXG_CHECK_ARG(ctx && f && nq >= 0 && (nq == 0 || (row_id && s && e && hist_host)), "bad arguments");
+    if (nq == 0) return FXG_OK;
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)nq * sizeof(int64_t);
+    int rc = ctx->misc.reserve(qb * 3 + (size_t)(nq + 1) * 8 + (size_t)nq * 4 + 64 + (size_t)nq * 2048);
+    if (rc) return rc;
+    int64_t *d_row = (int64_t *)ctx->misc.ptr, *d_s = d_row + nq, *d_e = d_s + nq, *d_off = d_e + nq;
+    int32_t *d_fl = (int32_t *)(d_off + nq + 1);
+    int64_t *d_hist = (int64_t *)(((uintptr_t)(d_fl + nq) + 15) & ~(uintptr_t)15);
+    FXG_CUDA(cudaMemcpyAsync(d_row, row_id, qb, cudaMemcpyHostToDevice, ctx->stream));
+    FXG_CUDA(cudaMemcpyAsync(d_s, s, qb, cudaMemcpyHostToDevice, ctx->stream));
+    FXG_CUDA(cudaMemcpyAsync(d_e, e, qb, cudaMemcpyHostToDevice, ctx->stream));
+    if (flags) FXG_CUDA(cudaMemcpyAsync(d_fl, flags, (size_t)nq * 4, cudaMemcpyHostToDevice, ctx->stream));
+    FXG_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)nq * 2048, ctx->stream));
+    int64_t total = 0;
+    rc = prefix_lengths(ctx, d_s, d_e, nullptr, nullptr, 0, nq, d_off, &total);
+    if (rc) return rc;
+    if ((rc = ctx->row_tmp.reserve((size_t)total + 64))) return rc;
+    uint8_t *d_out = (uint8_t *)ctx->row_tmp.ptr;
+    rc = fxg_extract_dev(ctx, f, d_rows, n_rows, d_row, d_s, d_e, flags ? d_fl : nullptr, nq, d_off, d_out, nullptr);
+    if (rc) return rc;
+    ctx->launches += 1;
+    hist_kernel<<<(unsigned)nq, 256, 0, ctx->stream>>>(d_out, d_off, d_hist);
+    FXG_CUDA(cudaGetLastError());
+    FXG_CUDA(cudaMemcpyAsync(hist_host, d_hist, (size_t)nq * 2048, cudaMemcpyDeviceToHost, ctx->stream));
     FXG_CUDA(cudaStreamSynchronize(ctx->stream));
     return FXG_OK;
 }

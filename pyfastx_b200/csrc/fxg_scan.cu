@@ -730,6 +730,8 @@ __global__ void fasta_finalize_kernel(const FastaTmp *tmp, int64_t nrows, int64_
         o.boff = t.boff; o.blen = blen; o.slen = slen; o.llen = t.llen;
         o.dlen = t.dlen; o.nlen = t.nlen; o.elen = (uint8_t)t.elen; o.norm = (uint8_t)norm;
         for (int i = 0; i < 6; ++i) o.pad[i] = 0;
+        // uniform lines: no length change at all, or a single SHORTER line at the very end
+        o.pad[0] = (t.D == 0 || (t.D == 1 && (int64_t)t.evmax == t.lineidx + nlines && (int64_t)t.S < 0)) ? 1 : 0;
         rows[r] = o;
         slen_acc = (unsigned long long)slen;
     }
