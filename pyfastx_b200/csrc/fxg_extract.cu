@@ -194,15 +194,147 @@ __device__ __forceinline__ uint8_t complement_byte(int b) {
     return (uint8_t)(r + low);
 }
 
+// ---- fast path ("pull"): records with uniform lines ---------------------------------------------
+// Output-driven: every lane assembles one aligned 16-byte OUTPUT word per round.  The kept rank of
+// its first byte gives the source position through the slice formula (sequence.c:498-510):
+//   src(k) = boff + k + elen * (k / bpl)
+// Six aligned 32-bit loads cover the <= 18 source bytes; two funnel-shift extractions (before /
+// after the line break) are merged with a byte mask.  The layout assumption is VERIFIED on the
+// fly (no strippable byte among the kept ones, '\r' where elen = 2 says so); any violation makes
+// the warp redo the query with the general strip path, so results stay exact.
+// tables: 0 = complement, 1 = upper, 2 = upper then complement
+template <bool WANT_ACGT>
+__device__ bool pull_one(const uint8_t *__restrict__ file, int64_t boff, int64_t s, int64_t out_len, uint32_t bpl,
+                         int elen, int flags, uint8_t *__restrict__ dst, const uint8_t (*__restrict__ s_lut)[256],
+                         int lane, int64_t *acgt_out) {
+    const bool raw = (flags & FXG_X_RAW) != 0;
+    const bool rev = (flags & FXG_X_REVERSE) != 0;
+    const bool upper = (flags & FXG_X_UPPER) != 0, comp = (flags & FXG_X_COMPLEMENT) != 0;
+    const uint8_t *tbl = comp ? (upper ? s_lut[2] : s_lut[0]) : s_lut[1];
+    const bool xform = upper || comp;
+    const int a = (int)((uintptr_t)dst & 15);
+    const int64_t nwords = (a + out_len + 15) >> 4;
+    const int64_t q_s = raw ? 0 : s / (int64_t)bpl;
+    const uint32_t rem_s = raw ? 0u : (uint32_t)(s - q_s * (int64_t)bpl);
+    bool bad = false;
+    int cntA = 0, cntC = 0, cntG = 0, cntT = 0;
+    for (int64_t w0 = 0; w0 < nwords; w0 += 32) {
+        const int64_t w = w0 + lane;
+        if (w < nwords) {
+            const int64_t jw = 16 * w - a;                              // output index of slot 0
+            const int lo = jw < 0 ? (int)(-jw) : 0;
+            const int hi = (jw + 16 > out_len) ? (int)(out_len - jw) : 16;
+            const int nb = hi - lo;                                     // valid slots [lo, hi)
+            const uint32_t d = (uint32_t)(rev ? (out_len - (jw + hi)) : (jw + lo));   // first kept rank - s
+            uint32_t dq = 0, c = 0xffffffffu;
+            if (!raw) {
+                const uint32_t t = rem_s + d;
+                dq = t / bpl;
+                c = bpl - (t - dq * bpl);                               // bytes left on this line
+            }
+            const int64_t p = boff + s + (int64_t)d + (int64_t)elen * (q_s + (int64_t)dq);
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(file + (p & ~(int64_t)3));
+            uint32_t W[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) W[i] = wp[i];
+            const int o1 = (int)(p & 3);
+            uint32_t V[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) V[i] = __funnelshift_r(W[i], W[i + 1], o1 * 8);
+            if (c < (uint32_t)nb) {                                     // a line break inside this word
+                const int o2 = o1 + elen, ws2 = o2 >> 2, bs2 = (o2 & 3) * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t lo_w = ws2 ? W[i + 1] : W[i], hi_w = ws2 ? W[(i + 2 < 6) ? i + 2 : 5] : W[i + 1];
+                    const uint32_t e2 = __funnelshift_r(lo_w, hi_w, bs2);
+                    const int rel = (int)c - 4 * i;                     // bytes of this word taken before the break
+                    const uint32_t m = rel <= 0 ? 0xffffffffu : (rel >= 4 ? 0u : (0xffffffffu << (8 * rel)));
+                    V[i] = (V[i] & ~m) | (e2 & m);
+                }
+                if (elen == 2 && file[p + c] != '\r') bad = true;      // the skipped byte must be strippable
+            }
+            // valid-byte masks (0x80 per byte) of the first nb bytes
+            uint32_t vb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rel = nb - 4 * i;
+                vb[i] = rel >= 4 ? 0x80808080u : (rel <= 0 ? 0u : (0x80808080u & ((1u << (8 * rel)) - 1u)));
+            }
+            if (!raw) {
+                uint32_t strip = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    strip |= (byte_eq_mask(V[i], 0x0a0a0a0au) | byte_eq_mask(V[i], 0x0d0d0d0du) |
+                              byte_eq_mask(V[i], 0x20202020u)) & vb[i];
+                if (strip) bad = true;
+            }
+            if (xform) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t x = V[i];
+                    V[i] = (uint32_t)tbl[x & 0xff] | ((uint32_t)tbl[(x >> 8) & 0xff] << 8) |
+                           ((uint32_t)tbl[(x >> 16) & 0xff] << 16) | ((uint32_t)tbl[x >> 24] << 24);
+                }
+            }
+            if (WANT_ACGT) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cntA += count_letter(V[i], 0x61616161u, vb[i]);
+                    cntC += count_letter(V[i], 0x63636363u, vb[i]);
+                    cntG += count_letter(V[i], 0x67676767u, vb[i]);
+                    cntT += count_letter(V[i], 0x74747474u, vb[i]);
+                }
+            }
+            uint8_t *gw = dst + jw;                                     // 16-byte aligned
+            if (nb == 16) {
+                uint4 o;
+                if (rev) {
+                    o.x = __byte_perm(V[3], 0, 0x0123); o.y = __byte_perm(V[2], 0, 0x0123);
+                    o.z = __byte_perm(V[1], 0, 0x0123); o.w = __byte_perm(V[0], 0, 0x0123);
+                } else { o.x = V[0]; o.y = V[1]; o.z = V[2]; o.w = V[3]; }
+                *reinterpret_cast<uint4 *>(gw) = o;
+            } else {                                                    // ragged first / last word
+                uint32_t tmp[4] = {V[0], V[1], V[2], V[3]};
+                for (int i = 0; i < nb; ++i) {
+                    const int k = rev ? nb - 1 - i : i;
+                    gw[lo + i] = (uint8_t)(tmp[k >> 2] >> (8 * (k & 3)));
+                }
+            }
+        }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (bad) return false;
+    if (WANT_ACGT) {
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            cntA += __shfl_down_sync(0xffffffffu, cntA, dd);
+            cntC += __shfl_down_sync(0xffffffffu, cntC, dd);
+            cntG += __shfl_down_sync(0xffffffffu, cntG, dd);
+            cntT += __shfl_down_sync(0xffffffffu, cntT, dd);
+        }
+        if (lane == 0 && acgt_out) { acgt_out[0] = cntA; acgt_out[1] = cntC; acgt_out[2] = cntG; acgt_out[3] = cntT; }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void init_luts(uint8_t (*s_lut)[256]) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int up = (i >= 'a' && i <= 'z') ? i - 32 : i;
+        s_lut[0][i] = complement_byte(i);
+        s_lut[1][i] = (uint8_t)up;
+        s_lut[2][i] = complement_byte(up);
+    }
+}
+
 template <bool WANT_ACGT>
 __global__ void __launch_bounds__(XTHREADS) extract_kernel(
-    const uint8_t *__restrict__ file, int64_t fsize, const fxg_fasta_row *__restrict__ rows, int64_t n_rows,
-    const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s, const int64_t *__restrict__ q_e,
-    const int32_t *__restrict__ q_flags, int64_t nq, const int64_t *__restrict__ out_off,
-    uint8_t *__restrict__ out, int64_t *__restrict__ acgt) {
-    __shared__ uint8_t s_lut[256];
+    const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fasta_row *__restrict__ rows,
+    int64_t n_rows, const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s,
+    const int64_t *__restrict__ q_e, const int32_t *__restrict__ q_flags, int64_t nq,
+    const int64_t *__restrict__ out_off, uint8_t *__restrict__ out, int64_t *__restrict__ acgt) {
+    __shared__ uint8_t s_lut[3][256];
     __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
-    for (int i = threadIdx.x; i < 256; i += XTHREADS) s_lut[i] = complement_byte(i);
+    init_luts(s_lut);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * XWARPS;
@@ -216,11 +348,19 @@ __global__ void __launch_bounds__(XTHREADS) extract_kernel(
         job.skip = 0;
         job.src = 0; job.src_len = 0;
         job.out_len = e > s ? e - s : 0;
+        bool done = false;
         if (rid >= 0 && rid < n_rows && job.out_len > 0) {
             const fxg_fasta_row r = rows[rid];
             const int64_t bpl = r.llen - (int64_t)r.elen;
             const bool whole = (s == 0 && e == r.slen);
-            const bool formula_ok = !(flags & FXG_X_WHOLE) || (r.pad[0] & 1);
+            const bool uniform = (r.pad[0] & 1) != 0;
+            // fast path: uniform lines, sane sizes, source window inside the buffer
+            if (r.norm && uniform && bpl >= 16 && bpl < (1ll << 30) && job.out_len < (1ll << 30) && e <= r.slen &&
+                r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW)) {
+                done = pull_one<WANT_ACGT>(file, r.boff, s, job.out_len, (uint32_t)bpl, (int)r.elen, flags, job.dst, s_lut,
+                                           lane, WANT_ACGT ? acgt + 4 * q : nullptr);
+            }
+            const bool formula_ok = !(flags & FXG_X_WHOLE) || uniform;
             if (r.norm && bpl > 0 && !whole && formula_ok) {
                 const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
                 job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
@@ -229,20 +369,21 @@ __global__ void __launch_bounds__(XTHREADS) extract_kernel(
                 job.src = r.boff; job.src_len = r.blen; job.skip = s;           // sequence.c:100-102,108-110
             }
         }
+        if (done) continue;
         if (job.out_len > 0)
-            gather_one<WANT_ACGT>(file, fsize, job, s_lut, s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
+            gather_one<WANT_ACGT>(file, fsize, job, s_lut[0], s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
         else if (WANT_ACGT && lane == 0) { acgt[4 * q] = acgt[4 * q + 1] = acgt[4 * q + 2] = acgt[4 * q + 3] = 0; }
     }
 }
 
-// K5: which = 0 -> sequence line (soff), 1 -> quality line (qoff)
+// K5: FASTQ reads: raw copies of rlen bytes at soff (sequence) and qoff (quality)
 __global__ void __launch_bounds__(XTHREADS) reads_kernel(
-    const uint8_t *__restrict__ file, int64_t fsize, const fxg_fastq_row *__restrict__ rows, int64_t n_rows,
-    const int64_t *__restrict__ ids, int64_t nq, int flags, const int64_t *__restrict__ out_off,
+    const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fastq_row *__restrict__ rows,
+    int64_t n_rows, const int64_t *__restrict__ ids, int64_t nq, int flags, const int64_t *__restrict__ out_off,
     uint8_t *__restrict__ seq_out, uint8_t *__restrict__ qual_out) {
-    __shared__ uint8_t s_lut[256];
+    __shared__ uint8_t s_lut[3][256];
     __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
-    for (int i = threadIdx.x; i < 256; i += XTHREADS) s_lut[i] = complement_byte(i);
+    init_luts(s_lut);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * XWARPS;
@@ -250,16 +391,21 @@ __global__ void __launch_bounds__(XTHREADS) reads_kernel(
         const int64_t id = ids[q];
         if (id < 0 || id >= n_rows) continue;
         const fxg_fastq_row r = rows[id];
+        if (r.rlen <= 0) continue;
+        const bool fast = r.rlen < (1ll << 30) && r.soff + r.rlen + 32 <= capacity && r.qoff + r.rlen + 32 <= capacity &&
+                          r.soff >= 0 && r.qoff >= 0;
         GatherJob job;
         job.skip = 0; job.src_len = r.rlen; job.out_len = r.rlen;
         if (seq_out) {
             job.src = r.soff; job.dst = seq_out + out_off[q]; job.flags = flags | FXG_X_RAW;
-            gather_one<false>(file, fsize, job, s_lut, s_stage[warp], lane, nullptr);
+            if (!fast || !pull_one<false>(file, r.soff, 0, r.rlen, 1u << 30, 1, job.flags, job.dst, s_lut, lane, nullptr))
+                gather_one<false>(file, fsize, job, s_lut[0], s_stage[warp], lane, nullptr);
         }
         if (qual_out) {
             job.src = r.qoff; job.dst = qual_out + out_off[q];
             job.flags = (flags & FXG_X_REVERSE) | FXG_X_RAW;      // qualities are never complemented
-            gather_one<false>(file, fsize, job, s_lut, s_stage[warp], lane, nullptr);
+            if (!fast || !pull_one<false>(file, r.qoff, 0, r.rlen, 1u << 30, 1, job.flags, job.dst, s_lut, lane, nullptr))
+                gather_one<false>(file, fsize, job, s_lut[0], s_stage[warp], lane, nullptr);
         }
     }
 }
@@ -423,10 +569,10 @@ extern "C" int fxg_extract_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_
     const int grid = gather_grid(ctx, nq);
     FxgProfScope prof(ctx, FXG_PROF_GATHER);
     if (d_acgt)
-        extract_kernel<true><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_row_id, d_s, d_e,
+        extract_kernel<true><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e,
                                                                 d_flags, nq, d_out_off, d_out, d_acgt);
     else
-        extract_kernel<false><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_row_id, d_s, d_e,
+        extract_kernel<false><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e,
                                                                  d_flags, nq, d_out_off, d_out, nullptr);
     FXG_CUDA(cudaGetLastError());
     return FXG_OK;
@@ -480,7 +626,7 @@ extern "C" int fxg_reads_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_ro
     if (total > out_cap) { fxg_set_error("output needs %lld bytes, capacity %lld", (long long)total, (long long)out_cap); return FXG_ECAP; }
     if (nq == 0 || (!d_seq_out && !d_qual_out)) return FXG_OK;
     FxgProfScope prof(ctx, FXG_PROF_GATHER);
-    reads_kernel<<<gather_grid(ctx, nq), XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_ids, nq, flags,
+    reads_kernel<<<gather_grid(ctx, nq), XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_ids, nq, flags,
                                                                     d_out_off, d_seq_out, d_qual_out);
     FXG_CUDA(cudaGetLastError());
     return FXG_OK;
@@ -504,7 +650,7 @@ extern "C" int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_r
     uint8_t *d_seq = (uint8_t *)ctx->row_tmp.ptr;
     uint8_t *d_qual = d_seq + fxg_round_up(total + 16, 16);
     ctx->launches += 1;
-    reads_kernel<<<gather_grid(ctx, nq), XTHREADS, 0, ctx->stream>>>(f->d, f->size, d_rows, n_rows, d_ids, nq, flags, d_off,
+    reads_kernel<<<gather_grid(ctx, nq), XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_ids, nq, flags, d_off,
                                                                     seq_host ? d_seq : nullptr, qual_host ? d_qual : nullptr);
     FXG_CUDA(cudaGetLastError());
     FXG_CUDA(cudaMemcpyAsync(out_off_host, d_off, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
