@@ -214,8 +214,12 @@ __device__ bool pull_one(const uint8_t *__restrict__ file, int64_t boff, int64_t
     const bool xform = upper || comp;
     const int a = (int)((uintptr_t)dst & 15);
     const int64_t nwords = (a + out_len + 15) >> 4;
-    const int64_t q_s = raw ? 0 : s / (int64_t)bpl;
-    const uint32_t rem_s = raw ? 0u : (uint32_t)(s - q_s * (int64_t)bpl);
+    int64_t q_s = 0;
+    uint32_t rem_s = 0;
+    if (!raw) {
+        if ((uint64_t)s < (1ull << 32)) { const uint32_t qq = (uint32_t)s / bpl; q_s = qq; rem_s = (uint32_t)s - qq * bpl; }
+        else { q_s = s / (int64_t)bpl; rem_s = (uint32_t)(s - q_s * (int64_t)bpl); }
+    }
     bool bad = false;
     int cntA = 0, cntC = 0, cntG = 0, cntT = 0;
     for (int64_t w0 = 0; w0 < nwords; w0 += 32) {
@@ -261,12 +265,13 @@ __device__ bool pull_one(const uint8_t *__restrict__ file, int64_t boff, int64_t
                 vb[i] = rel >= 4 ? 0x80808080u : (rel <= 0 ? 0u : (0x80808080u & ((1u << (8 * rel)) - 1u)));
             }
             if (!raw) {
-                uint32_t strip = 0;
+                // conservative layout check: every kept byte must be >= 0x40 (letters); anything below
+                // (which includes the strippable 10 / 13 / 32, but also digits, '*', '-') sends the query
+                // to the general strip path, so the result is exact either way
+                uint32_t all = 0x40404040u;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    strip |= (byte_eq_mask(V[i], 0x0a0a0a0au) | byte_eq_mask(V[i], 0x0d0d0d0du) |
-                              byte_eq_mask(V[i], 0x20202020u)) & vb[i];
-                if (strip) bad = true;
+                for (int i = 0; i < 4; ++i) all &= ((V[i] | (V[i] >> 1)) | ~(vb[i] >> 1));
+                if ((all & 0x40404040u) != 0x40404040u) bad = true;
             }
             if (xform) {
 #pragma unroll
@@ -327,7 +332,7 @@ __device__ __forceinline__ void init_luts(uint8_t (*s_lut)[256]) {
 }
 
 template <bool WANT_ACGT>
-__global__ void __launch_bounds__(XTHREADS) extract_kernel(
+__global__ void __launch_bounds__(XTHREADS, 4) extract_kernel(
     const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fasta_row *__restrict__ rows,
     int64_t n_rows, const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s,
     const int64_t *__restrict__ q_e, const int32_t *__restrict__ q_flags, int64_t nq,
@@ -338,19 +343,41 @@ __global__ void __launch_bounds__(XTHREADS) extract_kernel(
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * XWARPS;
-    for (int64_t q = (int64_t)blockIdx.x * XWARPS + warp; q < nq; q += nwarps) {
-        const int64_t rid = q_row[q];
-        int64_t s = q_s[q], e = q_e[q];
-        const int flags = q_flags ? q_flags[q] : 0;
+    // software pipeline over queries: descriptors are fetched two queries ahead, index rows one
+    // ahead, so the dependent chain  query -> row -> file bytes  is off the critical path
+    struct Desc { int64_t rid, s, e, off; int flags; };
+    auto load_desc = [&](int64_t qq) -> Desc {
+        Desc d; d.rid = -1; d.s = 0; d.e = 0; d.off = 0; d.flags = 0;
+        if (qq < nq) { d.rid = q_row[qq]; d.s = q_s[qq]; d.e = q_e[qq]; d.off = out_off[qq]; d.flags = q_flags ? q_flags[qq] : 0; }
+        return d;
+    };
+    union RowU { fxg_fasta_row r; uint4 v[3]; };
+    auto load_row = [&](int64_t rid) -> RowU {
+        RowU u;
+        u.v[0] = u.v[1] = u.v[2] = make_uint4(0, 0, 0, 0);
+        if (rid >= 0 && rid < n_rows) {
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(rows + rid);
+            u.v[0] = p4[0]; u.v[1] = p4[1]; u.v[2] = p4[2];
+        }
+        return u;
+    };
+    int64_t q = (int64_t)blockIdx.x * XWARPS + warp;
+    Desc d0 = load_desc(q), d1 = load_desc(q + nwarps);
+    RowU r0 = load_row(d0.rid);
+    for (; q < nq; q += nwarps) {
+        const Desc d2 = load_desc(q + 2 * nwarps);
+        const RowU r1 = load_row(d1.rid);
+        const int64_t rid = d0.rid, s = d0.s, e = d0.e;
+        const int flags = d0.flags;
         GatherJob job;
         job.flags = flags;
-        job.dst = out + out_off[q];
+        job.dst = out + d0.off;
         job.skip = 0;
         job.src = 0; job.src_len = 0;
         job.out_len = e > s ? e - s : 0;
         bool done = false;
         if (rid >= 0 && rid < n_rows && job.out_len > 0) {
-            const fxg_fasta_row r = rows[rid];
+            const fxg_fasta_row &r = r0.r;
             const int64_t bpl = r.llen - (int64_t)r.elen;
             const bool whole = (s == 0 && e == r.slen);
             const bool uniform = (r.pad[0] & 1) != 0;
@@ -360,19 +387,23 @@ __global__ void __launch_bounds__(XTHREADS) extract_kernel(
                 done = pull_one<WANT_ACGT>(file, r.boff, s, job.out_len, (uint32_t)bpl, (int)r.elen, flags, job.dst, s_lut,
                                            lane, WANT_ACGT ? acgt + 4 * q : nullptr);
             }
-            const bool formula_ok = !(flags & FXG_X_WHOLE) || uniform;
-            if (r.norm && bpl > 0 && !whole && formula_ok) {
-                const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
-                job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
-                job.src_len = (e - s) + (be - bs) * (int64_t)r.elen;            // sequence.c:509
-            } else {
-                job.src = r.boff; job.src_len = r.blen; job.skip = s;           // sequence.c:100-102,108-110
+            if (!done) {
+                const bool formula_ok = !(flags & FXG_X_WHOLE) || uniform;
+                if (r.norm && bpl > 0 && !whole && formula_ok) {
+                    const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
+                    job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
+                    job.src_len = (e - s) + (be - bs) * (int64_t)r.elen;            // sequence.c:509
+                } else {
+                    job.src = r.boff; job.src_len = r.blen; job.skip = s;           // sequence.c:100-102,108-110
+                }
             }
         }
-        if (done) continue;
-        if (job.out_len > 0)
-            gather_one<WANT_ACGT>(file, fsize, job, s_lut[0], s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
-        else if (WANT_ACGT && lane == 0) { acgt[4 * q] = acgt[4 * q + 1] = acgt[4 * q + 2] = acgt[4 * q + 3] = 0; }
+        if (!done) {
+            if (job.out_len > 0)
+                gather_one<WANT_ACGT>(file, fsize, job, s_lut[0], s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
+            else if (WANT_ACGT && lane == 0) { acgt[4 * q] = acgt[4 * q + 1] = acgt[4 * q + 2] = acgt[4 * q + 3] = 0; }
+        }
+        d0 = d1; d1 = d2; r0 = r1;
     }
 }
 
