@@ -94,7 +94,7 @@ extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
     for (int i = 0; i < FXG_PROF_SLOTS; ++i)
         for (int j = 0; j < 2; ++j) if (c->prof_ev[i][j]) cudaEventDestroy(c->prof_ev[i][j]);
     c->tile_desc.release(); c->row_tmp.release(); c->rows.release();
-    c->counters.release(); c->plan.release(); c->misc.release();
+    c->counters.release(); c->plan.release(); c->misc.release(); c->stage_file.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -348,34 +348,46 @@ extern "C" void fxg_dev_free(void *d) {
 }
 
 // ---- one-call host-buffer index builds (end-to-end path) ------------------------------------------
+// The device copy lives in a context-owned, grow-only buffer: repeated builds do not pay
+// cudaMalloc / cudaFree of a multi-gigabyte buffer every call.
+static int stage_into_ctx(fxg_ctx *c, const void *host_buf, int64_t nbytes, fxg_file *view) {
+    FXG_CUDA(cudaSetDevice(c->device));
+    const int64_t cap = fxg_round_up(nbytes + 1, FXG_FILE_PAD) + FXG_FILE_PAD;
+    int rc = c->stage_file.reserve((size_t)cap);
+    if (rc) return rc;
+    view->d = (uint8_t *)c->stage_file.ptr;
+    view->size = nbytes; view->capacity = cap; view->owned = false; view->device = c->device;
+    const int64_t pad_from = nbytes & ~(int64_t)15;
+    FXG_CUDA(cudaMemsetAsync(view->d + pad_from, 0, (size_t)(cap - pad_from), c->stream));
+    return fxg_file_upload(c, view, 0, host_buf, nbytes);
+}
+
 extern "C" int fxg_fasta_build_index_host(fxg_ctx *c, const void *host_buf, int64_t nbytes, int flags,
                                           fxg_fasta_row *rows, int64_t rows_cap, fxg_scan_stats *stats) {
     FXG_CHECK_ARG(c && stats && (host_buf || nbytes == 0), "bad arguments");
-    fxg_file *f = nullptr;
-    int rc = fxg_file_from_host(c, host_buf, nbytes, &f);
+    fxg_file f;
+    int rc = stage_into_ctx(c, host_buf, nbytes, &f);
     if (rc) return rc;
     fxg_fasta_row *d_rows = nullptr;
-    rc = fxg_fasta_scan(c, f, 0, flags, &d_rows, stats);
+    rc = fxg_fasta_scan(c, &f, 0, flags, &d_rows, stats);
     if (rc == FXG_OK) {
         if (stats->n_rows > rows_cap) { fxg_set_error("rows_cap %lld < n_rows %lld", (long long)rows_cap, (long long)stats->n_rows); rc = FXG_ECAP; }
         else rc = fxg_rows_download(c, d_rows, stats->n_rows, (int)sizeof(fxg_fasta_row), rows);
     }
-    fxg_file_free(f);
     return rc;
 }
 
 extern "C" int fxg_fastq_build_index_host(fxg_ctx *c, const void *host_buf, int64_t nbytes,
                                           fxg_fastq_row *rows, int64_t rows_cap, fxg_scan_stats *stats) {
     FXG_CHECK_ARG(c && stats && (host_buf || nbytes == 0), "bad arguments");
-    fxg_file *f = nullptr;
-    int rc = fxg_file_from_host(c, host_buf, nbytes, &f);
+    fxg_file f;
+    int rc = stage_into_ctx(c, host_buf, nbytes, &f);
     if (rc) return rc;
     fxg_fastq_row *d_rows = nullptr;
-    rc = fxg_fastq_scan(c, f, 0, 0, &d_rows, stats);
+    rc = fxg_fastq_scan(c, &f, 0, 0, &d_rows, stats);
     if (rc == FXG_OK) {
         if (stats->n_rows > rows_cap) { fxg_set_error("rows_cap %lld < n_rows %lld", (long long)rows_cap, (long long)stats->n_rows); rc = FXG_ECAP; }
         else rc = fxg_rows_download(c, d_rows, stats->n_rows, (int)sizeof(fxg_fastq_row), rows);
     }
-    fxg_file_free(f);
     return rc;
 }

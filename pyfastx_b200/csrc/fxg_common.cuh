@@ -53,7 +53,7 @@ struct fxg_ctx {
     size_t       pinned_bytes = 0;
     cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
     // scan scratch
-    FxgScratch   tile_desc, row_tmp, rows, counters, plan, misc;
+    FxgScratch   tile_desc, row_tmp, rows, counters, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small
     // measurement hooks
     bool         profiling = false;
