@@ -211,6 +211,23 @@ int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows,
                    const int64_t *ids, int64_t nq, int32_t flags,
                    int64_t *out_off_host, uint8_t *seq_host, uint8_t *qual_host, int64_t out_cap);
 
+/* ---- K6: BGZF (block-gzip) inputs: member table on the host, member-parallel inflate on the GPU ----
+ * Replaces zlib's gzread during the scan (src/kseq.c:70), the second full inflate pass that builds
+ * the zran checkpoints (zran_build_index, src/index.c:381-387) and zran_seek + zran_read per random
+ * access (src/index.c:685-686, src/read.c:39-40): the whole file is inflated once into HBM (one
+ * warp per <= 64 KiB member) and every later access works on the uncompressed bytes.
+ * fxg_bgzf_members_host walks the member headers only ('BC' extra field, ISIZE trailer); cmp_off
+ * and ucmp_off receive n_members + 1 entries (pass NULL / cap 0 to just count).  FXG_EFORMAT if the
+ * stream is plain gzip rather than BGZF (the caller then inflates on the host while staging).
+ * d_status receives 0 per good member. */
+int fxg_bgzf_members_host(const void *host_buf, int64_t nbytes, int64_t *cmp_off, int64_t *ucmp_off,
+                          int64_t cap, int64_t *n_members, int64_t *total_uncompressed);
+int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed, const int64_t *d_cmp_off,
+                            const int64_t *d_ucmp_off, int64_t n_members, uint8_t *d_out, int64_t out_cap,
+                            int32_t *d_status);
+int fxg_file_from_bgzf_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, fxg_file **out,
+                            int64_t *n_members_out);
+
 /* ---- synthetic inputs generated directly in HBM (bench / test tooling) -------------------
  * Byte-identical to pyfastx_b200/synth.py.  rec_off has n_records+1 entries (device). */
 int fxg_synth_fasta_dev(fxg_ctx *ctx, uint64_t seed, const int64_t *d_lengths, const int64_t *d_rec_off,

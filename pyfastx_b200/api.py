@@ -11,7 +11,6 @@ of one); there is no CPU extraction path.  The file stays resident in HBM for th
 the object.
 """
 import gzip as _gzip
-import mmap
 import os
 
 import numpy as np
@@ -58,38 +57,42 @@ def reverse_complement(seq):
     return out.tobytes().decode("latin-1")
 
 
-def _read_host_bytes(path):
-    """(host bytes-like, is_gzip).  gzip members are inflated on the host before staging
-    (the GPU inflate of BGZF members is the K6 row of SURVEY.md section 8f, not built yet)."""
-    if gzip_check(path):
-        with _gzip.open(path, "rb") as g:
-            return g.read(), True
-    return None, False
-
-
 class _Staged:
-    """file bytes resident in HBM + a cheap host view for header text"""
+    """file bytes resident in HBM.  Plain files are staged with pinned-chunk copies; BGZF files are
+    inflated on the GPU (one warp per member); other gzip streams are inflated by zlib on the host
+    while staging (a single deflate stream has no independent entry points)."""
 
     def __init__(self, path):
         self.engine = get_engine()
-        host, self.is_gzip = _read_host_bytes(path)
+        self.is_gzip = gzip_check(path)
+        self.bgzf_members = 0
         if self.is_gzip:
-            self.host = memoryview(host)
-            self.dfile = self.engine.stage_bytes(np.frombuffer(host, dtype=np.uint8))
-            self._mm = None
+            with open(path, "rb") as fh:
+                comp = fh.read()
+            try:
+                self.dfile = self.engine.stage_bgzf(np.frombuffer(comp, dtype=np.uint8))
+                self.bgzf_members = self.dfile.n_members
+            except _cabi.FxgError as ex:
+                if ex.code != _cabi.FXG_EFORMAT:
+                    raise
+                self.dfile = self.engine.stage_bytes(np.frombuffer(_gzip.decompress(comp), dtype=np.uint8))
         else:
             self.dfile = self.engine.stage_path(path)
-            self._fh = open(path, "rb")
-            size = os.fstat(self._fh.fileno()).st_size
-            self._mm = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ) if size else None
-            self.host = memoryview(self._mm) if self._mm is not None else memoryview(b"")
 
     def first_non_space(self):
-        for i in range(min(len(self.host), 1 << 20)):
-            c = self.host[i]
+        head = self.dfile.download(0, min(self.dfile.size, 1 << 16))
+        for c in head.tolist():
             if c not in (9, 10, 11, 12, 13, 32):
                 return c
         return None
+
+    def ranges(self, offsets, lengths):
+        """list of bytes objects for the given file ranges (batched GPU gather)"""
+        if len(offsets) == 0:
+            return []
+        buf, off = self.engine.gather_ranges(self.dfile, offsets, lengths)
+        raw = buf.tobytes()
+        return [raw[off[i]:off[i + 1]] for i in range(len(offsets))]
 
     def close(self):
         try:
@@ -144,17 +147,14 @@ class Fasta:
         else:
             eng = self._st.engine
             rows, st = eng.fasta_scan(self._st.dfile, full_name=self.full_name)
-            host = self._st.host
+            name_off = rows["boff"] - rows["elen"].astype(np.int64) - rows["dlen"]
             if self.key_func is None:
-                names = [bytes(host[int(r["boff"]) - int(r["elen"]) - int(r["dlen"]):][:int(r["nlen"])]) for r in rows]
+                names = self._st.ranges(name_off, rows["nlen"].astype(np.int64))
             else:
                 # key_func receives the header text after '>' exactly as the reference passes it
                 # (NUL-terminated line, i.e. including a trailing '\r'), src/index.c:304-318
-                names = []
-                for r in rows:
-                    a = int(r["boff"]) - int(r["elen"]) - int(r["dlen"])
-                    hdr = bytes(host[a:a + int(r["dlen"]) + int(r["elen"]) - 1]).decode("latin-1")
-                    names.append(str(self.key_func(hdr)).encode("utf-8"))
+                hdrs = self._st.ranges(name_off, rows["dlen"].astype(np.int64) + rows["elen"].astype(np.int64) - 1)
+                names = [str(self.key_func(h.decode("latin-1"))).encode("utf-8") for h in hdrs]
             self._rows, self._total = rows, int(st["total_len"])
             self._con = fxi.write_fasta_index(self.index_file, rows, names, self._total)
             self._names = [fxi._text(b) for b in names]
@@ -546,8 +546,7 @@ class Fastq:
         else:
             eng = self._st.engine
             rows, st = eng.fastq_scan(self._st.dfile)
-            host = self._st.host
-            names = [bytes(host[int(r["soff"]) - int(r["dlen"]):][:int(r["nlen"])]) for r in rows]
+            names = self._st.ranges(rows["soff"] - rows["dlen"], rows["nlen"].astype(np.int64))
             self._rows = rows
             self._counts = st["n_lines"] // 4
             self.size = int(st["total_len"])

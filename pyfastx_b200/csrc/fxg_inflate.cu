@@ -1,0 +1,406 @@
+// fxg_inflate.cu -- K6: BGZF member-parallel DEFLATE decoding on the GPU (sm_100a).
+//
+// Replaces, for block-gzipped inputs, the reference's zlib read side: gzread during the index scan
+// (src/kseq.c:70) and zran_seek + zran_read per random access (src/index.c:685-686,
+// src/read.c:39-40).  A BGZF file is a series of independent gzip members (<= 64 KiB of output
+// each) whose sizes are in the 'BC' extra field, so
+//   * the host walks the member headers (no inflation) and gets, per member, the compressed range
+//     and -- from the ISIZE trailer -- the uncompressed offset: this is the checkpoint table that
+//     zran would have to inflate the whole file for (src/index.c:381-387);
+//   * one WARP per member inflates it straight into its slot of the uncompressed HBM buffer;
+//   * the K1/K2 scans and K3/K5 gathers then run on that buffer exactly as for plain files.
+// Lane 0 runs the (inherently serial) Huffman symbol loop with 10-bit / 9-bit primary lookup tables
+// in shared memory built by all lanes; LZ77 matches are copied by the whole warp.
+// Plain (non-BGZF) gzip streams are not handled here (no independent entry points without a
+// previous serial pass); the host layer inflates those while staging.
+#include "fxg_common.cuh"
+#include <string.h>
+
+namespace fxg {
+
+constexpr int IW = 8;                 // warps (members in flight) per CTA
+constexpr int LIT_BITS = 10, DIST_BITS = 9;
+
+struct __align__(8) WarpTables {
+    uint16_t lit[1 << LIT_BITS];      // (len << 9) | symbol, 0 = code longer than LIT_BITS
+    uint16_t dist[1 << DIST_BITS];    // (len << 5) | symbol
+    uint16_t litcnt[16], litsym[288];     // canonical tables for the slow path (long codes)
+    uint16_t distcnt[16], distsym[32];
+    uint8_t  lens[320];
+};
+
+struct BitReader {
+    const uint8_t *in;
+    int64_t pos, end;      // next byte to load / one past the member's deflate data
+    uint64_t buf;
+    int nbits;
+    __device__ __forceinline__ void refill() {
+        while (nbits <= 56) {
+            const uint64_t b = pos < end ? in[pos] : 0;
+            ++pos;
+            buf |= b << nbits;
+            nbits += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    __device__ __forceinline__ void drop(int n) { buf >>= n; nbits -= n; }
+    __device__ __forceinline__ uint32_t get(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }
+    __device__ __forceinline__ bool overrun() const { return pos - (nbits >> 3) > end; }
+};
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t v, int n) { return __brev(v) >> (32 - n); }
+
+// canonical slow decode (one bit at a time) -- only for codes longer than the primary table
+__device__ int slow_decode(BitReader &br, const uint16_t *cnt, const uint16_t *sym) {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)br.get(1);
+        const int count = cnt[len];
+        if (code - count < first) return sym[index + (code - first)];
+        index += count;
+        first += count;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+// Build primary + canonical tables for `n` symbols with code lengths lens[0..n) (all lanes).
+// Returns false on an over-subscribed code.
+__device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_bits, int sym_shift, uint16_t *cnt,
+                            uint16_t *sym, int lane) {
+    // counts / offsets by lane 0 (n <= 288)
+    int ok = 1;
+    if (lane == 0) {
+        for (int i = 0; i < 16; ++i) cnt[i] = 0;
+        for (int i = 0; i < n; ++i) cnt[lens[i]]++;
+        int left = 1;
+        for (int len = 1; len <= 15; ++len) {
+            left <<= 1;
+            left -= cnt[len];
+            if (left < 0) ok = 0;
+        }
+        int offs[16];
+        offs[1] = 0;
+        for (int len = 1; len < 15; ++len) offs[len + 1] = offs[len] + cnt[len];
+        for (int i = 0; i < n; ++i)
+            if (lens[i]) sym[offs[lens[i]]++] = (uint16_t)i;
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    __syncwarp();
+    for (int i = lane; i < (1 << tab_bits); i += 32) tab[i] = 0;
+    __syncwarp();
+    // canonical codes: first code of each length
+    int next[16];
+    {
+        int code = 0;
+        next[0] = 0;
+        const int c0 = cnt[0];
+        (void)c0;
+        for (int len = 1; len <= 15; ++len) {
+            code = (code + (len > 1 ? cnt[len - 1] : 0)) << 1;
+            next[len] = code;
+        }
+    }
+    // symbols are stored in `sym` grouped by length in increasing symbol order: entry k of length len has
+    // code next[len] + k
+    int base = 0;
+    for (int len = 1; len <= tab_bits; ++len) {
+        const int c = cnt[len];
+        for (int k = lane; k < c; k += 32) {
+            const int s = sym[base + k];
+            const uint32_t code = (uint32_t)(next[len] + k);
+            const uint32_t r = bitrev(code, len);
+            const uint16_t e = (uint16_t)((len << sym_shift) | s);
+            for (uint32_t j = r; j < (1u << tab_bits); j += (1u << len)) tab[j] = e;
+        }
+        base += c;
+    }
+    __syncwarp();
+    return ok != 0;
+}
+
+__constant__ uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// status codes per member: 0 ok, >0 error class
+enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_OVERRUN = 4, INF_SIZE = 5 };
+
+__global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restrict__ in, int64_t in_size,
+                                                         const int64_t *__restrict__ cmp_off,
+                                                         const int64_t *__restrict__ ucmp_off, int64_t n_members,
+                                                         uint8_t *__restrict__ out, int64_t out_cap,
+                                                         int32_t *__restrict__ status) {
+    __shared__ WarpTables tabs[IW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpTables &T = tabs[warp];
+    const int64_t nwarps = (int64_t)gridDim.x * IW;
+    for (int64_t m = (int64_t)blockIdx.x * IW + warp; m < n_members; m += nwarps) {
+        const int64_t c0 = cmp_off[m], c1 = cmp_off[m + 1];
+        const int64_t o0 = ucmp_off[m], o1 = ucmp_off[m + 1];
+        int err = INF_OK;
+        // ---- gzip member header: 10 fixed bytes, FEXTRA (BGZF always), optional name/comment/crc ----
+        int64_t p = c0;
+        if (c1 - c0 < 18 + 8 || c1 > in_size || in[p] != 0x1f || in[p + 1] != 0x8b || in[p + 2] != 8) err = INF_BAD_HEADER;
+        if (!err) {
+            const int flg = in[p + 3];
+            p += 10;
+            if (flg & 4) { const int xlen = in[p] | (in[p + 1] << 8); p += 2 + xlen; }
+            if (flg & 8) { while (p < c1 && in[p]) ++p; ++p; }
+            if (flg & 16) { while (p < c1 && in[p]) ++p; ++p; }
+            if (flg & 2) p += 2;
+            if (p > c1 - 8) err = INF_BAD_HEADER;
+        }
+        BitReader br;
+        br.in = in; br.pos = p; br.end = c1 - 8; br.buf = 0; br.nbits = 0;
+        int64_t opos = o0;
+        bool last = false;
+        while (!err && !last) {
+            // ---- block header (lane 0 reads, everyone follows) -----------------------------------------
+            int btype = 0, hlit = 0, hdist = 0;
+            if (lane == 0) {
+                last = br.get(1) != 0;
+                btype = (int)br.get(2);
+                if (btype == 0) {
+                    br.drop(br.nbits & 7);                       // to a byte boundary
+                    const uint32_t len = br.get(16), nlen = br.get(16);
+                    if ((len ^ 0xffffu) != nlen) err = INF_BAD_BLOCK;
+                    hlit = (int)len;
+                } else if (btype == 2) {
+                    hlit = (int)br.get(5) + 257;
+                    hdist = (int)br.get(5) + 1;
+                    const int hclen = (int)br.get(4) + 4;
+                    if (hlit > 286 || hdist > 30) err = INF_BAD_BLOCK;
+                    // code-length code
+                    uint8_t cl[19];
+                    for (int i = 0; i < 19; ++i) cl[i] = 0;
+                    for (int i = 0; i < hclen; ++i) cl[CL_ORDER[i]] = (uint8_t)br.get(3);
+                    // tiny canonical decoder for the 19-symbol code, bit by bit
+                    uint16_t ccnt[8], csym[19];
+                    for (int i = 0; i < 8; ++i) ccnt[i] = 0;
+                    for (int i = 0; i < 19; ++i) ccnt[cl[i]]++;
+                    int offs[8];
+                    offs[1] = 0;
+                    for (int i = 1; i < 7; ++i) offs[i + 1] = offs[i] + ccnt[i];
+                    for (int i = 0; i < 19; ++i)
+                        if (cl[i]) csym[offs[cl[i]]++] = (uint16_t)i;
+                    int idx = 0;
+                    while (!err && idx < hlit + hdist) {
+                        int code = 0, first = 0, index = 0, sym = -1;
+                        for (int len = 1; len <= 7; ++len) {
+                            code |= (int)br.get(1);
+                            const int count = ccnt[len];
+                            if (code - count < first) { sym = csym[index + (code - first)]; break; }
+                            index += count; first += count; first <<= 1; code <<= 1;
+                        }
+                        if (sym < 0) { err = INF_BAD_CODE; break; }
+                        if (sym < 16) T.lens[idx++] = (uint8_t)sym;
+                        else {
+                            int rep, val = 0;
+                            if (sym == 16) { if (idx == 0) { err = INF_BAD_CODE; break; } val = T.lens[idx - 1]; rep = 3 + (int)br.get(2); }
+                            else if (sym == 17) rep = 3 + (int)br.get(3);
+                            else rep = 11 + (int)br.get(7);
+                            if (idx + rep > hlit + hdist) { err = INF_BAD_CODE; break; }
+                            while (rep--) T.lens[idx++] = (uint8_t)val;
+                        }
+                    }
+                    if (!err && T.lens[256] == 0) err = INF_BAD_CODE;
+                } else if (btype == 3) err = INF_BAD_BLOCK;
+                if (br.overrun()) err = INF_OVERRUN;
+            }
+            err = __shfl_sync(0xffffffffu, err, 0);
+            btype = __shfl_sync(0xffffffffu, btype, 0);
+            hlit = __shfl_sync(0xffffffffu, hlit, 0);
+            hdist = __shfl_sync(0xffffffffu, hdist, 0);
+            last = __shfl_sync(0xffffffffu, (int)last, 0) != 0;
+            if (err) break;
+            if (btype == 0) {
+                // ---- stored block: warp-wide byte copy ------------------------------------------------------
+                int64_t src = 0;
+                if (lane == 0) { src = br.pos - (br.nbits >> 3); }
+                src = shfl_i64(src, 0);
+                const int len = hlit;
+                if (src + len > c1 - 8 || opos + len > o1 || opos + len > out_cap) { err = INF_OVERRUN; break; }
+                for (int i = lane; i < len; i += 32) out[opos + i] = in[src + i];
+                opos += len;
+                if (lane == 0) { br.pos = src + len; br.buf = 0; br.nbits = 0; }
+                __syncwarp();
+                continue;
+            }
+            // ---- Huffman tables (fixed or dynamic) ---------------------------------------------------------
+            if (btype == 1) {
+                for (int i = lane; i < 288; i += 32) T.lens[i] = (uint8_t)(i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8)));
+                for (int i = lane; i < 30; i += 32) T.lens[288 + i] = 5;
+                hlit = 288; hdist = 30;
+            }
+            __syncwarp();
+            bool ok = build_table(T.lens, hlit, T.lit, LIT_BITS, 9, T.litcnt, T.litsym, lane);
+            ok = build_table(T.lens + hlit, hdist, T.dist, DIST_BITS, 5, T.distcnt, T.distsym, lane) && ok;
+            // an incomplete distance code with a single symbol is legal; over-subscription is not
+            if (!ok) { err = INF_BAD_CODE; break; }
+            // ---- symbol loop: lane 0 decodes literals until a match / end of block, matches are copied by
+            //      the whole warp ---------------------------------------------------------------------------------
+            bool eob = false;
+            while (!eob && !err) {
+                int mlen = 0, mdist = 0;
+                if (lane == 0) {
+                    while (true) {
+                        br.refill();
+                        int sym;
+                        const uint16_t e = T.lit[br.peek(LIT_BITS)];
+                        if (e) { br.drop(e >> 9); sym = e & 511; }
+                        else sym = slow_decode(br, T.litcnt, T.litsym);
+                        if (sym < 0) { err = INF_BAD_CODE; break; }
+                        if (sym < 256) {
+                            if (opos >= o1 || opos >= out_cap) { err = INF_OVERRUN; break; }
+                            out[opos++] = (uint8_t)sym;
+                            continue;
+                        }
+                        if (sym == 256) { eob = true; break; }
+                        sym -= 257;
+                        if (sym >= 29) { err = INF_BAD_CODE; break; }
+                        br.refill();
+                        mlen = LEN_BASE[sym] + (int)br.peek(LEN_EXTRA[sym]);
+                        br.drop(LEN_EXTRA[sym]);
+                        br.refill();
+                        int ds;
+                        const uint16_t de = T.dist[br.peek(DIST_BITS)];
+                        if (de) { br.drop(de >> 5); ds = de & 31; }
+                        else ds = slow_decode(br, T.distcnt, T.distsym);
+                        if (ds < 0 || ds >= 30) { err = INF_BAD_CODE; break; }
+                        br.refill();
+                        mdist = DIST_BASE[ds] + (int)br.peek(DIST_EXTRA[ds]);
+                        br.drop(DIST_EXTRA[ds]);
+                        if (mdist > opos - o0) { err = INF_BAD_CODE; break; }        // BGZF members are self-contained
+                        if (opos + mlen > o1 || opos + mlen > out_cap) { err = INF_OVERRUN; break; }
+                        break;
+                    }
+                    if (br.overrun()) err = INF_OVERRUN;
+                }
+                __syncwarp();
+                err = __shfl_sync(0xffffffffu, err, 0);
+                eob = __shfl_sync(0xffffffffu, (int)eob, 0) != 0;
+                mlen = __shfl_sync(0xffffffffu, mlen, 0);
+                mdist = __shfl_sync(0xffffffffu, mdist, 0);
+                opos = shfl_i64(opos, 0);
+                if (err || eob) break;
+                if (mlen > 0) {
+                    __threadfence_block();
+                    const int64_t src = opos - mdist;
+                    for (int i = lane; i < mlen; i += 32) out[opos + i] = out[src + (mdist >= mlen ? i : i % mdist)];
+                    opos += mlen;
+                    __syncwarp();
+                }
+            }
+        }
+        if (!err && opos != o1) err = INF_SIZE;
+        if (lane == 0) status[m] = err;
+        __syncwarp();
+    }
+}
+
+}  // namespace fxg
+
+using namespace fxg;
+
+// Host: walk the BGZF member headers.  cmp_off / ucmp_off receive n_members + 1 entries.
+// Replaces the SECOND full inflate pass the reference needs to build its random-access
+// checkpoints (zran_build_index, src/index.c:381-387): BGZF carries the member sizes in the headers.
+extern "C" int fxg_bgzf_members_host(const void *host_buf, int64_t nbytes, int64_t *cmp_off, int64_t *ucmp_off,
+                                     int64_t cap, int64_t *n_members, int64_t *total_uncompressed) {
+    FXG_CHECK_ARG(host_buf && n_members && total_uncompressed && nbytes >= 0, "bad arguments");
+    const uint8_t *b = (const uint8_t *)host_buf;
+    int64_t p = 0, n = 0, u = 0;
+    while (p < nbytes) {
+        if (nbytes - p < 18 || b[p] != 0x1f || b[p + 1] != 0x8b || b[p + 2] != 8 || !(b[p + 3] & 4)) {
+            fxg_set_error("not a BGZF member at offset %lld", (long long)p);
+            return FXG_EFORMAT;
+        }
+        const int xlen = b[p + 10] | (b[p + 11] << 8);
+        int64_t q = p + 12, xe = p + 12 + xlen;
+        int64_t bsize = -1;
+        while (q + 4 <= xe && xe <= nbytes) {
+            const int slen = b[q + 2] | (b[q + 3] << 8);
+            if (b[q] == 'B' && b[q + 1] == 'C' && slen == 2 && q + 6 <= xe) bsize = (b[q + 4] | (b[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        if (bsize < 0 || p + bsize > nbytes || bsize < xlen + 20) {
+            fxg_set_error("gzip member without a valid BGZF 'BC' field at offset %lld", (long long)p);
+            return FXG_EFORMAT;
+        }
+        const uint8_t *t = b + p + bsize - 4;
+        const int64_t isize = (int64_t)t[0] | ((int64_t)t[1] << 8) | ((int64_t)t[2] << 16) | ((int64_t)t[3] << 24);
+        if (n < cap) {
+            if (cmp_off) cmp_off[n] = p;
+            if (ucmp_off) ucmp_off[n] = u;
+        }
+        ++n;
+        p += bsize;
+        u += isize;
+    }
+    if (n < cap) {
+        if (cmp_off) cmp_off[n] = p;
+        if (ucmp_off) ucmp_off[n] = u;
+    }
+    *n_members = n;
+    *total_uncompressed = u;
+    return n + 1 <= cap || (!cmp_off && !ucmp_off) ? FXG_OK : FXG_ECAP;
+}
+
+extern "C" int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed, const int64_t *d_cmp_off,
+                                       const int64_t *d_ucmp_off, int64_t n_members, uint8_t *d_out, int64_t out_cap,
+                                       int32_t *d_status) {
+    FXG_CHECK_ARG(ctx && compressed && n_members >= 0, "bad arguments");
+    if (n_members == 0) return FXG_OK;
+    FXG_CHECK_ARG(d_cmp_off && d_ucmp_off && d_out && d_status, "null device pointer");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    int64_t blocks = (n_members + IW - 1) / IW;
+    const int64_t maxb = (int64_t)ctx->sm_count * 6;
+    if (blocks > maxb) blocks = maxb;
+    FxgProfScope prof(ctx, FXG_PROF_GATHER);
+    inflate_kernel<<<(unsigned)blocks, IW * 32, 0, ctx->stream>>>(compressed->d, compressed->size, d_cmp_off, d_ucmp_off,
+                                                                  n_members, d_out, out_cap, d_status);
+    FXG_CUDA(cudaGetLastError());
+    return FXG_OK;
+}
+
+// Host-buffer convenience: BGZF bytes in host memory -> uncompressed fxg_file resident in HBM.
+extern "C" int fxg_file_from_bgzf_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, fxg_file **out,
+                                       int64_t *n_members_out) {
+    FXG_CHECK_ARG(ctx && host_buf && out, "bad arguments");
+    *out = nullptr;
+    int64_t n = 0, total = 0;
+    int rc = fxg_bgzf_members_host(host_buf, nbytes, nullptr, nullptr, 0, &n, &total);
+    if (rc) return rc;
+    int64_t *tab = (int64_t *)malloc((size_t)(n + 1) * 2 * sizeof(int64_t));
+    if (!tab) { fxg_set_error("out of host memory"); return FXG_ENOMEM; }
+    rc = fxg_bgzf_members_host(host_buf, nbytes, tab, tab + n + 1, n + 1, &n, &total);
+    fxg_file *cf = nullptr, *uf = nullptr;
+    void *d_tab = nullptr;
+    int32_t *d_status = nullptr;
+    int32_t *h_status = nullptr;
+    if (!rc) rc = fxg_file_from_host(ctx, host_buf, nbytes, &cf);
+    if (!rc) rc = fxg_file_alloc(ctx, total, &uf);
+    if (!rc) rc = fxg_rows_upload(ctx, tab, (n + 1) * 2, (int)sizeof(int64_t), &d_tab);
+    if (!rc && cudaMalloc((void **)&d_status, (size_t)(n + 1) * sizeof(int32_t)) != cudaSuccess) { fxg_set_error("cudaMalloc failed"); rc = FXG_ENOMEM; }
+    if (!rc) rc = fxg_inflate_members_dev(ctx, cf, (const int64_t *)d_tab, (const int64_t *)d_tab + n + 1, n, uf->d, total, d_status);
+    if (!rc) {
+        h_status = (int32_t *)malloc((size_t)(n + 1) * sizeof(int32_t));
+        cudaError_t e = cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { fxg_set_error("inflate failed: %s", cudaGetErrorString(e)); rc = FXG_ECUDA; }
+        for (int64_t i = 0; !rc && i < n; ++i)
+            if (h_status[i]) { fxg_set_error("BGZF member %lld is corrupt (inflate status %d)", (long long)i, h_status[i]); rc = FXG_EFORMAT; }
+    }
+    free(tab); free(h_status);
+    if (d_tab) cudaFree(d_tab);
+    if (d_status) cudaFree(d_status);
+    if (cf) fxg_file_free(cf);
+    if (rc) { if (uf) fxg_file_free(uf); return rc; }
+    *out = uf;
+    if (n_members_out) *n_members_out = n;
+    return FXG_OK;
+}

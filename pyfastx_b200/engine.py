@@ -117,6 +117,32 @@ class Engine:
         self.sync()
         return DeviceFile(self, h)
 
+    def stage_bgzf(self, data):
+        """BGZF bytes (host) -> uncompressed DeviceFile, inflated member-parallel on the GPU (K6).
+        Raises FxgError(FXG_EFORMAT) if the stream is plain gzip rather than BGZF."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        h = C.c_void_p()
+        nm = C.c_int64(0)
+        check(lib().fxg_file_from_bgzf_host(self.ctx, a.ctypes.data, a.size, C.byref(h), C.byref(nm)))
+        f = DeviceFile(self, h)
+        f.n_members = nm.value
+        return f
+
+    def gather_ranges(self, dfile, offsets, lengths):
+        """raw byte ranges of the resident file (e.g. record names) -> (packed uint8, offsets[n+1])"""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        rows = np.zeros(offsets.size, dtype=FASTQ_ROW)
+        rows["soff"] = offsets
+        rows["qoff"] = offsets
+        rows["rlen"] = lengths
+        d = self.upload_rows(rows)
+        try:
+            seq, _, off = self.reads(dfile, d, np.arange(offsets.size, dtype=np.int64), want_qual=False, rlens=lengths)
+        finally:
+            d.free()
+        return seq, off
+
     def stage_path(self, path):
         h = C.c_void_p()
         check(lib().fxg_file_from_path(self.ctx, os.fsencode(path), C.byref(h)))
