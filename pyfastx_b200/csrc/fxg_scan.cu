@@ -169,44 +169,40 @@ struct ScanParams {
     unsigned long long *dbg; // optional cycle counters (FXG_SCAN_DEBUG=1)
 };
 
-// Per-CTA roles (warp specialisation):
-//   warps 0..7  "workers": phase A of tile i (as soon as its TMA load lands) then phase C of
-//               tile i-1.  They never spin on other CTAs.
-//   warp  8     "prefix warp": takes each tile's aggregate from a mailbox, publishes it, runs the
-//               decoupled look-back and hands the exclusive prefix (+ the two preceding newline
-//               positions) back.  Its waiting overlaps phase A of the next tile, and -- crucially --
-//               a tile's aggregate is published a fixed, short time after the tile was claimed,
-//               never behind another tile's look-back.
-constexpr int WORKERS = THREADS;            // 256 worker threads
-constexpr int CTA_THREADS = THREADS + 32;   // + prefix warp
+// Per-CTA roles (warp specialisation).  All hand-offs are mbarriers on a ring of RING tile slots; no
+// role ever executes another role's code, so the instruction cost of a tile is the sum of
+//   16 byte warps   phase A only: newline masks of their 1 KiB region -> ordered entries in the slot
+//    1 publisher    16 per-warp counts -> tile aggregate, published for the other CTAs
+//    1 prefix warp  decoupled look-back (the only code that waits on other CTAs)
+//    1 producer     claims tiles in file order and issues their TMA loads as ring slots free up
+//    4 line warps   phase C: one thread per line, for the (few) lines of a tile
+// and byte warps stream tile after tile without ever waiting for a look-back.
+constexpr int NBYTE = NWARPS;                  // 16 byte warps
+constexpr int NLINE = 4;                       // line warps
+constexpr int W_PUB = NBYTE, W_PREF = NBYTE + 1, W_PROD = NBYTE + 2, W_LINE0 = NBYTE + 3;
+constexpr int CTA_THREADS = (NBYTE + 3 + NLINE) * 32;
+constexpr int LINE_THREADS = NLINE * 32;
+constexpr int RING = 5;                        // tile slots (stage buffer + metadata) in flight per CTA
+constexpr int SEG_PER_LINE_WARP = NBYTE / NLINE;
 
-struct Mail {           // workers -> prefix warp (per pipeline slot)
-    int64_t  t;         // tile id, -1 = no more tiles
-    uint32_t tsh, pad;
-};
-struct Pref {           // prefix warp -> workers
+struct Pref {           // prefix warp -> line warps
     uint64_t ex_nl, ex_hdr;
     int64_t  cpos[2];   // the two newlines preceding the tile: [1] = nearest, [0] = the one before (NOPOS if none)
     uint32_t cflag[2];  // bit31: the line starting after that newline begins with '>' ; low bits: header count (only [1])
     uint32_t pad[2];
 };
-struct Slot {           // everything phase C needs about a tile whose phase A has run
-    uint16_t seg_pos[NWARPS][SEGCAP];    // per-warp newline positions (tile relative), file order
-    uint16_t seg_flag[NWARPS][SEGCAP];   // bit15: next line starts with '>', low bits: warp-local inclusive header count
-    uint32_t wcnt[NWARPS];               // per warp: newlines | header starts << 16
-    uint32_t wstart[NWARPS];             // exclusive prefix of wcnt (filled by warp 0 in phase A)
-    int      T_nl, pad0;                 // newlines in the tile
-    Mail     mail;
+struct Slot {           // metadata of one tile in flight
+    uint16_t seg_pos[NBYTE][SEGCAP];     // per byte-warp newline positions (tile relative), file order
+    uint16_t seg_flag[NBYTE][SEGCAP];    // bit15: next line starts with '>', low bits: warp-local inclusive header count
+    uint32_t wcnt[NBYTE];                // per warp: newlines | header starts << 16
+    uint32_t wstart[NBYTE];              // exclusive prefix of wcnt (publisher)
+    int64_t  tile;                       // tile id, -1 = no more tiles
+    int      T_nl, dense;                // newlines in the tile; some warp overflowed its segment
+    uint32_t tsh, pad0;                  // the tile's first byte starts a header line
     Pref     pref;
 };
 
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
-// worker barrier that also ORs a predicate over all workers (bar.red)
-__device__ __forceinline__ bool worker_bar_or(bool p) {
-    int r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\tbar.red.or.pred q, 1, %2, p;\n\tselp.b32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"((int)p), "n"(WORKERS) : "memory");
-    return r != 0;
-}
+__device__ __forceinline__ void line_bar() { asm volatile("bar.sync 2, %0;" ::"n"(LINE_THREADS) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -242,14 +238,15 @@ __device__ __forceinline__ int64_t find_first_of2(const uint8_t *h, int64_t limi
 template <int MODE>   // 0 = FASTA, 1 = FASTQ
 __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P) {
     extern __shared__ __align__(128) uint8_t dyn_smem[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ __align__(8) uint64_t mail_bar[NSLOT];
-    __shared__ __align__(8) uint64_t pref_bar[NSLOT];
-    __shared__ int64_t  s_tile[STAGES];
-    __shared__ __align__(16) Slot slots[NSLOT];
-    __shared__ int64_t  l_pos[LB + 2];       // compacted line list of the tile in phase C ([0],[1] = carry)
+    __shared__ __align__(8) uint64_t full_bar[RING];   // TMA data landed            (tx)    -> byte warps
+    __shared__ __align__(8) uint64_t fill_bar[RING];   // byte warps wrote the slot   (16)    -> publisher
+    __shared__ __align__(8) uint64_t mail_bar[RING];   // aggregate published         (1)     -> prefix warp
+    __shared__ __align__(8) uint64_t pref_bar[RING];   // exclusive prefix ready      (1)     -> line warps
+    __shared__ __align__(8) uint64_t free_bar[RING];   // line warps done             (NLINE) -> TMA issuer
+    __shared__ __align__(16) Slot slots[RING];
+    __shared__ int64_t  l_pos[LB + 2];       // dense path only: line list of the tile ([0],[1] = carry)
     __shared__ uint32_t l_flag[LB + 2];
-    __shared__ uint32_t s_scan[NWARPS];      // dense path block scan
+    __shared__ uint32_t s_scan[NLINE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -259,13 +256,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
     const bool full_name = (P.flags & FXG_SCAN_FULL_NAME) != 0;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&mail_bar[s], 1); mbar_init(&pref_bar[s], 1); }
+        for (int s = 0; s < RING; ++s) {
+            mbar_init(&full_bar[s], 1); mbar_init(&fill_bar[s], NBYTE); mbar_init(&mail_bar[s], 1);
+            mbar_init(&pref_bar[s], 1); mbar_init(&free_bar[s], NLINE);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto stage_ptr = [&](int it) -> uint8_t * { return dyn_smem + (size_t)(it % STAGES) * STAGE_BYTES + HALO; };
+    auto stage_ptr = [&](int s) -> uint8_t * { return dyn_smem + (size_t)s * STAGE_BYTES + HALO; };
     // byte at buffer-relative position x, given the tile (id t, base) whose stage is tb
     auto byte_at = [&](const uint8_t *tb, int64_t t, int64_t base, int64_t x) -> uint8_t {
         const int64_t r = x - base;
@@ -274,24 +273,250 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
     };
 
     // =========================================================================================
+    // byte warps: phase A, tile after tile
+    // =========================================================================================
+    if (warp < NBYTE) {
+        const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
+        const int lbase = warp * REGION + lane * BPT;              // this thread's BPT contiguous bytes
+        const int rot = (lane / (8 / NCH)) % NCH;                  // chunk rotation: conflict-free LDS.128
+        int s = 0;
+        uint32_t par = 0;
+        for (;;) {
+            mbar_wait(&full_bar[s], par);
+            Slot &sl = slots[s];
+            const int64_t t = sl.tile;
+            if (t < 0) {                                           // no more tiles: pass the baton and leave
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fill_bar[s]);
+                break;
+            }
+            uint8_t *tb = stage_ptr(s);
+            const int64_t base = t * TILE;
+            // the tile that contains EOF: every warp neutralises the bytes past n in its own region and the
+            // owner of position n plants the virtual newline
+            if (base + TILE > n) {
+                for (int x = warp * REGION + lane; x < (warp + 1) * REGION; x += 32)
+                    if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
+                __syncwarp();
+            }
+            // ---------------- phase A ------------------------------------------------------------------
+            uint4 v[NCH];
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) v[j] = *reinterpret_cast<const uint4 *>(tb + lbase + 16 * ((j + rot) % NCH));
+            uint32_t m[NCH];
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) { m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80); cnt += __popc(m[j]); }
+            uint32_t run;         // newlines | header starts << 16 of the whole warp
+            if (!__any_sync(0xffffffffu, cnt > 1)) {
+                int x = 0;
+                uint32_t nh = 0;
+                if (cnt) {
+                    int j = 0;
+                    uint32_t mm = 0;
+#pragma unroll
+                    for (int jj = NCH - 1; jj >= 0; --jj) if (m[jj]) { j = jj; mm = m[jj]; }
+                    x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
+                    if (MODE == 0) nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u;
+                }
+                const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
+                const uint32_t bh = (MODE == 0) ? __ballot_sync(0xffffffffu, nh != 0) : 0u;
+                if (cnt) {
+                    const int wi = __popc(bn & lt_mask);
+                    sl.seg_pos[warp][wi] = (uint16_t)x;
+                    sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | (__popc(bh & lt_mask) + nh));
+                }
+                run = __popc(bn) | (__popc(bh) << 16);
+            } else if (!__any_sync(0xffffffffu, cnt > 2)) {
+                // at most two newlines per thread (e.g. a header line inside the 32 bytes): two ballots
+                int xa = 0x7fffffff, xb = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    if (m[j]) {
+                        const int qoff = lbase + 16 * ((j + rot) % NCH);
+                        const int x1 = qoff + chunk_bit_to_off(__ffs(m[j]) - 1);
+                        if (x1 < xa) { xb = xa; xa = x1; } else if (x1 < xb) xb = x1;
+                        const uint32_t m2 = m[j] & (m[j] - 1);
+                        if (m2) {
+                            const int x2 = qoff + chunk_bit_to_off(__ffs(m2) - 1);
+                            if (x2 < xa) { xb = xa; xa = x2; } else if (x2 < xb) xb = x2;
+                        }
+                    }
+                }
+                uint32_t nha = 0, nhb = 0;
+                if (MODE == 0) {
+                    if (cnt >= 1) nha = (xa + 1 < TILE && base + xa + 1 < n && tb[xa + 1] == '>') ? 1u : 0u;
+                    if (cnt >= 2) nhb = (xb + 1 < TILE && base + xb + 1 < n && tb[xb + 1] == '>') ? 1u : 0u;
+                }
+                const uint32_t bn1 = __ballot_sync(0xffffffffu, cnt >= 1), bn2 = __ballot_sync(0xffffffffu, cnt >= 2);
+                const uint32_t bh1 = (MODE == 0) ? __ballot_sync(0xffffffffu, nha != 0) : 0u;
+                const uint32_t bh2 = (MODE == 0) ? __ballot_sync(0xffffffffu, nhb != 0) : 0u;
+                const int wi = __popc(bn1 & lt_mask) + __popc(bn2 & lt_mask);
+                const uint32_t hcb = __popc(bh1 & lt_mask) + __popc(bh2 & lt_mask);
+                if (cnt >= 1 && wi < SEGCAP) { sl.seg_pos[warp][wi] = (uint16_t)xa; sl.seg_flag[warp][wi] = (uint16_t)((nha << 15) | (hcb + nha)); }
+                if (cnt >= 2 && wi + 1 < SEGCAP) { sl.seg_pos[warp][wi + 1] = (uint16_t)xb; sl.seg_flag[warp][wi + 1] = (uint16_t)((nhb << 15) | (hcb + nha + nhb)); }
+                run = (__popc(bn1) + __popc(bn2)) | ((__popc(bh1) + __popc(bh2)) << 16);
+            } else {
+                // short lines (three or more newlines in some thread's bytes): shuffle scan + ordered
+                // iteration over the masks
+                uint32_t h = 0;
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < NCH; ++j) {
+                        uint32_t mm = m[j];
+                        while (mm) {
+                            const int x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
+                            mm &= mm - 1;
+                            if (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ++h;
+                        }
+                    }
+                }
+                const uint32_t my_cnt = cnt | (h << 16);
+                uint32_t incl = my_cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                run = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t wi = (incl - my_cnt) & 0xffffu, hc = (incl - my_cnt) >> 16;
+                if (cnt && (run & 0xffffu) <= (uint32_t)SEGCAP) {
+#pragma unroll 1
+                    for (int qc = 0; qc < NCH; ++qc) {
+                        const int j = (qc - rot + NCH) % NCH;
+                        uint32_t mq = 0;
+#pragma unroll
+                        for (int jj = 0; jj < NCH; ++jj) if (jj == j) mq = m[jj];
+#pragma unroll 1
+                        for (int w = 0; w < 4; ++w) {                 // byte order: word, then byte
+                            uint32_t mw = mq & (0x80808080u >> w);
+                            while (mw) {
+                                const int x = lbase + 16 * qc + chunk_bit_to_off(__ffs(mw) - 1);
+                                mw &= mw - 1;
+                                uint32_t nh = 0;
+                                if (MODE == 0) { nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
+                                sl.seg_pos[warp][wi] = (uint16_t)x;
+                                sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | hc);
+                                ++wi;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { sl.wcnt[warp] = run; mbar_arrive(&fill_bar[s]); }
+            if (++s == RING) { s = 0; par ^= 1u; }
+        }
+        return;
+    }
+
+    // =========================================================================================
+    // producer: claims tiles in file order and issues their TMA loads as ring slots are released.
+    // A tile is claimed only when its load can start at once, so it is published a short, fixed time
+    // later -- the byte warps never wait for anything but TMA data.
+    // =========================================================================================
+    if (warp == W_PROD) {
+        if (lane == 0) {
+            for (int64_t seq = 0;; ++seq) {
+                const int s = (int)(seq % RING);
+                if (seq >= RING) mbar_wait(&free_bar[s], (uint32_t)(((seq / RING) - 1) & 1));
+                const int64_t t = (int64_t)atomicAdd(P.tile_counter, 1u);
+                uint8_t *buf = dyn_smem + (size_t)s * STAGE_BYTES;
+                bool loaded = false;
+                if (t < P.ntiles) {
+                    slots[s].tile = t;
+                    const int64_t base = t * TILE;
+                    int64_t src = base - HALO, dst = 0, want = STAGE_BYTES;
+                    if (t == 0) { src = 0; dst = HALO; want = TILE; }
+                    int64_t avail = P.capacity - src;
+                    if (avail < want) want = avail > 0 ? (avail & ~(int64_t)15) : 0;
+                    if (want > 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(&full_bar[s], (uint32_t)want);
+                        tma_load_1d(buf + dst, P.file + src, (uint32_t)want, &full_bar[s]);
+                        loaded = true;
+                    }
+                } else {
+                    slots[s].tile = -1;
+                }
+                if (!loaded) mbar_arrive(&full_bar[s]);
+                if (t >= P.ntiles) break;
+            }
+        }
+        return;
+    }
+
+    // =========================================================================================
+    // publisher warp: per-warp counts -> tile aggregate, published for the other CTAs right away
+    // =========================================================================================
+    if (warp == W_PUB) {
+        int s = 0;
+        uint32_t par = 0;
+        for (;;) {
+            mbar_wait(&fill_bar[s], par);
+            Slot &sl = slots[s];
+            const int64_t t = sl.tile;
+            if (t < 0) { if (lane == 0) mbar_arrive(&mail_bar[s]); break; }
+            const int64_t base = t * TILE;
+            const uint8_t *tb = stage_ptr(s);
+            const uint32_t c = lane < NBYTE ? sl.wcnt[lane] : 0u;
+            const bool dense = __any_sync(0xffffffffu, (c & 0xffffu) > (uint32_t)SEGCAP);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < NBYTE; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane < NBYTE) sl.wstart[lane] = incl - c;
+            const uint32_t ttot = __shfl_sync(0xffffffffu, incl, NBYTE - 1);
+            const int T_nl = (int)(ttot & 0xffffu);
+            if (lane == 0) {
+                const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
+                const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
+                const uint32_t T_h = (ttot >> 16) + tsh;
+                int64_t l0 = NOPOS, l1 = NOPOS;
+                if (!dense) {
+                    int found = 0;
+                    for (int w = NBYTE - 1; w >= 0 && found < 2; --w) {
+                        const int cw = (int)(sl.wcnt[w] & 0xffffu);
+                        for (int k = cw - 1; k >= 0 && found < 2; --k) {
+                            const int64_t pp = base + sl.seg_pos[w][k];
+                            if (found == 0) l0 = pp; else l1 = pp;
+                            ++found;
+                        }
+                    }
+                } else {
+                    int found = 0;
+                    for (int x = TILE - 1; x >= 0 && found < 2; --x)
+                        if (tb[x] == '\n') { if (found == 0) l0 = base + x; else l1 = base + x; ++found; }
+                }
+                st_desc(&P.cnt[t], ST_AGG | (uint64_t)T_nl, ST_AGG | (uint64_t)T_h);
+                st_desc(&P.pos[t], T_nl >= 1 ? (uint64_t)(l0 + 2) : 1ull, T_nl >= 2 ? (uint64_t)(l1 + 2) : 1ull);
+                sl.T_nl = T_nl; sl.dense = dense ? 1 : 0; sl.tsh = tsh;
+                mbar_arrive(&mail_bar[s]);
+            }
+            __syncwarp();
+            if (++s == RING) { s = 0; par ^= 1u; }
+        }
+        return;
+    }
+
+    // =========================================================================================
     // prefix warp: decoupled look-back for one tile after the other
     // =========================================================================================
-    if (warp == NWARPS) {
-        int q = 0;
-        uint32_t qpar = 0;
-        for (int it = 0;; ++it) {
-            FXG_DBG(const long long tm0 = clock64();)
-            mbar_wait(&mail_bar[q], qpar);
-            FXG_DBG(if (P.dbg && lane == 0) atomicAdd(&P.dbg[7], (unsigned long long)(clock64() - tm0));)
-            const Mail m = slots[q].mail;
-            if (m.t < 0) break;
-            const int64_t t = m.t, base = t * TILE;
-            const uint8_t *tb = stage_ptr(it);
+    if (warp == W_PREF) {
+        int s = 0;
+        uint32_t par = 0;
+        for (;;) {
+            mbar_wait(&mail_bar[s], par);
+            Slot &sl = slots[s];
+            const int64_t t = sl.tile;
+            if (t < 0) { if (lane == 0) mbar_arrive(&pref_bar[s]); break; }
+            const int64_t base = t * TILE;
+            const uint8_t *tb = stage_ptr(s);
             uint64_t ex_nl = 0, ex_hdr = 0;
             int nwin = 0;
-            FXG_DBG(const long long tl0 = clock64();)
             lookback_counts(P.cnt, t, lane, ex_nl, ex_hdr, nwin);
-            FXG_DBG(if (P.dbg && lane == 0) { atomicAdd(&P.dbg[4], (unsigned long long)(clock64() - tl0)); atomicAdd(&P.dbg[5], (unsigned long long)nwin); atomicAdd(&P.dbg[6], 1ull); })
             if (lane == 0) {
                 const ulonglong2 own = ld_desc(&P.cnt[t]);
                 const uint64_t in_nl = ex_nl + (own.x & ~ST_MASK), in_hdr = ex_hdr + (own.y & ~ST_MASK);
@@ -301,55 +526,34 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                 lookback_positions(P.pos, t, pl, pp, k);
                 uint32_t nh1 = 0, hc1 = 0, nh2 = 0;
                 if (MODE == 0) {
-                    if (pl + 1 == base) { nh1 = m.tsh; hc1 = m.tsh; }
+                    if (pl + 1 == base) { nh1 = sl.tsh; hc1 = sl.tsh; }
                     else nh1 = (byte_at(tb, t, base, pl + 1) == '>') ? 1u : 0u;
                     if (k >= 2) nh2 = (byte_at(tb, t, base, pp + 1) == '>') ? 1u : 0u;
                 }
-                Pref &pr = slots[q].pref;
+                Pref &pr = sl.pref;
                 pr.ex_nl = ex_nl; pr.ex_hdr = ex_hdr;
                 pr.cpos[1] = pl;                    pr.cflag[1] = (nh1 << 31) | hc1;
                 pr.cpos[0] = k >= 2 ? pp : NOPOS;   pr.cflag[0] = (nh2 << 31);
-                mbar_arrive(&pref_bar[q]);
+                mbar_arrive(&pref_bar[s]);
             }
             __syncwarp();
-            if (++q == NSLOT) { q = 0; qpar ^= 1u; }
+            if (++s == RING) { s = 0; par ^= 1u; }
         }
         return;
     }
 
     // =========================================================================================
-    // workers
+    // line warps: phase C
     // =========================================================================================
-    unsigned long long my_size = 0;   // FASTQ: sum of rlen seen by this thread
-
-    auto issue = [&](int st) {
-        const int64_t t = (int64_t)atomicAdd(P.tile_counter, 1u);
-        s_tile[st] = t;
-        uint8_t *buf = dyn_smem + (size_t)st * STAGE_BYTES;
-        if (t < P.ntiles) {
-            const int64_t base = t * TILE;
-            int64_t src = base - HALO, dst = 0, want = STAGE_BYTES;
-            if (t == 0) { src = 0; dst = HALO; want = TILE; }
-            int64_t avail = P.capacity - src;
-            if (avail < want) want = avail > 0 ? (avail & ~(int64_t)15) : 0;
-            if (want > 0) {
-                fence_proxy_async();
-                mbar_expect_tx(&full_bar[st], (uint32_t)want);
-                tma_load_1d(buf + dst, P.file + src, (uint32_t)want, &full_bar[st]);
-                return;
-            }
-        }
-        mbar_arrive(&full_bar[st]);
-    };
-
+    const int lw = warp - W_LINE0;                 // 0..NLINE-1
+    const int ltid = lw * 32 + lane;               // 0..LINE_THREADS-1
+    unsigned long long my_size = 0;                // FASTQ: sum of rlen seen by this thread
     struct TileState { int64_t t, base; };
-    const int lbase = warp * REGION + lane * BPT;              // this thread's BPT contiguous bytes
-    const int rot = (lane / (8 / NCH)) % NCH;                  // chunk rotation: conflict-free LDS.128
 
-    // ---- one line: list entry e (>= 2) of the tile in phase C ---------------------------------------
-    auto do_line = [&](const TileState &S, const uint8_t *tb, const Pref &pr, int e, int idx) {
-        const int64_t p = l_pos[e], pm1 = l_pos[e - 1], pm2 = l_pos[e - 2];
-        const uint32_t f1 = l_flag[e - 1], f2 = l_flag[e - 2];
+    // ---- one line: newline at p, previous newlines pm1, pm2, their flags (bit31: the line that STARTS
+    //      after that newline is a header; low bits: tile-level header count up to there), line index ----
+    auto do_line_v = [&](const TileState &S, const uint8_t *tb, const Pref &pr, int64_t p, int64_t pm1, int64_t pm2,
+                         uint32_t f1, uint32_t f2, int idx) {
         const int64_t s = pm1 + 1;
         const int64_t L = p - pm1;                            // len + 1
         const int64_t lineidx = (int64_t)pr.ex_nl + idx;      // buffer-local line index
@@ -367,9 +571,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                 if (!full_name) {
                     nlen = 0;
                     if (near) {
-                        const uint8_t *h = tb + rs + 1;
                         int which;
-                        nlen = find_first_of2(h, dlen, 0x20202020u, 0x09090909u, &which);
+                        nlen = find_first_of2(tb + rs + 1, dlen, 0x20202020u, 0x09090909u, &which);
                     } else {
                         while (nlen < dlen) {
                             const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + nlen);
@@ -420,9 +623,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                     if (l < 0) l = 0;
                     int64_t k = 0;
                     if (near) {
-                        const uint8_t *h = tb + rs + 1;
                         int which;
-                        k = find_first_of2(h, l, 0x20202020u, 0x00000000u, &which);
+                        k = find_first_of2(tb + rs + 1, l, 0x20202020u, 0x00000000u, &which);
                         if (which == 2) k = l;          // a NUL before any space: strchr() finds nothing (fastq.c:112)
                     } else {
                         for (; k < l; ++k) {
@@ -439,54 +641,77 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
         }
     };
 
-    // ---- phase C of a regular tile: compact the warp segments into the line list, then one
-    //      thread per line (two rounds when the tile has more than 256 lines) ------------------------
+    // ---- regular tile: line warp lw owns the segments of byte warps [lw*4, lw*4+4); their lines are
+    //      flattened over the 32 lanes; predecessors come from the segments (or the tile carry) ---------
     auto phase_c = [&](const TileState &S, const uint8_t *tb, const Slot &sl) {
-        // compaction: warp w copies its own segment to its tile-level position
-        const uint32_t wb = sl.wstart[warp];
-        const int wn = (int)(sl.wcnt[warp] & 0xffffu), wb_nl = (int)(wb & 0xffffu);
-        const uint32_t wb_h = sl.mail.tsh + (wb >> 16);
-        for (int k = lane; k < wn; k += 32) {
-            const uint32_t f = sl.seg_flag[warp][k];
-            l_pos[2 + wb_nl + k] = S.base + sl.seg_pos[warp][k];
-            l_flag[2 + wb_nl + k] = ((f >> 15) << 31) | (wb_h + (f & 0x7fffu));
+        const int w0 = lw * SEG_PER_LINE_WARP;
+        const uint32_t tsh = sl.tsh;
+        auto eflag = [&](int w2, int k) -> uint32_t {
+            const uint32_t f = sl.seg_flag[w2][k];
+            return ((f >> 15) << 31) | (tsh + (sl.wstart[w2] >> 16) + (f & 0x7fffu));
+        };
+        // entry `back` (1 or 2) positions before the first entry of byte-warp segment w2
+        auto before_seg = [&](int w2, int back, int64_t &pp, uint32_t &ff) {
+            for (int w3 = w2 - 1; w3 >= 0; --w3) {
+                const int c = (int)(sl.wcnt[w3] & 0xffffu);
+                if (c >= back) { pp = S.base + sl.seg_pos[w3][c - back]; ff = eflag(w3, c - back); return; }
+                back -= c;
+            }
+            pp = sl.pref.cpos[2 - back]; ff = sl.pref.cflag[2 - back];      // back 1 -> cpos[1], back 2 -> cpos[0]
+        };
+        int cn[SEG_PER_LINE_WARP], tot = 0;
+#pragma unroll
+        for (int b = 0; b < SEG_PER_LINE_WARP; ++b) { cn[b] = (int)(sl.wcnt[w0 + b] & 0xffffu); tot += cn[b]; }
+        for (int i = lane; i < tot; i += 32) {
+            int b = 0, k = i;
+#pragma unroll
+            for (int bb = 0; bb < SEG_PER_LINE_WARP - 1; ++bb) if (b == bb && k >= cn[bb]) { k -= cn[bb]; ++b; }
+            const int w = w0 + b;
+            const int64_t p = S.base + sl.seg_pos[w][k];
+            int64_t pm1, pm2;
+            uint32_t f1, f2;
+            if (k >= 1) { pm1 = S.base + sl.seg_pos[w][k - 1]; f1 = eflag(w, k - 1); } else before_seg(w, 1, pm1, f1);
+            if (k >= 2) { pm2 = S.base + sl.seg_pos[w][k - 2]; f2 = eflag(w, k - 2); } else before_seg(w, 2 - k, pm2, f2);
+            do_line_v(S, tb, sl.pref, p, pm1, pm2, f1, f2, (int)(sl.wstart[w] & 0xffffu) + k);
         }
-        if (tid < 2) { l_pos[tid] = sl.pref.cpos[tid]; l_flag[tid] = sl.pref.cflag[tid]; }
-        worker_bar();
-        const int T_nl = sl.T_nl;
-        for (int idx = tid; idx < T_nl; idx += WORKERS) do_line(S, tb, sl.pref, 2 + idx, idx);
     };
 
-    // ---- dense tile (more than LB lines, or a warp region with more than SEGCAP): rebuild the
-    //      newline list byte-wise in batches of LB lines; slow but fully general ----------------------
-    auto dense_tile = [&](const TileState &S, const uint8_t *tb, const Slot &sl, uint32_t my_cnt /* nl | h<<16 */) {
-        // exclusive block prefix of per-thread (newline, header) counts in thread order == file order
+    // ---- dense tile (a byte warp found more than SEGCAP newlines in its region): the line warps rebuild
+    //      the newline list byte-wise in batches of LB lines; slow but fully general --------------------------
+    auto dense_tile = [&](const TileState &S, const uint8_t *tb, const Slot &sl) {
+        constexpr int DB = TILE / LINE_THREADS;          // bytes per line thread
+        const int dbase = ltid * DB;
+        uint32_t my_cnt = 0;
+        for (int b = 0; b < DB; ++b) {
+            const int x = dbase + b;
+            if (tb[x] == '\n') { my_cnt += 1; if (MODE == 0 && x + 1 < TILE && S.base + x + 1 < n && tb[x + 1] == '>') my_cnt += 1u << 16; }
+        }
         uint32_t incl = my_cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += o;
         }
-        if (lane == 31) s_scan[warp] = incl;
-        worker_bar();
+        if (lane == 31) s_scan[lw] = incl;
+        line_bar();
         uint32_t wb = 0;
-        for (int w = 0; w < warp; ++w) wb += s_scan[w];
+        for (int w = 0; w < lw; ++w) wb += s_scan[w];
         const uint32_t excl = wb + incl - my_cnt;
         const int T_nl = sl.T_nl;
         for (int b0 = 0; b0 < T_nl; b0 += LB) {
-            worker_bar();                                   // previous batch fully consumed
+            line_bar();                                   // previous batch fully consumed
             int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
-            if (b0 > 0 && tid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
-            worker_bar();
-            if (tid == 0) {
+            if (b0 > 0 && ltid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
+            line_bar();
+            if (ltid == 0) {
                 if (b0 == 0) { l_pos[0] = sl.pref.cpos[0]; l_pos[1] = sl.pref.cpos[1]; l_flag[0] = sl.pref.cflag[0]; l_flag[1] = sl.pref.cflag[1]; }
                 else { l_pos[0] = c0; l_pos[1] = c1; l_flag[0] = g0; l_flag[1] = g1; }
             }
             int idx = (int)(excl & 0xffffu);
-            uint32_t hc = sl.mail.tsh + (excl >> 16);
+            uint32_t hc = sl.tsh + (excl >> 16);
             if ((my_cnt & 0xffffu) && idx < b0 + LB && idx + (int)(my_cnt & 0xffffu) > b0) {
-                for (int b = 0; b < BPT; ++b) {
-                    const int x = lbase + b;
+                for (int b = 0; b < DB; ++b) {
+                    const int x = dbase + b;
                     if (tb[x] != '\n') continue;
                     uint32_t nh = 0;
                     if (MODE == 0) { nh = (x + 1 < TILE && S.base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
@@ -495,233 +720,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P
                     ++idx;
                 }
             }
-            worker_bar();
+            line_bar();
             const int nb = T_nl - b0 < LB ? T_nl - b0 : LB;
-            for (int i = tid; i < nb; i += WORKERS) do_line(S, tb, sl.pref, 2 + i, b0 + i);
+            for (int i = ltid; i < nb; i += LINE_THREADS)
+                do_line_v(S, tb, sl.pref, l_pos[2 + i], l_pos[1 + i], l_pos[i], l_flag[1 + i], l_flag[i], b0 + i);
         }
-        worker_bar();   // the line list is shared with phase C of the pending tile
+        line_bar();
     };
 
-    if (tid == 0) issue(0);
-
-    static_assert(STAGES == 4, "stage ring indexing assumes 4 stages");
-    const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
-    TileState pend[LAG];
-    for (int i = 0; i < LAG; ++i) { pend[i].t = -1; pend[i].base = 0; }
-    bool draining = false;
-    int q = 0, pq = 0;                 // slot of the tile in phase A / of the tile in phase C
-    uint32_t qpar = 0, pqpar = 0;
-    for (int it = 0;; ++it) {
-        const int st = it & (STAGES - 1);
-        int64_t t = P.ntiles;
-        FXG_DBG(const long long tw0 = clock64();)
-        if (!draining) {
-            mbar_wait(&full_bar[st], (uint32_t)((it >> 2) & 1));
-            t = s_tile[st];
+    {
+        int s = 0;
+        uint32_t par = 0;
+        for (;;) {
+            mbar_wait(&pref_bar[s], par);
+            Slot &sl = slots[s];
+            const int64_t t = sl.tile;
+            if (t < 0) break;
+            TileState S;
+            S.t = t; S.base = t * TILE;
+            if (sl.dense) dense_tile(S, stage_ptr(s), sl);
+            else phase_c(S, stage_ptr(s), sl);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&free_bar[s]);
+            if (++s == RING) { s = 0; par ^= 1u; }
         }
-        FXG_DBG(const long long tw1 = clock64(); if (P.dbg && tid == 0) atomicAdd(&P.dbg[0], (unsigned long long)(tw1 - tw0));)
-        const bool have = t < P.ntiles;
-        uint8_t *tb = stage_ptr(it);
-        Slot &sl = slots[q];
-        TileState cur;
-        cur.t = -1; cur.base = 0;
-        if (have) {
-            // claim + prefetch the next tile: stage (it+1)%STAGES held tile it-LAG-1, whose phase C
-            // ended (worker barrier) in iteration it-1
-            if (tid == 0) issue((it + 1) & (STAGES - 1));
-            const int64_t base = t * TILE;
-            // the tile that contains EOF: neutralise bytes past n, plant the virtual newline
-            if (base + TILE > n) {
-                for (int x = tid; x < TILE; x += WORKERS)
-                    if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
-                worker_bar();
-            }
-            // ---------------- phase A ------------------------------------------------------------------
-            // each thread owns 64 contiguous bytes (4 x LDS.128 in a lane-rotated chunk order, so the
-            // loads are bank-conflict free); lines are normally longer than that, so a thread holds at
-            // most one newline and ONE ballot ranks all newlines of the warp's 2 KiB region.
-            uint4 v[NCH];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) v[j] = *reinterpret_cast<const uint4 *>(tb + lbase + 16 * ((j + rot) % NCH));
-            uint32_t m[NCH];
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) { m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80); cnt += __popc(m[j]); }
-            uint32_t my_cnt;      // newlines | header starts << 16 of this thread
-            uint32_t run;         // same, whole warp
-            if (!__any_sync(0xffffffffu, cnt > 1)) {
-                int x = 0;
-                uint32_t nh = 0;
-                if (cnt) {
-                    int j = 0;
-                    uint32_t mm = 0;
-#pragma unroll
-                    for (int jj = NCH - 1; jj >= 0; --jj) if (m[jj]) { j = jj; mm = m[jj]; }
-                    x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
-                    if (MODE == 0) nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u;
-                }
-                const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
-                const uint32_t bh = (MODE == 0) ? __ballot_sync(0xffffffffu, nh != 0) : 0u;
-                if (cnt) {
-                    const int wi = __popc(bn & lt_mask);
-                    sl.seg_pos[warp][wi] = (uint16_t)x;
-                    sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | (__popc(bh & lt_mask) + nh));
-                }
-                my_cnt = cnt | (nh << 16);
-                run = __popc(bn) | (__popc(bh) << 16);
-            } else if (!__any_sync(0xffffffffu, cnt > 2)) {
-                // at most two newlines per thread (e.g. a header line inside the 64 bytes): two ballots
-                int xa = 0x7fffffff, xb = 0x7fffffff;
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    if (m[j]) {
-                        const int qoff = lbase + 16 * ((j + rot) % NCH);
-                        const int x1 = qoff + chunk_bit_to_off(__ffs(m[j]) - 1);
-                        if (x1 < xa) { xb = xa; xa = x1; } else if (x1 < xb) xb = x1;
-                        const uint32_t m2 = m[j] & (m[j] - 1);
-                        if (m2) {
-                            const int x2 = qoff + chunk_bit_to_off(__ffs(m2) - 1);
-                            if (x2 < xa) { xb = xa; xa = x2; } else if (x2 < xb) xb = x2;
-                        }
-                    }
-                }
-                uint32_t nha = 0, nhb = 0;
-                if (MODE == 0) {
-                    if (cnt >= 1) nha = (xa + 1 < TILE && base + xa + 1 < n && tb[xa + 1] == '>') ? 1u : 0u;
-                    if (cnt >= 2) nhb = (xb + 1 < TILE && base + xb + 1 < n && tb[xb + 1] == '>') ? 1u : 0u;
-                }
-                const uint32_t bn1 = __ballot_sync(0xffffffffu, cnt >= 1), bn2 = __ballot_sync(0xffffffffu, cnt >= 2);
-                const uint32_t bh1 = (MODE == 0) ? __ballot_sync(0xffffffffu, nha != 0) : 0u;
-                const uint32_t bh2 = (MODE == 0) ? __ballot_sync(0xffffffffu, nhb != 0) : 0u;
-                const int wi = __popc(bn1 & lt_mask) + __popc(bn2 & lt_mask);
-                const uint32_t hcb = __popc(bh1 & lt_mask) + __popc(bh2 & lt_mask);
-                if (cnt >= 1) { sl.seg_pos[warp][wi] = (uint16_t)xa; sl.seg_flag[warp][wi] = (uint16_t)((nha << 15) | (hcb + nha)); }
-                if (cnt >= 2) { sl.seg_pos[warp][wi + 1] = (uint16_t)xb; sl.seg_flag[warp][wi + 1] = (uint16_t)((nhb << 15) | (hcb + nha + nhb)); }
-                my_cnt = cnt | ((nha + nhb) << 16);
-                run = (__popc(bn1) + __popc(bn2)) | ((__popc(bh1) + __popc(bh2)) << 16);
-            } else {
-                // short lines (three or more newlines in some thread's 64 bytes): shuffle scan + ordered
-                // iteration over the masks
-                uint32_t h = 0;
-                if (MODE == 0) {
-#pragma unroll
-                    for (int j = 0; j < NCH; ++j) {
-                        uint32_t mm = m[j];
-                        while (mm) {
-                            const int x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
-                            mm &= mm - 1;
-                            if (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ++h;
-                        }
-                    }
-                }
-                my_cnt = cnt | (h << 16);
-                uint32_t incl = my_cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                run = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t wi = (incl - my_cnt) & 0xffffu, hc = (incl - my_cnt) >> 16;
-                if (cnt && (run & 0xffffu) <= (uint32_t)SEGCAP) {
-#pragma unroll 1
-                    for (int qc = 0; qc < NCH; ++qc) {
-                        const int j = (qc - rot + NCH) % NCH;
-                        uint32_t mq = 0;
-#pragma unroll
-                        for (int jj = 0; jj < NCH; ++jj) if (jj == j) mq = m[jj];
-#pragma unroll 1
-                        for (int w = 0; w < 4; ++w) {                 // byte order: word, then byte
-                            uint32_t mw = mq & (0x80808080u >> w);
-                            while (mw) {
-                                const int x = lbase + 16 * qc + chunk_bit_to_off(__ffs(mw) - 1);
-                                mw &= mw - 1;
-                                uint32_t nh = 0;
-                                if (MODE == 0) { nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
-                                sl.seg_pos[warp][wi] = (uint16_t)x;
-                                sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | hc);
-                                ++wi;
-                            }
-                        }
-                    }
-                }
-            }
-            if (lane == 0) sl.wcnt[warp] = run;
-            // (1) segments + per-warp counts visible; OR-reduce "some warp overflowed its segment".
-            // SEGCAP * NWARPS == LB, so a tile without overflow always fits the line list.
-            const bool dense = worker_bar_or((run & 0xffffu) > (uint32_t)SEGCAP);
-            cur.t = t; cur.base = base;
-            if (warp == 0) {
-                // warp 0: prefix over the per-warp counts, tile totals, last two newline positions, publish
-                const uint32_t c = lane < NWARPS ? sl.wcnt[lane] : 0u;
-                uint32_t incl = c;
-#pragma unroll
-                for (int d = 1; d < NWARPS; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                if (lane < NWARPS) sl.wstart[lane] = incl - c;
-                const uint32_t ttot = __shfl_sync(0xffffffffu, incl, NWARPS - 1);
-                const int T_nl = (int)(ttot & 0xffffu);
-                if (lane == 0) {
-                    const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
-                    const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
-                    const uint32_t T_h = (ttot >> 16) + tsh;
-                    int64_t l0 = NOPOS, l1 = NOPOS;
-                    if (!dense) {
-                        int found = 0;
-                        for (int w = NWARPS - 1; w >= 0 && found < 2; --w) {
-                            const int cw = (int)(sl.wcnt[w] & 0xffffu);
-                            for (int k = cw - 1; k >= 0 && found < 2; --k) {
-                                const int64_t pp = base + sl.seg_pos[w][k];
-                                if (found == 0) l0 = pp; else l1 = pp;
-                                ++found;
-                            }
-                        }
-                    } else {
-                        int found = 0;
-                        for (int x = TILE - 1; x >= 0 && found < 2; --x)
-                            if (tb[x] == '\n') { if (found == 0) l0 = base + x; else l1 = base + x; ++found; }
-                    }
-                    // publish the tile aggregate NOW (not from the prefix warp, whose look-backs are
-                    // sequential): every tile becomes visible a fixed, short time after it was claimed
-                    st_desc(&P.cnt[t], ST_AGG | (uint64_t)T_nl, ST_AGG | (uint64_t)T_h);
-                    st_desc(&P.pos[t], T_nl >= 1 ? (uint64_t)(l0 + 2) : 1ull, T_nl >= 2 ? (uint64_t)(l1 + 2) : 1ull);
-                    sl.T_nl = T_nl;
-                    sl.mail.t = t; sl.mail.tsh = tsh;
-                    mbar_arrive(&mail_bar[q]);
-                }
-            }
-            if (dense) {
-                // not pipelined: wait for our own prefix (also orders warp 0's slot writes) and finish now
-                mbar_wait(&pref_bar[q], qpar);
-                dense_tile(cur, tb, sl, my_cnt);
-                cur.t = -1;   // nothing pending
-            }
-        }
-        if (!have && !draining && tid == 0) {   // no more tiles: release the prefix warp
-            sl.mail.t = -1;
-            mbar_arrive(&mail_bar[q]);
-        }
-        if (!have) draining = true;
-        FXG_DBG(const long long tw2 = clock64(); if (P.dbg && tid == 0) atomicAdd(&P.dbg[1], (unsigned long long)(tw2 - tw1));)
-        // ---------------- phase C of tile it-LAG (its look-back had LAG iterations to finish) --------
-        if (pend[0].t >= 0) {
-            mbar_wait(&pref_bar[pq], pqpar);
-            FXG_DBG(const long long tw3 = clock64(); if (P.dbg && tid == 0) atomicAdd(&P.dbg[2], (unsigned long long)(tw3 - tw2));)
-            phase_c(pend[0], stage_ptr(it - LAG), slots[pq]);
-            FXG_DBG(if (P.dbg && tid == 0) atomicAdd(&P.dbg[3], (unsigned long long)(clock64() - tw3));)
-        }
-        worker_bar();   // (3) stage, slot and line list are free again
-        if (++q == NSLOT) { q = 0; qpar ^= 1u; }
-        if (it >= LAG && ++pq == NSLOT) { pq = 0; pqpar ^= 1u; }
-#pragma unroll
-        for (int i = 0; i + 1 < LAG; ++i) pend[i] = pend[i + 1];
-        pend[LAG - 1] = cur;
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < LAG; ++i) any |= pend[i].t >= 0;
-        if (draining && !any) break;
     }
     if (MODE == 1) {
 #pragma unroll
@@ -818,7 +840,7 @@ __global__ void count_newlines_kernel(const uint8_t *file, int64_t n, unsigned l
 using namespace fxg;
 
 static int scan_launch_config(fxg_ctx *ctx, int mode, int *grid, size_t *smem) {
-    *smem = (size_t)STAGES * STAGE_BYTES + 16;   // + slack for word-wise header reads
+    *smem = (size_t)RING * STAGE_BYTES + 16;     // + slack for word-wise header reads
     int per_sm = 0;
     if (mode == 0) {
         FXG_CUDA(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
