@@ -108,10 +108,12 @@ int         fxg_ctx_sync(fxg_ctx *ctx);
 int         fxg_ctx_sm_count(fxg_ctx *ctx);
 
 /* measurement hooks (bench.py): with profiling on, the dominant kernels are bracketed by
- * CUDA events on the context's stream; slot 0 = scan kernel, 1 = FASTA finalize,
- * 2 = extract/reads kernel, 3 = offset prefix-sum kernels.  fxg_profile_last_ms waits for
+ * CUDA events on the context's stream; slot 0 = scan (mark) kernel, 1 = FASTA finalize,
+ * 2 = extract/reads kernel, 3 = offset prefix-sum kernels, 4 = region-count prefix kernels,
+ * 5 = scan lines kernel.  fxg_profile_last_ms waits for
  * the slot's end event.  fxg_ctx_launch_count = kernels launched by this context so far. */
-enum { FXG_PROF_SCAN = 0, FXG_PROF_FINALIZE = 1, FXG_PROF_GATHER = 2, FXG_PROF_PLAN = 3, FXG_PROF_SLOTS = 4 };
+enum { FXG_PROF_SCAN = 0, FXG_PROF_FINALIZE = 1, FXG_PROF_GATHER = 2, FXG_PROF_PLAN = 3, FXG_PROF_PREFIX = 4,
+       FXG_PROF_LINES = 5, FXG_PROF_SLOTS = 6 };
 int         fxg_profile_enable(fxg_ctx *ctx, int on);
 int         fxg_profile_last_ms(fxg_ctx *ctx, int slot, float *ms);
 int64_t     fxg_ctx_launch_count(fxg_ctx *ctx);

@@ -2,7 +2,7 @@
 # Build libfxg.so (C-ABI + sm_100a kernels) in-tree: pyfastx_b200/libfxg.so
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
-OUT="$HERE/../libfxg.so"
+OUT="${FXG_OUT:-$HERE/../libfxg.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC,-O2,-Wall -Xptxas -v --shared ${FXG_DEFS:-} \

@@ -93,7 +93,7 @@ extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
     }
     for (int i = 0; i < FXG_PROF_SLOTS; ++i)
         for (int j = 0; j < 2; ++j) if (c->prof_ev[i][j]) cudaEventDestroy(c->prof_ev[i][j]);
-    c->tile_desc.release(); c->row_tmp.release(); c->rows.release();
+    c->tile_desc.release(); c->seg.release(); c->row_tmp.release(); c->rows.release();
     c->counters.release(); c->plan.release(); c->misc.release(); c->stage_file.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;

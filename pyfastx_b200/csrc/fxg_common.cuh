@@ -53,7 +53,7 @@ struct fxg_ctx {
     size_t       pinned_bytes = 0;
     cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
     // scan scratch
-    FxgScratch   tile_desc, row_tmp, rows, counters, plan, misc, stage_file;
+    FxgScratch   tile_desc, seg, row_tmp, rows, counters, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small
     // measurement hooks
     bool         profiling = false;
@@ -172,6 +172,11 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
 __device__ __forceinline__ int64_t shfl_i64(int64_t v, int src) {
     int lo = __shfl_sync(0xffffffffu, (int)(uint32_t)(uint64_t)v, src);
     int hi = __shfl_sync(0xffffffffu, (int)(uint32_t)((uint64_t)v >> 32), src);
+    return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
+}
+__device__ __forceinline__ int64_t shfl_up_i64(int64_t v, int d) {
+    int lo = __shfl_up_sync(0xffffffffu, (int)(uint32_t)(uint64_t)v, d);
+    int hi = __shfl_up_sync(0xffffffffu, (int)(uint32_t)((uint64_t)v >> 32), d);
     return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
 }
 __device__ __forceinline__ int64_t shfl_down_i64(int64_t v, int d) {

@@ -2,130 +2,43 @@
 //
 // Replaces the per-line loops of pyfastx_create_index (reference src/index.c:226-361) and
 // pyfastx_fastq_create_index (src/fastq.c:84-171), both driven by ks_getuntil2
-// (src/kseq.c:59-109), with ONE pass over the file bytes resident in HBM.
+// (src/kseq.c:59-109).  The file bytes resident in HBM are read ONCE; everything after that
+// works on a compact newline list (2 bytes per line, ~3 % of the file for 80-column FASTA).
 //
 // Design:
-//   * persistent CTAs claim 16 KiB tiles in file order from an atomic counter; each tile
-//     (+ a 256 B left halo) is brought into shared memory by a 1-D TMA bulk copy
-//     (cp.async.bulk -> SASS UBLKCP) through a 3-stage mbarrier ring;
-//   * phase A: every thread tests 4 x 16 B for '\n' with 3 ALU ops per 32-bit word and the
-//     warp turns the per-chunk masks into ordered newline indices with ballots/popc;
-//   * the tile publishes {#newlines, #header starts, last two newline positions} and obtains
-//     the exclusive prefix over all earlier tiles with a decoupled look-back (single pass,
-//     no second read of the file);
-//   * phase C: one thread per LINE.  Every quantity the reference carries from line to line
-//     is re-expressed as a local rule on (this line, previous line, global line index,
-//     global header ordinal):
-//       - a header line writes boff / dlen / elen / name length / its line index;
-//       - a sequence line that follows a header writes llen;
-//       - a sequence line whose length differs from the previous sequence line raises an
-//         "event" (count, min/max line index, sum of length deltas) on its record;
-//     a tiny finalize kernel then derives blen, slen, norm per record from neighbouring
-//     headers and the event summary (proof of equivalence with index.c:325-342 in DESIGN.md);
-//   * FASTQ needs no per-record state at all: line k of the file writes field k%4 of row k/4.
+//   mark    one warp per 2 KiB region, no communication between warps at all: 4 coalesced
+//           16-byte loads per lane, exact SWAR newline masks (3 ALU ops per 32-bit word),
+//           ballot-ranked compaction into the region's segment of the newline list
+//           {position in region | '\r' before | '>' after}, plus the region's counts
+//           {#newlines, #header starts}.  This kernel carries all of the file traffic and is
+//           a pure stream: nothing in it waits on another CTA.
+//   prefix  exclusive prefix of the region counts (three small kernels over 4 bytes per region).
+//   lines   one thread per LINE, reading only the newline list.  Every quantity the reference
+//           carries from line to line is re-expressed as a local rule on (this line, previous
+//           line, global line index, global header ordinal):
+//             - a header line writes boff / dlen / elen / name length / its line index;
+//             - a sequence line that follows a header writes llen;
+//             - a sequence line whose length differs from the previous sequence line raises an
+//               "event" (count, min/max line index, sum of length deltas) on its record;
+//           a tiny finalize kernel then derives blen, slen, norm per record from neighbouring
+//           headers and the event summary (proof of equivalence with index.c:325-342 in DESIGN.md).
+//           FASTQ needs no per-record state at all: line k of the file writes field k%4 of row k/4.
+//           File bytes are touched again only for header / read-name lines (the name cut).
+//
+// An earlier single-pass variant (TMA tile ring + decoupled look-back inside one kernel) topped out at
+// 1.85 TB/s: every tile's shared-memory slot stayed occupied for the ~13k cycles its look-back spent
+// waiting on L2 round trips.  Splitting the dependency out of the streaming kernel removes that wait.
 #include "fxg_common.cuh"
 #include <stdlib.h>
 
 namespace fxg {
 
-#ifdef FXG_SCAN_PROFILE
-#define FXG_DBG(x) x
-#else
-#define FXG_DBG(x)
-#endif
-
-constexpr int TILE    = 16384;          // bytes per tile
-constexpr int HALO    = 256;            // left halo kept in smem (previous line starts)
-constexpr int LAG     = 2;          // phase C of tile i-LAG runs after phase A of tile i
-constexpr int STAGES  = LAG + 2;    // tiles i-LAG..i-1 (awaiting phase C) | tile i (phase A) | tile i+1 (loading)
-constexpr int NSLOT   = LAG + 1;    // line-list / mailbox slots
-constexpr int THREADS = 512;          // worker threads (16 warps) + one prefix warp
-constexpr int NWARPS  = THREADS / 32;
-constexpr int REGION  = TILE / NWARPS;  // contiguous bytes per warp (2048)
-constexpr int BPT     = TILE / THREADS; // contiguous bytes per worker thread (32)
-constexpr int NCH     = BPT / 16;       // 16-byte chunks per thread (2)
-constexpr int LB      = 512;            // line-list capacity of a regular tile (lines >= 32 B on average)
-constexpr int SEGCAP  = 32;             // per-warp entry segment (2 KiB region: lines >= 21 B on average)
-constexpr int STAGE_BYTES = HALO + TILE;
-static_assert(SEGCAP * (THREADS / 32) <= LB, "a tile without segment overflow must fit the line list");
-
+constexpr int REGION   = 2048;            // bytes per warp
+constexpr int SEGCAP   = 128;             // newline-list entries kept per region (lines >= 16 B on average)
+constexpr int MARK_WARPS = 8;             // warps per CTA of the mark / lines kernels
+constexpr int PS_THREADS = 256, PS_PER_THREAD = 16, PS_BLOCK = PS_THREADS * PS_PER_THREAD;   // regions per prefix block
 constexpr int64_t NOPOS = INT64_MIN / 4;
-
-// ---- decoupled look-back state ---------------------------------------------------------------
-// Two 16-byte entries per tile, every 64-bit word self-validating (0 = not written yet), so no
-// fence / flag ordering is needed and a reader costs ONE L2 round trip:
-//   cnt[t] = { st<<62 | newlines , st<<62 | header starts }   st 1 = tile aggregate, 2 = inclusive prefix
-//   pos[t] = { p_last + 2 , p_prev + 2 }  positions of the tile's last two newlines; 1 = none
-constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = 3ull << 62;
-
-struct Agg {          // exclusive prefix handed to phase C
-    uint64_t nl, hdr;
-    int64_t  p_last, p_prev;
-    int      k;
-};
-
-__device__ __forceinline__ ulonglong2 ld_desc(const ulonglong2 *p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_desc(ulonglong2 *p, uint64_t x, uint64_t y) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
-}
-__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) { return (uint64_t)shfl_i64((int64_t)v, src); }
-
-// Exclusive (newline, header) counts of tile t: warp-wide look-back over windows of 128 tiles
-// (4 independent 16-byte loads per lane in flight).  Sums are commutative, so a window reduces
-// with two REDUX instructions plus one shuffle of the (large) inclusive value it ends on.
-__device__ void lookback_counts(const ulonglong2 *cnt, int64_t t, int lane, uint64_t &ex_nl, uint64_t &ex_hdr, int &nwin) {
-    uint64_t snl = 0, shdr = 0;
-    nwin = 0;
-    int64_t j0 = t - 1;
-    while (true) {
-        ulonglong2 v[4];
-        ++nwin;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int64_t j = j0 - lane - 32 * m;
-            v[m] = (j >= 0) ? ld_desc(cnt + j) : make_ulonglong2(ST_INC, ST_INC);   // before tile 0: prefix 0
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int64_t j = j0 - lane - 32 * m;
-            while ((v[m].x & ST_MASK) == 0 || ((v[m].x ^ v[m].y) & ST_MASK) != 0) v[m] = ld_desc(cnt + j);
-            const bool inc = (v[m].x & ST_MASK) == ST_INC;
-            const uint32_t ball = __ballot_sync(0xffffffffu, inc);
-            const int first = ball ? (__ffs(ball) - 1) : 32;
-            const uint32_t a = lane < first ? (uint32_t)(v[m].x & ~ST_MASK) : 0u;   // tile aggregates are < 2^15
-            const uint32_t b = lane < first ? (uint32_t)(v[m].y & ~ST_MASK) : 0u;
-            snl += __reduce_add_sync(0xffffffffu, a);
-            shdr += __reduce_add_sync(0xffffffffu, b);
-            if (ball) {
-                snl += shfl_u64(v[m].x & ~ST_MASK, first);
-                shdr += shfl_u64(v[m].y & ~ST_MASK, first);
-                ex_nl = snl; ex_hdr = shdr;
-                return;
-            }
-        }
-        j0 -= 128;
-    }
-}
-
-// The two newlines preceding tile t (buffer-relative); -1 is the virtual newline before byte 0.
-__device__ void lookback_positions(const ulonglong2 *pos, int64_t t, int64_t &p_last, int64_t &p_prev, int &k) {
-    int64_t got[2] = {NOPOS, NOPOS};
-    int n = 0;
-    for (int64_t j = t - 1; n < 2; --j) {
-        if (j < 0) { got[n++] = -1; break; }
-        ulonglong2 pv;
-        do { pv = ld_desc(pos + j); } while (pv.x == 0 || pv.y == 0);
-        if (pv.x != 1) {
-            got[n++] = (int64_t)pv.x - 2;
-            if (n < 2 && pv.y != 1) got[n++] = (int64_t)pv.y - 2;
-        }
-    }
-    p_last = got[0]; p_prev = got[1]; k = n;
-}
+constexpr uint32_t E_POS = 0x07ffu, E_CR = 1u << 14, E_HDR = 1u << 15;
 
 struct __align__(16) FastaTmp {   // per header slot (slot 0 = lines before the first header)
     int64_t  boff;       // header thread
@@ -141,9 +54,9 @@ struct __align__(16) FastaTmp {   // per header slot (slot 0 = lines before the 
 };
 static_assert(sizeof(FastaTmp) == 64, "FastaTmp layout");
 
-struct ScanTotals {     // written by the CTA that owns the last tile (+ finalize)
-    uint64_t nl;
-    uint64_t hdr;
+struct ScanTotals {
+    uint64_t nl;        // newlines (incl. the virtual one at n)
+    uint64_t hdr;       // header starts
     int64_t  n_eff;     // n + 1 if the last line has no '\n'
     uint64_t sum_len;   // FASTA: sum(slen) (finalize); FASTQ: sum(rlen)
     int64_t  lead_lines, lead_bytes, lead_llen;
@@ -154,62 +67,279 @@ struct ScanParams {
     const uint8_t *file;
     int64_t   n;            // bytes
     int64_t   capacity;     // readable bytes at file (multiple of 16)
-    int64_t   ntiles;
+    int64_t   nreg;         // regions that can hold a newline: ceil((n + 1) / REGION)
     int64_t   base_offset;  // added to every file offset written to rows
     int64_t   first_line;   // FASTQ: global index of the first line of this buffer
     int       flags;
-    ulonglong2 *cnt;        // look-back: counts (aggregate -> inclusive, in place)
-    ulonglong2 *pos;        // look-back: last two newline positions per tile
-    uint32_t *tile_counter;
+    uint2    *rc;           // per region: {newlines | header starts << 16, last entry | the one before << 16}
+                            // (padded to PS_BLOCK with zeros)
+    uint4    *rec2;         // FASTA, per region: {first entry | second << 16, interesting-line mask, header mask, 0}
+    uint16_t *seg;          // per region: SEGCAP entries, file order
+    ulonglong2 *ex;         // per region: exclusive {newlines, header starts}
+    ulonglong2 *bs;         // per prefix block
     ScanTotals *totals;
     FastaTmp *tmp;          // FASTA
     int64_t   tmp_cap;      // slots
     fxg_fastq_row *qrows;   // FASTQ
     int64_t   qrows_cap;
-    unsigned long long *dbg; // optional cycle counters (FXG_SCAN_DEBUG=1)
 };
 
-// Per-CTA roles (warp specialisation).  All hand-offs are mbarriers on a ring of RING tile slots; no
-// role ever executes another role's code, so the instruction cost of a tile is the sum of
-//   16 byte warps   phase A only: newline masks of their 1 KiB region -> ordered entries in the slot
-//    1 publisher    16 per-warp counts -> tile aggregate, published for the other CTAs
-//    1 prefix warp  decoupled look-back (the only code that waits on other CTAs)
-//    1 producer     claims tiles in file order and issues their TMA loads as ring slots free up
-//    4 line warps   phase C: one thread per line, for the (few) lines of a tile
-// and byte warps stream tile after tile without ever waiting for a look-back.
-constexpr int NBYTE = NWARPS;                  // 16 byte warps
-constexpr int NLINE = 4;                       // line warps
-constexpr int W_PUB = NBYTE, W_PREF = NBYTE + 1, W_PROD = NBYTE + 2, W_LINE0 = NBYTE + 3;
-constexpr int CTA_THREADS = (NBYTE + 3 + NLINE) * 32;
-constexpr int LINE_THREADS = NLINE * 32;
-constexpr int RING = 5;                        // tile slots (stage buffer + metadata) in flight per CTA
-constexpr int SEG_PER_LINE_WARP = NBYTE / NLINE;
-
-struct Pref {           // prefix warp -> line warps
-    uint64_t ex_nl, ex_hdr;
-    int64_t  cpos[2];   // the two newlines preceding the tile: [1] = nearest, [0] = the one before (NOPOS if none)
-    uint32_t cflag[2];  // bit31: the line starting after that newline begins with '>' ; low bits: header count (only [1])
-    uint32_t pad[2];
-};
-struct Slot {           // metadata of one tile in flight
-    uint16_t seg_pos[NBYTE][SEGCAP];     // per byte-warp newline positions (tile relative), file order
-    uint16_t seg_flag[NBYTE][SEGCAP];    // bit15: next line starts with '>', low bits: warp-local inclusive header count
-    uint32_t wcnt[NBYTE];                // per warp: newlines | header starts << 16
-    uint32_t wstart[NBYTE];              // exclusive prefix of wcnt (publisher)
-    int64_t  tile;                       // tile id, -1 = no more tiles
-    int      T_nl, dense;                // newlines in the tile; some warp overflowed its segment
-    uint32_t tsh, pad0;                  // the tile's first byte starts a header line
-    Pref     pref;
-};
-
-__device__ __forceinline__ void line_bar() { asm volatile("bar.sync 2, %0;" ::"n"(LINE_THREADS) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
-// First k in [0, limit) with h[k] == a or h[k] == b (h in shared memory), else limit.  Word-wise:
-// four aligned 32-bit loads in flight per step instead of one dependent byte load per character.
-// (May read up to 15 bytes past h + limit: the dynamic shared buffer carries 16 bytes of slack.)
+// =============================================================================================
+// mark: newline list + counts of one 2 KiB region per warp
+// =============================================================================================
+template <int MODE>   // 0 = FASTA, 1 = FASTQ
+__global__ void __launch_bounds__(MARK_WARPS * 32, 6) mark_kernel(const ScanParams P) {
+    __shared__ uint4    s_data[MARK_WARPS][REGION / 16];   // the region's bytes (neighbour-byte lookups)
+    __shared__ uint16_t s_ent[MARK_WARPS][SEGCAP];         // newline positions, then complete entries
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * MARK_WARPS + warp;
+    if (r >= P.nreg) return;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t n = P.n;
+    const int64_t base = r * REGION;
+    const uint8_t *file = P.file;
+    const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
+
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t o = base + j * 512 + lane * 16;
+        if (o + 16 <= n) v[j] = ld_stream16(file + o);
+        else {
+            // the chunk that contains EOF (or lies past it): bytes >= n read as 0, and a file that does
+            // not end in '\n' gets a virtual newline at n (kseq returns the last line all the same)
+            const bool virt = n > 0 && file[n - 1] != '\n';
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 16; ++i) {
+                const int64_t x = o + i;
+                const uint32_t b = x < n ? file[x] : ((virt && x == n) ? 0x0au : 0u);
+                w[i >> 2] |= b << ((i & 3) * 8);
+            }
+            v[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+
+    // ---- pass 1: positions, ranked in file order (chunk-major, lane-minor) ------------------
+    uint32_t m[4];
+    uint32_t nlc = 0;
+    bool multi = false;
+    uint16_t *ent = s_ent[warp];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s_data[warp][j * 32 + lane] = v[j];
+        m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80);
+        const int c = __popc(m[j]);
+        multi |= c > 1;
+        const uint32_t bn = __ballot_sync(0xffffffffu, c != 0);
+        if (c) {
+            const uint32_t idx = nlc + __popc(bn & lt_mask);
+            if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(j * 512 + lane * 16 + chunk_bit_to_off(__ffs(m[j]) - 1));
+        }
+        nlc += __popc(bn);
+    }
+    if (__any_sync(0xffffffffu, multi)) {
+        // short lines: several newlines inside one lane's 16 bytes -> shuffle scan per chunk, then each lane
+        // walks its own newlines in byte order (word, then byte within the word)
+        nlc = 0;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            uint32_t mj = 0;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) if (jj == j) mj = m[jj];
+            const uint32_t c = (uint32_t)__popc(mj);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o2 = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o2;
+            }
+            uint32_t idx = nlc + incl - c;
+#pragma unroll 1
+            for (int w = 0; w < 4; ++w) {
+                uint32_t mw = mj & (0x80808080u >> w);
+                while (mw) {
+                    if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(j * 512 + lane * 16 + chunk_bit_to_off(__ffs(mw) - 1));
+                    mw &= mw - 1;
+                    ++idx;
+                }
+            }
+            nlc += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncwarp();
+
+    // ---- pass 2: one lane per newline: neighbour byte -> flag; counts; write-out --------------
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data[warp]);
+    uint32_t hc = 0;
+    if (nlc <= (uint32_t)SEGCAP) {
+        uint16_t *dst = P.seg + r * SEGCAP;
+        const uint32_t nround = (nlc + 15u) & ~15u;         // whole 32-byte sectors, zero padded
+        uint32_t imask = 0, hmask = 0;
+        for (uint32_t k0 = 0; k0 < nround; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint32_t e = 0;
+            if (k < nlc) {
+                const uint32_t pos = ent[k];
+                e = pos;
+                if (MODE == 0) {
+                    const uint32_t next = pos < (uint32_t)(REGION - 1) ? (uint32_t)sb[pos + 1]
+                                                                      : (base + REGION < n ? (uint32_t)file[base + REGION] : 0u);
+                    if (next == '>') e |= E_HDR;
+                } else {
+                    const uint32_t prev = pos > 0 ? (uint32_t)sb[pos - 1] : (base > 0 ? (uint32_t)file[base - 1] : 0u);
+                    if (prev == '\r') e |= E_CR;
+                }
+            }
+            if (MODE == 0) {
+                const uint32_t hb = __ballot_sync(0xffffffffu, (e & E_HDR) != 0);
+                hc += __popc(hb);
+                if (k0 == 0) {
+                    // lines the lines kernel has to look at: header lines, the line after a header, and
+                    // lines whose length differs from the previous line's (k >= 2: all inside the region)
+                    const uint32_t e1 = __shfl_up_sync(0xffffffffu, e, 1), e2 = __shfl_up_sync(0xffffffffu, e, 2);
+                    const bool it = lane >= 2 && k < nlc &&
+                                    (((e1 | e2) & E_HDR) != 0 || (e & E_POS) - (e1 & E_POS) != (e1 & E_POS) - (e2 & E_POS));
+                    imask = __ballot_sync(0xffffffffu, it);
+                    hmask = hb;
+                }
+            }
+            if (k < nround) dst[k] = (uint16_t)e;
+            if (k < nlc) ent[k] = (uint16_t)e;                   // complete entries (for the region records)
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t last = nlc >= 1 ? ent[nlc - 1] : 0u, prev = nlc >= 2 ? ent[nlc - 2] : 0u;
+            P.rc[r] = make_uint2(nlc | (hc << 16), last | (prev << 16));
+            if (MODE == 0) {
+                const uint32_t f0 = nlc >= 1 ? ent[0] : 0u, f1 = nlc >= 2 ? ent[1] : 0u;
+                P.rec2[r] = make_uint4(f0 | (f1 << 16), nlc > 32u ? 0xffffffffu : imask, hmask, 0u);
+            }
+        }
+    } else {
+        // dense region: only the counts; the lines kernel re-reads the bytes
+        if (MODE == 0) {
+            uint32_t myh = 0;
+            for (int x = lane; x < REGION; x += 32)
+                if (sb[x] == '\n') {
+                    const uint32_t next = x < REGION - 1 ? (uint32_t)sb[x + 1] : (base + REGION < n ? (uint32_t)file[base + REGION] : 0u);
+                    myh += next == '>';
+                }
+            hc = __reduce_add_sync(0xffffffffu, myh);
+        }
+        if (lane == 0) {
+            P.rc[r] = make_uint2(nlc | (hc << 16), 0u);
+            if (MODE == 0) P.rec2[r] = make_uint4(0u, 0xffffffffu, 0u, 0u);
+        }
+    }
+}
+
+// =============================================================================================
+// prefix over the region counts
+// =============================================================================================
+// per block of PS_BLOCK regions: {sum newlines, sum header starts}
+__global__ void __launch_bounds__(PS_THREADS) prefix_reduce_kernel(const uint2 *rc, ulonglong2 *bs) {
+    __shared__ uint32_t sm[16];
+    const uint4 *p = reinterpret_cast<const uint4 *>(rc + (size_t)blockIdx.x * PS_BLOCK + (size_t)threadIdx.x * PS_PER_THREAD);
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < PS_PER_THREAD / 2; ++i) {
+        const uint4 q = p[i];
+        a += (q.x & 0xffffu) + (q.z & 0xffffu);
+        b += (q.x >> 16) + (q.z >> 16);
+    }
+    a = __reduce_add_sync(0xffffffffu, a);
+    b = __reduce_add_sync(0xffffffffu, b);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm[warp] = a; sm[8 + warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t ta = 0, tb = 0;
+        for (int w = 0; w < PS_THREADS / 32; ++w) { ta += sm[w]; tb += sm[8 + w]; }
+        bs[blockIdx.x] = make_ulonglong2(ta, tb);
+    }
+}
+
+// exclusive scan of the block sums (one CTA), seeds, totals
+__global__ void __launch_bounds__(1024) prefix_blocks_kernel(ulonglong2 *bs, int64_t nb, const uint8_t *file, int64_t n,
+                                                             int mode, ScanTotals *tot) {
+    __shared__ uint64_t s_a[32], s_b[32];
+    __shared__ uint64_t s_ca, s_cb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_ca = 0; s_cb = (mode == 0 && n > 0 && file[0] == '>') ? 1u : 0u; }   // header at byte 0
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
+        const int64_t i = b0 + threadIdx.x;
+        const ulonglong2 v = i < nb ? bs[i] : make_ulonglong2(0, 0);
+        uint64_t a = v.x, b = v.y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t oa = (uint64_t)shfl_up_i64((int64_t)a, d), ob = (uint64_t)shfl_up_i64((int64_t)b, d);
+            if (lane >= d) { a += oa; b += ob; }
+        }
+        if (lane == 31) { s_a[warp] = a; s_b[warp] = b; }
+        __syncthreads();
+        uint64_t wa = 0, wb = 0;
+        for (int w = 0; w < warp; ++w) { wa += s_a[w]; wb += s_b[w]; }
+        const uint64_t ca = s_ca, cb = s_cb;
+        if (i < nb) bs[i] = make_ulonglong2(ca + wa + a - v.x, cb + wb + b - v.y);
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_ca = ca + wa + a; s_cb = cb + wb + b; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const bool virt = n > 0 && file[n - 1] != '\n';
+        tot->nl = s_ca; tot->hdr = s_cb; tot->n_eff = n + (virt ? 1 : 0);
+    }
+}
+
+// per region: exclusive {newlines, header starts}
+__global__ void __launch_bounds__(PS_THREADS) prefix_expand_kernel(const uint2 *rc, const ulonglong2 *bs, ulonglong2 *ex,
+                                                                 int64_t nreg) {
+    __shared__ uint32_t s_a[PS_THREADS / 32], s_b[PS_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t r0 = (size_t)blockIdx.x * PS_BLOCK + (size_t)threadIdx.x * PS_PER_THREAD;
+    const uint4 *p = reinterpret_cast<const uint4 *>(rc + r0);
+    uint32_t c[PS_PER_THREAD];
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < PS_PER_THREAD / 2; ++i) {
+        const uint4 q = p[i];
+        c[2 * i] = q.x; c[2 * i + 1] = q.z;
+        a += (q.x & 0xffffu) + (q.z & 0xffffu);
+        b += (q.x >> 16) + (q.z >> 16);
+    }
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oa = __shfl_up_sync(0xffffffffu, ia, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= d) { ia += oa; ib += ob; }
+    }
+    if (lane == 31) { s_a[warp] = ia; s_b[warp] = ib; }
+    __syncthreads();
+    uint32_t wa = 0, wb = 0;
+    for (int w = 0; w < warp; ++w) { wa += s_a[w]; wb += s_b[w]; }
+    const ulonglong2 bb = bs[blockIdx.x];
+    uint64_t ea = bb.x + wa + ia - a, eb = bb.y + wb + ib - b;
+#pragma unroll
+    for (int i = 0; i < PS_PER_THREAD; ++i) {
+        if ((int64_t)(r0 + i) < nreg) ex[r0 + i] = make_ulonglong2(ea, eb);
+        ea += c[i] & 0xffffu; eb += c[i] >> 16;
+    }
+}
+
+// =============================================================================================
+// lines: one thread per line, from the newline list
+// =============================================================================================
+// First k in [0, limit) with h[k] == a or h[k] == b, else limit.  Word-wise: four aligned 32-bit
+// loads in flight per step instead of one dependent byte load per character.  Reads whole aligned
+// words up to 18 bytes past h + limit (the caller checks the buffer capacity).
 __device__ __forceinline__ int64_t find_first_of2(const uint8_t *h, int64_t limit, uint32_t a4, uint32_t b4, int *which) {
     const int mis = (int)((uintptr_t)h & 3);
     const uint32_t *wp = reinterpret_cast<const uint32_t *>(h - mis);
@@ -235,520 +365,371 @@ __device__ __forceinline__ int64_t find_first_of2(const uint8_t *h, int64_t limi
     return limit;
 }
 
-template <int MODE>   // 0 = FASTA, 1 = FASTQ
-__global__ void __launch_bounds__(CTA_THREADS, 2) scan_kernel(const ScanParams P) {
-    extern __shared__ __align__(128) uint8_t dyn_smem[];
-    __shared__ __align__(8) uint64_t full_bar[RING];   // TMA data landed            (tx)    -> byte warps
-    __shared__ __align__(8) uint64_t fill_bar[RING];   // byte warps wrote the slot   (16)    -> publisher
-    __shared__ __align__(8) uint64_t mail_bar[RING];   // aggregate published         (1)     -> prefix warp
-    __shared__ __align__(8) uint64_t pref_bar[RING];   // exclusive prefix ready      (1)     -> line warps
-    __shared__ __align__(8) uint64_t free_bar[RING];   // line warps done             (NLINE) -> TMA issuer
-    __shared__ __align__(16) Slot slots[RING];
-    __shared__ int64_t  l_pos[LB + 2];       // dense path only: line list of the tile ([0],[1] = carry)
-    __shared__ uint32_t l_flag[LB + 2];
-    __shared__ uint32_t s_scan[NLINE];
+struct Prev2 {            // the two newlines before some point: [1] nearest, [0] the one before
+    int64_t  pos1, pos0;  // NOPOS if there is none; -1 = the virtual newline before byte 0
+    uint32_t h1, h0;      // the line starting after that newline begins with '>'
+};
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int64_t n = P.n;
-    const bool virt = (n > 0) && (P.file[n - 1] != '\n');
-    const int64_t n_eff = n + (virt ? 1 : 0);
-    const bool full_name = (P.flags & FXG_SCAN_FULL_NAME) != 0;
+template <int MODE>
+__device__ __forceinline__ uint32_t is_hdr_at(const ScanParams &P, int64_t x) {     // does a header line start at byte x?
+    return (MODE == 0 && x < P.n && P.file[x] == '>') ? 1u : 0u;
+}
+__device__ __forceinline__ bool nl_at(const ScanParams &P, int64_t x) {             // incl. the virtual newline at n
+    return x < P.n ? P.file[x] == '\n' : (x == P.n && P.n > 0 && P.file[P.n - 1] != '\n');
+}
 
-    if (tid == 0) {
-        for (int s = 0; s < RING; ++s) {
-            mbar_init(&full_bar[s], 1); mbar_init(&fill_bar[s], NBYTE); mbar_init(&mail_bar[s], 1);
-            mbar_init(&pref_bar[s], 1); mbar_init(&free_bar[s], NLINE);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    auto stage_ptr = [&](int s) -> uint8_t * { return dyn_smem + (size_t)s * STAGE_BYTES + HALO; };
-    // byte at buffer-relative position x, given the tile (id t, base) whose stage is tb
-    auto byte_at = [&](const uint8_t *tb, int64_t t, int64_t base, int64_t x) -> uint8_t {
-        const int64_t r = x - base;
-        if (r >= -(int64_t)HALO && (t > 0 || r >= 0)) return tb[r];
-        return P.file[x];
-    };
-
-    // =========================================================================================
-    // byte warps: phase A, tile after tile
-    // =========================================================================================
-    if (warp < NBYTE) {
-        const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
-        const int lbase = warp * REGION + lane * BPT;              // this thread's BPT contiguous bytes
-        const int rot = (lane / (8 / NCH)) % NCH;                  // chunk rotation: conflict-free LDS.128
-        int s = 0;
-        uint32_t par = 0;
-        for (;;) {
-            mbar_wait(&full_bar[s], par);
-            Slot &sl = slots[s];
-            const int64_t t = sl.tile;
-            if (t < 0) {                                           // no more tiles: pass the baton and leave
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&fill_bar[s]);
-                break;
-            }
-            uint8_t *tb = stage_ptr(s);
-            const int64_t base = t * TILE;
-            // the tile that contains EOF: every warp neutralises the bytes past n in its own region and the
-            // owner of position n plants the virtual newline
-            if (base + TILE > n) {
-                for (int x = warp * REGION + lane; x < (warp + 1) * REGION; x += 32)
-                    if (base + x >= n) tb[x] = (virt && base + x == n) ? (uint8_t)'\n' : (uint8_t)0;
-                __syncwarp();
-            }
-            // ---------------- phase A ------------------------------------------------------------------
-            uint4 v[NCH];
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) v[j] = *reinterpret_cast<const uint4 *>(tb + lbase + 16 * ((j + rot) % NCH));
-            uint32_t m[NCH];
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) { m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80); cnt += __popc(m[j]); }
-            uint32_t run;         // newlines | header starts << 16 of the whole warp
-            if (!__any_sync(0xffffffffu, cnt > 1)) {
-                int x = 0;
-                uint32_t nh = 0;
-                if (cnt) {
-                    int j = 0;
-                    uint32_t mm = 0;
-#pragma unroll
-                    for (int jj = NCH - 1; jj >= 0; --jj) if (m[jj]) { j = jj; mm = m[jj]; }
-                    x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
-                    if (MODE == 0) nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u;
-                }
-                const uint32_t bn = __ballot_sync(0xffffffffu, cnt != 0);
-                const uint32_t bh = (MODE == 0) ? __ballot_sync(0xffffffffu, nh != 0) : 0u;
-                if (cnt) {
-                    const int wi = __popc(bn & lt_mask);
-                    sl.seg_pos[warp][wi] = (uint16_t)x;
-                    sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | (__popc(bh & lt_mask) + nh));
-                }
-                run = __popc(bn) | (__popc(bh) << 16);
-            } else if (!__any_sync(0xffffffffu, cnt > 2)) {
-                // at most two newlines per thread (e.g. a header line inside the 32 bytes): two ballots
-                int xa = 0x7fffffff, xb = 0x7fffffff;
-#pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    if (m[j]) {
-                        const int qoff = lbase + 16 * ((j + rot) % NCH);
-                        const int x1 = qoff + chunk_bit_to_off(__ffs(m[j]) - 1);
-                        if (x1 < xa) { xb = xa; xa = x1; } else if (x1 < xb) xb = x1;
-                        const uint32_t m2 = m[j] & (m[j] - 1);
-                        if (m2) {
-                            const int x2 = qoff + chunk_bit_to_off(__ffs(m2) - 1);
-                            if (x2 < xa) { xb = xa; xa = x2; } else if (x2 < xb) xb = x2;
-                        }
+// ---- one line: newline at p, previous newlines pm1, pm2; h1 / h2: the line starting after pm1 / pm2 is a
+//      header; hcount: header starts up to and including the one after pm1 (= record ordinal + 1);
+//      cr: the byte before p is '\r' (FASTQ entries carry it; FASTA looks it up for header lines only) ----
+template <int MODE>
+__device__ __forceinline__ void do_line(const ScanParams &P, int64_t p, int64_t pm1, int64_t pm2, bool h1, bool h2,
+                                        int64_t hcount, int64_t lineidx, bool cr, unsigned long long &my_size) {
+    const uint8_t *file = P.file;
+    const int64_t s = pm1 + 1;
+    const int64_t L = p - pm1;                            // len + 1
+    if (MODE == 0) {
+        const int64_t slot = hcount;                      // rec + 1
+        if (h1) {
+            const int elen = (p >= 1 && (p - 1 < P.n ? file[p - 1] : 0) == '\r') ? 2 : 1;
+            const int64_t dlen = L - 1 - elen;
+            int64_t nlen = dlen;
+            if (!(P.flags & FXG_SCAN_FULL_NAME)) {
+                nlen = 0;
+                if (s + 1 + dlen + 20 <= P.capacity) {
+                    int which;
+                    nlen = find_first_of2(file + s + 1, dlen, 0x20202020u, 0x09090909u, &which);
+                } else {
+                    while (nlen < dlen) {
+                        const uint8_t ch = file[s + 1 + nlen];
+                        if (ch == ' ' || ch == '\t') break;
+                        ++nlen;
                     }
                 }
-                uint32_t nha = 0, nhb = 0;
-                if (MODE == 0) {
-                    if (cnt >= 1) nha = (xa + 1 < TILE && base + xa + 1 < n && tb[xa + 1] == '>') ? 1u : 0u;
-                    if (cnt >= 2) nhb = (xb + 1 < TILE && base + xb + 1 < n && tb[xb + 1] == '>') ? 1u : 0u;
-                }
-                const uint32_t bn1 = __ballot_sync(0xffffffffu, cnt >= 1), bn2 = __ballot_sync(0xffffffffu, cnt >= 2);
-                const uint32_t bh1 = (MODE == 0) ? __ballot_sync(0xffffffffu, nha != 0) : 0u;
-                const uint32_t bh2 = (MODE == 0) ? __ballot_sync(0xffffffffu, nhb != 0) : 0u;
-                const int wi = __popc(bn1 & lt_mask) + __popc(bn2 & lt_mask);
-                const uint32_t hcb = __popc(bh1 & lt_mask) + __popc(bh2 & lt_mask);
-                if (cnt >= 1 && wi < SEGCAP) { sl.seg_pos[warp][wi] = (uint16_t)xa; sl.seg_flag[warp][wi] = (uint16_t)((nha << 15) | (hcb + nha)); }
-                if (cnt >= 2 && wi + 1 < SEGCAP) { sl.seg_pos[warp][wi + 1] = (uint16_t)xb; sl.seg_flag[warp][wi + 1] = (uint16_t)((nhb << 15) | (hcb + nha + nhb)); }
-                run = (__popc(bn1) + __popc(bn2)) | ((__popc(bh1) + __popc(bh2)) << 16);
+            }
+            if (slot < P.tmp_cap) {
+                FastaTmp *t = &P.tmp[slot];
+                t->boff = P.base_offset + p + 1;
+                t->lineidx = lineidx;
+                t->dlen = (int32_t)dlen;
+                t->nlen = (int32_t)nlen;
+                t->elen = (uint32_t)elen;
+            }
+        } else if (slot < P.tmp_cap) {
+            const bool prev_exists = pm1 >= 0;
+            if (!prev_exists || h2) {
+                P.tmp[slot].llen = L;
             } else {
-                // short lines (three or more newlines in some thread's bytes): shuffle scan + ordered
-                // iteration over the masks
-                uint32_t h = 0;
-                if (MODE == 0) {
-#pragma unroll
-                    for (int j = 0; j < NCH; ++j) {
-                        uint32_t mm = m[j];
-                        while (mm) {
-                            const int x = lbase + 16 * ((j + rot) % NCH) + chunk_bit_to_off(__ffs(mm) - 1);
-                            mm &= mm - 1;
-                            if (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ++h;
-                        }
-                    }
-                }
-                const uint32_t my_cnt = cnt | (h << 16);
-                uint32_t incl = my_cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                run = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t wi = (incl - my_cnt) & 0xffffu, hc = (incl - my_cnt) >> 16;
-                if (cnt && (run & 0xffffu) <= (uint32_t)SEGCAP) {
-#pragma unroll 1
-                    for (int qc = 0; qc < NCH; ++qc) {
-                        const int j = (qc - rot + NCH) % NCH;
-                        uint32_t mq = 0;
-#pragma unroll
-                        for (int jj = 0; jj < NCH; ++jj) if (jj == j) mq = m[jj];
-#pragma unroll 1
-                        for (int w = 0; w < 4; ++w) {                 // byte order: word, then byte
-                            uint32_t mw = mq & (0x80808080u >> w);
-                            while (mw) {
-                                const int x = lbase + 16 * qc + chunk_bit_to_off(__ffs(mw) - 1);
-                                mw &= mw - 1;
-                                uint32_t nh = 0;
-                                if (MODE == 0) { nh = (x + 1 < TILE && base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
-                                sl.seg_pos[warp][wi] = (uint16_t)x;
-                                sl.seg_flag[warp][wi] = (uint16_t)((nh << 15) | hc);
-                                ++wi;
-                            }
-                        }
-                    }
+                const int64_t prevL = pm1 - pm2;
+                if (L != prevL) {
+                    FastaTmp *t = &P.tmp[slot];
+                    atomicAdd(&t->D, 1u);
+                    atomicMax((unsigned long long *)&t->evmax, (unsigned long long)lineidx);
+                    atomicMax((unsigned long long *)&t->evminc, ~(unsigned long long)lineidx);
+                    atomicAdd((unsigned long long *)&t->S, (unsigned long long)(L - prevL));
                 }
             }
-            __syncwarp();
-            if (lane == 0) { sl.wcnt[warp] = run; mbar_arrive(&fill_bar[s]); }
-            if (++s == RING) { s = 0; par ^= 1u; }
         }
-        return;
-    }
-
-    // =========================================================================================
-    // producer: claims tiles in file order and issues their TMA loads as ring slots are released.
-    // A tile is claimed only when its load can start at once, so it is published a short, fixed time
-    // later -- the byte warps never wait for anything but TMA data.
-    // =========================================================================================
-    if (warp == W_PROD) {
-        if (lane == 0) {
-            for (int64_t seq = 0;; ++seq) {
-                const int s = (int)(seq % RING);
-                if (seq >= RING) mbar_wait(&free_bar[s], (uint32_t)(((seq / RING) - 1) & 1));
-                const int64_t t = (int64_t)atomicAdd(P.tile_counter, 1u);
-                uint8_t *buf = dyn_smem + (size_t)s * STAGE_BYTES;
-                bool loaded = false;
-                if (t < P.ntiles) {
-                    slots[s].tile = t;
-                    const int64_t base = t * TILE;
-                    int64_t src = base - HALO, dst = 0, want = STAGE_BYTES;
-                    if (t == 0) { src = 0; dst = HALO; want = TILE; }
-                    int64_t avail = P.capacity - src;
-                    if (avail < want) want = avail > 0 ? (avail & ~(int64_t)15) : 0;
-                    if (want > 0) {
-                        fence_proxy_async();
-                        mbar_expect_tx(&full_bar[s], (uint32_t)want);
-                        tma_load_1d(buf + dst, P.file + src, (uint32_t)want, &full_bar[s]);
-                        loaded = true;
-                    }
+    } else {
+        const int64_t gline = P.first_line + lineidx;
+        const int ph = (int)(gline & 3);
+        const int64_t row = (gline >> 2) - (P.first_line >> 2);
+        const int64_t len = L - 1;
+        if (ph == 1) {
+            const int64_t rlen = (len > 0 && cr) ? len - 1 : len;
+            my_size += (unsigned long long)rlen;
+            if (row < P.qrows_cap) { P.qrows[row].soff = P.base_offset + s; P.qrows[row].rlen = rlen; }
+        } else if (row < P.qrows_cap) {
+            if (ph == 0) {
+                int64_t l = len - 1;
+                if (l > 0 && cr) --l;
+                if (l < 0) l = 0;
+                int64_t k = 0;
+                if (s + 1 + l + 20 <= P.capacity) {
+                    int which;
+                    k = find_first_of2(file + s + 1, l, 0x20202020u, 0x00000000u, &which);
+                    if (which == 2) k = l;          // a NUL before any space: strchr() finds nothing (fastq.c:112)
                 } else {
-                    slots[s].tile = -1;
-                }
-                if (!loaded) mbar_arrive(&full_bar[s]);
-                if (t >= P.ntiles) break;
-            }
-        }
-        return;
-    }
-
-    // =========================================================================================
-    // publisher warp: per-warp counts -> tile aggregate, published for the other CTAs right away
-    // =========================================================================================
-    if (warp == W_PUB) {
-        int s = 0;
-        uint32_t par = 0;
-        for (;;) {
-            mbar_wait(&fill_bar[s], par);
-            Slot &sl = slots[s];
-            const int64_t t = sl.tile;
-            if (t < 0) { if (lane == 0) mbar_arrive(&mail_bar[s]); break; }
-            const int64_t base = t * TILE;
-            const uint8_t *tb = stage_ptr(s);
-            const uint32_t c = lane < NBYTE ? sl.wcnt[lane] : 0u;
-            const bool dense = __any_sync(0xffffffffu, (c & 0xffffu) > (uint32_t)SEGCAP);
-            uint32_t incl = c;
-#pragma unroll
-            for (int d = 1; d < NBYTE; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            if (lane < NBYTE) sl.wstart[lane] = incl - c;
-            const uint32_t ttot = __shfl_sync(0xffffffffu, incl, NBYTE - 1);
-            const int T_nl = (int)(ttot & 0xffffu);
-            if (lane == 0) {
-                const bool line_start_at_base = (base == 0) || (tb[-1] == '\n');
-                const uint32_t tsh = (MODE == 0 && line_start_at_base && base < n && tb[0] == '>') ? 1u : 0u;
-                const uint32_t T_h = (ttot >> 16) + tsh;
-                int64_t l0 = NOPOS, l1 = NOPOS;
-                if (!dense) {
-                    int found = 0;
-                    for (int w = NBYTE - 1; w >= 0 && found < 2; --w) {
-                        const int cw = (int)(sl.wcnt[w] & 0xffffu);
-                        for (int k = cw - 1; k >= 0 && found < 2; --k) {
-                            const int64_t pp = base + sl.seg_pos[w][k];
-                            if (found == 0) l0 = pp; else l1 = pp;
-                            ++found;
-                        }
-                    }
-                } else {
-                    int found = 0;
-                    for (int x = TILE - 1; x >= 0 && found < 2; --x)
-                        if (tb[x] == '\n') { if (found == 0) l0 = base + x; else l1 = base + x; ++found; }
-                }
-                st_desc(&P.cnt[t], ST_AGG | (uint64_t)T_nl, ST_AGG | (uint64_t)T_h);
-                st_desc(&P.pos[t], T_nl >= 1 ? (uint64_t)(l0 + 2) : 1ull, T_nl >= 2 ? (uint64_t)(l1 + 2) : 1ull);
-                sl.T_nl = T_nl; sl.dense = dense ? 1 : 0; sl.tsh = tsh;
-                mbar_arrive(&mail_bar[s]);
-            }
-            __syncwarp();
-            if (++s == RING) { s = 0; par ^= 1u; }
-        }
-        return;
-    }
-
-    // =========================================================================================
-    // prefix warp: decoupled look-back for one tile after the other
-    // =========================================================================================
-    if (warp == W_PREF) {
-        int s = 0;
-        uint32_t par = 0;
-        for (;;) {
-            mbar_wait(&mail_bar[s], par);
-            Slot &sl = slots[s];
-            const int64_t t = sl.tile;
-            if (t < 0) { if (lane == 0) mbar_arrive(&pref_bar[s]); break; }
-            const int64_t base = t * TILE;
-            const uint8_t *tb = stage_ptr(s);
-            uint64_t ex_nl = 0, ex_hdr = 0;
-            int nwin = 0;
-            lookback_counts(P.cnt, t, lane, ex_nl, ex_hdr, nwin);
-            if (lane == 0) {
-                const ulonglong2 own = ld_desc(&P.cnt[t]);
-                const uint64_t in_nl = ex_nl + (own.x & ~ST_MASK), in_hdr = ex_hdr + (own.y & ~ST_MASK);
-                st_desc(&P.cnt[t], ST_INC | in_nl, ST_INC | in_hdr);
-                if (t == P.ntiles - 1) { P.totals->nl = in_nl; P.totals->hdr = in_hdr; P.totals->n_eff = n_eff; }
-                int64_t pl, pp; int k;
-                lookback_positions(P.pos, t, pl, pp, k);
-                uint32_t nh1 = 0, hc1 = 0, nh2 = 0;
-                if (MODE == 0) {
-                    if (pl + 1 == base) { nh1 = sl.tsh; hc1 = sl.tsh; }
-                    else nh1 = (byte_at(tb, t, base, pl + 1) == '>') ? 1u : 0u;
-                    if (k >= 2) nh2 = (byte_at(tb, t, base, pp + 1) == '>') ? 1u : 0u;
-                }
-                Pref &pr = sl.pref;
-                pr.ex_nl = ex_nl; pr.ex_hdr = ex_hdr;
-                pr.cpos[1] = pl;                    pr.cflag[1] = (nh1 << 31) | hc1;
-                pr.cpos[0] = k >= 2 ? pp : NOPOS;   pr.cflag[0] = (nh2 << 31);
-                mbar_arrive(&pref_bar[s]);
-            }
-            __syncwarp();
-            if (++s == RING) { s = 0; par ^= 1u; }
-        }
-        return;
-    }
-
-    // =========================================================================================
-    // line warps: phase C
-    // =========================================================================================
-    const int lw = warp - W_LINE0;                 // 0..NLINE-1
-    const int ltid = lw * 32 + lane;               // 0..LINE_THREADS-1
-    unsigned long long my_size = 0;                // FASTQ: sum of rlen seen by this thread
-    struct TileState { int64_t t, base; };
-
-    // ---- one line: newline at p, previous newlines pm1, pm2, their flags (bit31: the line that STARTS
-    //      after that newline is a header; low bits: tile-level header count up to there), line index ----
-    auto do_line_v = [&](const TileState &S, const uint8_t *tb, const Pref &pr, int64_t p, int64_t pm1, int64_t pm2,
-                         uint32_t f1, uint32_t f2, int idx) {
-        const int64_t s = pm1 + 1;
-        const int64_t L = p - pm1;                            // len + 1
-        const int64_t lineidx = (int64_t)pr.ex_nl + idx;      // buffer-local line index
-        const int rp = (int)(p - S.base);                     // newline, tile relative (>= 0)
-        const bool near = (s - S.base) >= -(int64_t)HALO && (S.t > 0 || s >= S.base);   // line start inside smem window
-        const int rs = (int)(s - S.base);
-        if (MODE == 0) {
-            const bool is_hdr = (f1 >> 31) != 0;
-            const int64_t slot = (int64_t)pr.ex_hdr + (int64_t)(f1 & 0x7fffffffu);   // rec + 1
-            if (is_hdr) {
-                const uint8_t before = (rp >= 1 || S.t > 0) ? tb[rp - 1] : P.file[p - 1];
-                const int elen = (before == '\r') ? 2 : 1;
-                const int64_t dlen = L - 1 - elen;
-                int64_t nlen = dlen;
-                if (!full_name) {
-                    nlen = 0;
-                    if (near) {
-                        int which;
-                        nlen = find_first_of2(tb + rs + 1, dlen, 0x20202020u, 0x09090909u, &which);
-                    } else {
-                        while (nlen < dlen) {
-                            const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + nlen);
-                            if (ch == ' ' || ch == '\t') break;
-                            ++nlen;
-                        }
+                    for (; k < l; ++k) {
+                        const uint8_t ch = file[s + 1 + k];
+                        if (ch == 0) { k = l; break; }
+                        if (ch == ' ') break;
                     }
                 }
-                if (slot < P.tmp_cap) {
-                    FastaTmp *r = &P.tmp[slot];
-                    r->boff = P.base_offset + p + 1;
-                    r->lineidx = lineidx;
-                    r->dlen = (int32_t)dlen;
-                    r->nlen = (int32_t)nlen;
-                    r->elen = (uint32_t)elen;
-                }
-            } else if (slot < P.tmp_cap) {
-                const bool prev_exists = pm1 >= 0;
-                const bool prev_is_hdr = (f2 >> 31) != 0;
-                if (!prev_exists || prev_is_hdr) {
-                    P.tmp[slot].llen = L;
-                } else {
-                    const int64_t prevL = pm1 - pm2;
-                    if (L != prevL) {
-                        FastaTmp *r = &P.tmp[slot];
-                        atomicAdd(&r->D, 1u);
-                        atomicMax((unsigned long long *)&r->evmax, (unsigned long long)lineidx);
-                        atomicMax((unsigned long long *)&r->evminc, ~(unsigned long long)lineidx);
-                        atomicAdd((unsigned long long *)&r->S, (unsigned long long)(L - prevL));
-                    }
-                }
+                *reinterpret_cast<int2 *>(&P.qrows[row].dlen) = make_int2((int)len, (int)k);
+            } else if (ph == 3) {
+                P.qrows[row].qoff = P.base_offset + s;
+            }
+        }
+    }
+}
+
+// ---- the two newlines before region r (warp-uniform): walk back over the region records, 32 at a time.
+//      General path: long lines (more than ~60 KiB without a newline) and neighbours of dense regions. ----
+template <int MODE>
+__device__ __noinline__ void carry_walk(const ScanParams &P, int64_t r, Prev2 &cy) {
+    const int lane = threadIdx.x & 31;
+    cy.pos1 = cy.pos0 = NOPOS; cy.h1 = cy.h0 = 0;
+    int need = 2;
+    auto push = [&](int64_t pos, uint32_t h) {
+        if (need == 2) { cy.pos1 = pos; cy.h1 = h; } else { cy.pos0 = pos; cy.h0 = h; }
+        --need;
+    };
+    int64_t q = r - 1;
+    while (need > 0 && q >= 0) {
+        const int64_t qq = q - lane;
+        const uint32_t c = qq >= 0 ? (P.rc[qq].x & 0xffffu) : 0u;
+        const uint32_t nz = __ballot_sync(0xffffffffu, c != 0);
+        if (!nz) { q -= 32; continue; }
+        const int f = __ffs(nz) - 1;
+        q -= f;
+        const int cq = (int)__shfl_sync(0xffffffffu, c, f);
+        if (cq <= SEGCAP) {
+            const uint16_t *sg = P.seg + q * SEGCAP;
+            for (int i = cq - 1; i >= 0 && need > 0; --i) {
+                const uint32_t e = sg[i];
+                push(q * REGION + (int64_t)(e & E_POS), MODE == 0 ? (e >> 15) : 0u);
             }
         } else {
-            const int64_t gline = P.first_line + lineidx;
-            const int ph = (int)(gline & 3);
-            const int64_t row = (gline >> 2) - (P.first_line >> 2);
-            const int64_t len = L - 1;
-            if (ph == 1) {
-                const uint8_t before = (rp >= 1 || S.t > 0) ? tb[rp - 1] : (p >= 1 ? P.file[p - 1] : (uint8_t)0);
-                const int64_t rlen = (len > 0 && before == '\r') ? len - 1 : len;
-                my_size += (unsigned long long)rlen;
-                if (row < P.qrows_cap) { P.qrows[row].soff = P.base_offset + s; P.qrows[row].rlen = rlen; }
-            } else if (row < P.qrows_cap) {
-                if (ph == 0) {
-                    const uint8_t before = (rp >= 1 || S.t > 0) ? tb[rp - 1] : (p >= 1 ? P.file[p - 1] : (uint8_t)0);
-                    int64_t l = len - 1;
-                    if (l > 0 && before == '\r') --l;
-                    if (l < 0) l = 0;
-                    int64_t k = 0;
-                    if (near) {
-                        int which;
-                        k = find_first_of2(tb + rs + 1, l, 0x20202020u, 0x00000000u, &which);
-                        if (which == 2) k = l;          // a NUL before any space: strchr() finds nothing (fastq.c:112)
-                    } else {
-                        for (; k < l; ++k) {
-                            const uint8_t ch = byte_at(tb, S.t, S.base, s + 1 + k);
-                            if (ch == 0) { k = l; break; }
-                            if (ch == ' ') break;
-                        }
-                    }
-                    *reinterpret_cast<int2 *>(&P.qrows[row].dlen) = make_int2((int)len, (int)k);
-                } else if (ph == 3) {
-                    P.qrows[row].qoff = P.base_offset + s;
-                }
-            }
+            for (int64_t x = q * REGION + REGION - 1; x >= q * REGION && need > 0; --x)
+                if (nl_at(P, x)) push(x, is_hdr_at<MODE>(P, x + 1));
         }
-    };
+        q -= 1;
+    }
+    if (need > 0) push(-1, is_hdr_at<MODE>(P, 0));            // the virtual newline before byte 0
+}
 
-    // ---- regular tile: line warp lw owns the segments of byte warps [lw*4, lw*4+4); their lines are
-    //      flattened over the 32 lanes; predecessors come from the segments (or the tile carry) ---------
-    auto phase_c = [&](const TileState &S, const uint8_t *tb, const Slot &sl) {
-        const int w0 = lw * SEG_PER_LINE_WARP;
-        const uint32_t tsh = sl.tsh;
-        auto eflag = [&](int w2, int k) -> uint32_t {
-            const uint32_t f = sl.seg_flag[w2][k];
-            return ((f >> 15) << 31) | (tsh + (sl.wstart[w2] >> 16) + (f & 0x7fffu));
-        };
-        // entry `back` (1 or 2) positions before the first entry of byte-warp segment w2
-        auto before_seg = [&](int w2, int back, int64_t &pp, uint32_t &ff) {
-            for (int w3 = w2 - 1; w3 >= 0; --w3) {
-                const int c = (int)(sl.wcnt[w3] & 0xffffu);
-                if (c >= back) { pp = S.base + sl.seg_pos[w3][c - back]; ff = eflag(w3, c - back); return; }
-                back -= c;
-            }
-            pp = sl.pref.cpos[2 - back]; ff = sl.pref.cflag[2 - back];      // back 1 -> cpos[1], back 2 -> cpos[0]
-        };
-        int cn[SEG_PER_LINE_WARP], tot = 0;
-#pragma unroll
-        for (int b = 0; b < SEG_PER_LINE_WARP; ++b) { cn[b] = (int)(sl.wcnt[w0 + b] & 0xffffu); tot += cn[b]; }
-        for (int i = lane; i < tot; i += 32) {
-            int b = 0, k = i;
-#pragma unroll
-            for (int bb = 0; bb < SEG_PER_LINE_WARP - 1; ++bb) if (b == bb && k >= cn[bb]) { k -= cn[bb]; ++b; }
-            const int w = w0 + b;
-            const int64_t p = S.base + sl.seg_pos[w][k];
-            int64_t pm1, pm2;
-            uint32_t f1, f2;
-            if (k >= 1) { pm1 = S.base + sl.seg_pos[w][k - 1]; f1 = eflag(w, k - 1); } else before_seg(w, 1, pm1, f1);
-            if (k >= 2) { pm2 = S.base + sl.seg_pos[w][k - 2]; f2 = eflag(w, k - 2); } else before_seg(w, 2 - k, pm2, f2);
-            do_line_v(S, tb, sl.pref, p, pm1, pm2, f1, f2, (int)(sl.wstart[w] & 0xffffu) + k);
-        }
-    };
-
-    // ---- dense tile (a byte warp found more than SEGCAP newlines in its region): the line warps rebuild
-    //      the newline list byte-wise in batches of LB lines; slow but fully general --------------------------
-    auto dense_tile = [&](const TileState &S, const uint8_t *tb, const Slot &sl) {
-        constexpr int DB = TILE / LINE_THREADS;          // bytes per line thread
-        const int dbase = ltid * DB;
-        uint32_t my_cnt = 0;
-        for (int b = 0; b < DB; ++b) {
-            const int x = dbase + b;
-            if (tb[x] == '\n') { my_cnt += 1; if (MODE == 0 && x + 1 < TILE && S.base + x + 1 < n && tb[x + 1] == '>') my_cnt += 1u << 16; }
-        }
-        uint32_t incl = my_cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_scan[lw] = incl;
-        line_bar();
-        uint32_t wb = 0;
-        for (int w = 0; w < lw; ++w) wb += s_scan[w];
-        const uint32_t excl = wb + incl - my_cnt;
-        const int T_nl = sl.T_nl;
-        for (int b0 = 0; b0 < T_nl; b0 += LB) {
-            line_bar();                                   // previous batch fully consumed
-            int64_t c0 = 0, c1 = 0; uint32_t g0 = 0, g1 = 0;
-            if (b0 > 0 && ltid == 0) { c0 = l_pos[LB]; c1 = l_pos[LB + 1]; g0 = l_flag[LB]; g1 = l_flag[LB + 1]; }
-            line_bar();
-            if (ltid == 0) {
-                if (b0 == 0) { l_pos[0] = sl.pref.cpos[0]; l_pos[1] = sl.pref.cpos[1]; l_flag[0] = sl.pref.cflag[0]; l_flag[1] = sl.pref.cflag[1]; }
-                else { l_pos[0] = c0; l_pos[1] = c1; l_flag[0] = g0; l_flag[1] = g1; }
-            }
-            int idx = (int)(excl & 0xffffu);
-            uint32_t hc = sl.tsh + (excl >> 16);
-            if ((my_cnt & 0xffffu) && idx < b0 + LB && idx + (int)(my_cnt & 0xffffu) > b0) {
-                for (int b = 0; b < DB; ++b) {
-                    const int x = dbase + b;
-                    if (tb[x] != '\n') continue;
-                    uint32_t nh = 0;
-                    if (MODE == 0) { nh = (x + 1 < TILE && S.base + x + 1 < n && tb[x + 1] == '>') ? 1u : 0u; hc += nh; }
-                    const int rel = idx - b0;
-                    if (rel >= 0 && rel < LB) { l_pos[2 + rel] = S.base + x; l_flag[2 + rel] = (nh << 31) | hc; }
-                    ++idx;
-                }
-            }
-            line_bar();
-            const int nb = T_nl - b0 < LB ? T_nl - b0 : LB;
-            for (int i = ltid; i < nb; i += LINE_THREADS)
-                do_line_v(S, tb, sl.pref, l_pos[2 + i], l_pos[1 + i], l_pos[i], l_flag[1 + i], l_flag[i], b0 + i);
-        }
-        line_bar();
-    };
-
-    {
-        int s = 0;
-        uint32_t par = 0;
-        for (;;) {
-            mbar_wait(&pref_bar[s], par);
-            Slot &sl = slots[s];
-            const int64_t t = sl.tile;
-            if (t < 0) break;
-            TileState S;
-            S.t = t; S.base = t * TILE;
-            if (sl.dense) dense_tile(S, stage_ptr(s), sl);
-            else phase_c(S, stage_ptr(s), sl);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&free_bar[s]);
-            if (++s == RING) { s = 0; par ^= 1u; }
+// ---- dense region (more than SEGCAP newlines in 2 KiB): re-read the bytes; every lane owns 64 of them ----
+template <int MODE>
+__device__ __noinline__ void dense_region(const ScanParams &P, int64_t r, const Prev2 &cy, ulonglong2 exv,
+                                          unsigned long long &my_size) {
+    const int lane = threadIdx.x & 31;
+    const uint8_t *file = P.file;
+    const int64_t b0 = r * REGION + lane * 64;
+    // per lane: count, header count, last two newlines
+    uint32_t c = 0, h = 0;
+    Prev2 inc; inc.pos1 = inc.pos0 = NOPOS; inc.h1 = inc.h0 = 0;
+    for (int i = 0; i < 64; ++i) {
+        const int64_t x = b0 + i;
+        if (nl_at(P, x)) {
+            const uint32_t hh = is_hdr_at<MODE>(P, x + 1);
+            ++c; h += hh;
+            inc.pos0 = inc.pos1; inc.h0 = inc.h1; inc.pos1 = x; inc.h1 = hh;
         }
     }
+    // inclusive scans: counts, and the "last two newlines" pair (the right operand wins slot by slot)
+    uint32_t ic = c, ih = h;
+    uint32_t icnt = c > 2 ? 2 : c;                        // how many of inc's slots are filled (0..2)
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oc = __shfl_up_sync(0xffffffffu, ic, d), oh = __shfl_up_sync(0xffffffffu, ih, d);
+        const int64_t op1 = shfl_up_i64(inc.pos1, d), op0 = shfl_up_i64(inc.pos0, d);
+        const uint32_t oh1 = __shfl_up_sync(0xffffffffu, inc.h1, d), oh0 = __shfl_up_sync(0xffffffffu, inc.h0, d);
+        const uint32_t ocnt = __shfl_up_sync(0xffffffffu, icnt, d);
+        if (lane >= d) {
+            ic += oc; ih += oh;
+            if (icnt == 0) { inc.pos1 = op1; inc.h1 = oh1; inc.pos0 = op0; inc.h0 = oh0; icnt = ocnt; }
+            else if (icnt == 1 && ocnt >= 1) { inc.pos0 = op1; inc.h0 = oh1; icnt = 2; }
+        }
+    }
+    // exclusive = inclusive of lane-1, completed from the region carry
+    Prev2 pv;
+    pv.pos1 = shfl_up_i64(inc.pos1, 1); pv.pos0 = shfl_up_i64(inc.pos0, 1);
+    pv.h1 = __shfl_up_sync(0xffffffffu, inc.h1, 1); pv.h0 = __shfl_up_sync(0xffffffffu, inc.h0, 1);
+    uint32_t pcnt = __shfl_up_sync(0xffffffffu, icnt, 1);
+    if (lane == 0) pcnt = 0;
+    if (pcnt == 0) pv = cy;
+    else if (pcnt == 1) { pv.pos0 = cy.pos1; pv.h0 = cy.h1; }
+    int64_t idx = (int64_t)exv.x + (ic - c);
+    int64_t hcount = (int64_t)exv.y + (ih - h);
+    for (int i = 0; i < 64 && c; ++i) {
+        const int64_t x = b0 + i;
+        if (!nl_at(P, x)) continue;
+        const bool cr = x > 0 && file[x - 1] == '\r';
+        do_line<MODE>(P, x, pv.pos1, pv.pos0, pv.h1 != 0, pv.h0 != 0, hcount, idx, cr, my_size);
+        const uint32_t hh = is_hdr_at<MODE>(P, x + 1);
+        hcount += hh; ++idx;
+        pv.pos0 = pv.pos1; pv.h0 = pv.h1; pv.pos1 = x; pv.h1 = hh;
+    }
+}
+
+// ---- the lines of one region with at most SEGCAP newlines, warp-cooperative: batches of 32 entries.
+//      E0 / E1: the first two batches (entry k0 + lane), loaded by the caller. ----
+template <int MODE>
+__device__ __forceinline__ void region_batches(const ScanParams &P, int64_t r, int nl, Prev2 cy, ulonglong2 X,
+                                               uint32_t E0, uint32_t E1, unsigned long long &my_size) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int64_t base = r * REGION;
+    const uint16_t *sg = P.seg + r * SEGCAP;
+    int64_t hrun = (int64_t)X.y;                      // header starts through the newline before the batch
+    for (int k0 = 0; k0 < nl; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < nl;
+        uint32_t e = k0 == 0 ? E0 : (k0 == 32 ? E1 : (valid ? (uint32_t)sg[k] : 0u));
+        if (!valid) e = 0;
+        const uint32_t hb = __ballot_sync(0xffffffffu, (e & E_HDR) != 0);
+        const uint32_t e1 = __shfl_up_sync(0xffffffffu, e, 1), e2 = __shfl_up_sync(0xffffffffu, e, 2);
+        if (valid) {
+            int64_t pm1, pm2;
+            bool h1, h2;
+            if (lane >= 1) { pm1 = base + (e1 & E_POS); h1 = (e1 & E_HDR) != 0; } else { pm1 = cy.pos1; h1 = cy.h1 != 0; }
+            if (lane >= 2) { pm2 = base + (e2 & E_POS); h2 = (e2 & E_HDR) != 0; }
+            else if (lane == 1) { pm2 = cy.pos1; h2 = cy.h1 != 0; }
+            else { pm2 = cy.pos0; h2 = cy.h0 != 0; }
+            do_line<MODE>(P, base + (e & E_POS), pm1, pm2, h1, h2, hrun + __popc(hb & lt_mask), (int64_t)X.x + k,
+                          (e & E_CR) != 0, my_size);
+        }
+        // carry for the next batch (only reached when this one was full)
+        const uint32_t l31 = __shfl_sync(0xffffffffu, e, 31), l30 = __shfl_sync(0xffffffffu, e, 30);
+        cy.pos1 = base + (l31 & E_POS); cy.h1 = (l31 >> 15) & 1u;
+        cy.pos0 = base + (l30 & E_POS); cy.h0 = (l30 >> 15) & 1u;
+        hrun += __popc(hb);
+    }
+}
+
+// ---- general path for one region: everything looked up from scratch ----
+template <int MODE>
+__device__ __noinline__ void full_region(const ScanParams &P, int64_t r, unsigned long long &my_size) {
+    const int lane = threadIdx.x & 31;
+    const int nl = (int)(P.rc[r].x & 0xffffu);
+    if (nl == 0) return;
+    const ulonglong2 X = P.ex[r];
+    Prev2 cy;
+    carry_walk<MODE>(P, r, cy);
+    if (MODE != 0) cy.h1 = cy.h0 = 0;
+    if (nl <= SEGCAP) region_batches<MODE>(P, r, nl, cy, X, P.seg[r * SEGCAP + lane], P.seg[r * SEGCAP + 32 + lane], my_size);
+    else dense_region<MODE>(P, r, cy, X, my_size);
+}
+
+constexpr int LG = 4;     // consecutive regions per warp of the lines kernel (all their loads in flight together)
+
+// Every line does work (FASTQ): one warp per LG regions, lane per line.
+template <int MODE>
+__global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x * MARK_WARPS + (threadIdx.x >> 5)) * LG;
+    if (r0 >= P.nreg) return;
+    unsigned long long my_size = 0;                // FASTQ: sum of rlen seen by this thread
+
+    // everything this warp needs, requested at once: the records of its LG regions and the 32 - LG regions
+    // before them (lane l <-> region r0 + LG-1 - l), the exclusive prefixes, the first 64 entries of each segment
+    const int64_t rq = r0 + (LG - 1) - lane;
+    const uint2 A = rq >= 0 ? P.rc[rq] : make_uint2(0u, 0u);       // rc is zero padded past nreg
+    ulonglong2 X[LG];
+    uint32_t E[LG][2];
+#pragma unroll
+    for (int i = 0; i < LG; ++i) {
+        const int64_t r = r0 + i;
+        X[i] = make_ulonglong2(0, 0); E[i][0] = E[i][1] = 0;
+        if (r < P.nreg) {
+            X[i] = P.ex[r];
+            E[i][0] = P.seg[r * SEGCAP + lane];          // speculative: entries past the count are never used
+            E[i][1] = P.seg[r * SEGCAP + 32 + lane];
+        }
+    }
+    const uint32_t cntl = A.x & 0xffffu;
+    const uint32_t nzall = __ballot_sync(0xffffffffu, cntl != 0);
+    const bool window_hits_start = r0 + (LG - 1) - 31 <= 0;         // no region before the window
+
+#pragma unroll
+    for (int i = 0; i < LG; ++i) {
+        const int64_t r = r0 + i;
+        const int me = LG - 1 - i;                                    // the lane holding region r's record
+        const int nl = (int)__shfl_sync(0xffffffffu, cntl, me);
+        if (nl == 0) continue;
+
+        // ---- the two newlines before the region, from the records of the regions before it ----
+        Prev2 cy;
+        cy.pos1 = cy.pos0 = NOPOS; cy.h1 = cy.h0 = 0;
+        {
+            bool slow = false;
+            const uint32_t nz = nzall & ~((2u << me) - 1u);           // non-empty regions before r
+            if (nz) {
+                const int f1 = __ffs(nz) - 1;
+                const uint32_t n1 = __shfl_sync(0xffffffffu, cntl, f1), y1 = __shfl_sync(0xffffffffu, A.y, f1);
+                const int64_t b1 = (r0 + (LG - 1) - f1) * REGION;
+                if (n1 > (uint32_t)SEGCAP) slow = true;
+                else {
+                    cy.pos1 = b1 + (y1 & E_POS); cy.h1 = (y1 >> 15) & 1u;
+                    if (n1 >= 2) { cy.pos0 = b1 + ((y1 >> 16) & E_POS); cy.h0 = y1 >> 31; }
+                    else {
+                        const uint32_t nz2 = nz & ~(1u << f1);
+                        if (nz2) {
+                            const int f2 = __ffs(nz2) - 1;
+                            const uint32_t n2 = __shfl_sync(0xffffffffu, cntl, f2), y2 = __shfl_sync(0xffffffffu, A.y, f2);
+                            if (n2 > (uint32_t)SEGCAP) slow = true;
+                            else { cy.pos0 = (r0 + (LG - 1) - f2) * REGION + (y2 & E_POS); cy.h0 = (y2 >> 15) & 1u; }
+                        } else if (window_hits_start) { cy.pos0 = -1; cy.h0 = is_hdr_at<MODE>(P, 0); }
+                        else slow = true;
+                    }
+                }
+            } else if (window_hits_start) { cy.pos1 = -1; cy.h1 = is_hdr_at<MODE>(P, 0); }
+            else slow = true;
+            if (slow) carry_walk<MODE>(P, r, cy);
+            if (MODE != 0) cy.h1 = cy.h0 = 0;
+        }
+        if (nl <= SEGCAP) region_batches<MODE>(P, r, nl, cy, X[i], E[i][0], E[i][1], my_size);
+        else dense_region<MODE>(P, r, cy, X[i], my_size);
+    }
+
     if (MODE == 1) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) my_size += (unsigned long long)shfl_down_i64((int64_t)my_size, d);
         if (lane == 0 && my_size) atomicAdd((unsigned long long *)&P.totals->sum_len, my_size);
+    }
+}
+
+// FASTA: almost no line does work (only header lines, the line after a header, and lines whose length
+// differs from the previous line's).  One LANE per region screens it from the region records the mark
+// kernel left behind and then walks just those lines; regions the records cannot settle (more than 32
+// newlines, dense neighbours, a line start further back than the previous region) take the general path.
+__global__ void __launch_bounds__(MARK_WARPS * 32) fasta_lines_kernel(const ScanParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t R0 = ((int64_t)blockIdx.x * MARK_WARPS + (threadIdx.x >> 5)) * 32;
+    if (R0 >= P.nreg) return;
+    const int64_t r = R0 + lane;
+    const bool inb = r < P.nreg;
+    unsigned long long dummy = 0;
+    uint2 me = make_uint2(0u, 0u), pv = make_uint2(0u, 0u);
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    ulonglong2 X = make_ulonglong2(0, 0);
+    if (inb) {
+        me = P.rc[r];
+        if (r >= 1) pv = P.rc[r - 1];
+        q = P.rec2[r];
+        X = P.ex[r];
+    }
+    const uint32_t nl = me.x & 0xffffu, pnl = pv.x & 0xffffu;
+    const bool full = nl != 0 && (nl > 32u || r == 0 || pnl < 2u || pnl > (uint32_t)SEGCAP || q.y == 0xffffffffu);
+    uint32_t mask = 0;
+    const uint32_t c1 = pv.y & 0xffffu, c0 = pv.y >> 16, f0 = q.x & 0xffffu, f1 = q.x >> 16;
+    if (nl != 0 && !full) {
+        const int p_c1 = (int)(c1 & E_POS) - REGION, p_c0 = (int)(c0 & E_POS) - REGION;     // relative to this region
+        const int p_f0 = (int)(f0 & E_POS), p_f1 = (int)(f1 & E_POS);
+        const int L0 = p_f0 - p_c1;
+        const bool i0 = ((c1 | c0) & E_HDR) != 0 || L0 != p_c1 - p_c0;
+        const bool i1 = nl >= 2u && (((f0 | c1) & E_HDR) != 0 || p_f1 - p_f0 != L0);
+        mask = (q.y & ~3u) | (i0 ? 1u : 0u) | (i1 ? 2u : 0u);
+        if (nl < 32u) mask &= (1u << nl) - 1u;
+    }
+    const int64_t base = r * REGION;
+    const uint16_t *sg = P.seg + r * SEGCAP;
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        uint32_t e, m1, m2;
+        int64_t b1 = base, b2 = base;
+        if (k >= 2) { e = sg[k]; m1 = sg[k - 1]; m2 = sg[k - 2]; }
+        else if (k == 1) { e = f1; m1 = f0; m2 = c1; b2 = base - REGION; }
+        else { e = f0; m1 = c1; m2 = c0; b1 = b2 = base - REGION; }
+        do_line<0>(P, base + (e & E_POS), b1 + (m1 & E_POS), b2 + (m2 & E_POS), (m1 & E_HDR) != 0, (m2 & E_HDR) != 0,
+                   (int64_t)X.y + __popc(q.z & ((1u << k) - 1u)), (int64_t)X.x + k, false, dummy);
+    }
+    uint32_t fm = __ballot_sync(0xffffffffu, full);
+    while (fm) {
+        const int f = __ffs(fm) - 1;
+        fm &= fm - 1;
+        full_region<0>(P, R0 + f, dummy);
     }
 }
 
@@ -803,22 +784,6 @@ __global__ void fasta_finalize_kernel(const FastaTmp *tmp, int64_t nrows, int64_
     }
 }
 
-// ---- density sample: headers / newlines in evenly spaced windows (capacity estimate) -------
-__global__ void sample_density_kernel(const uint8_t *file, int64_t n, int64_t nwin, int64_t win,
-                                      unsigned long long *out /* [0]=newlines, [1]=header starts */) {
-    const int64_t w = blockIdx.x;
-    const int64_t start = (nwin > 1) ? (int64_t)((__int128)(n - win) * w / (nwin - 1)) : 0;
-    unsigned long long nl = 0, h = 0;
-    for (int64_t i = start + threadIdx.x; i < start + win && i < n; i += blockDim.x) {
-        if (file[i] == '\n') { ++nl; if (i + 1 < n && file[i + 1] == '>') ++h; }
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-        nl += (unsigned long long)shfl_down_i64((int64_t)nl, d);
-        h += (unsigned long long)shfl_down_i64((int64_t)h, d);
-    }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], nl); atomicAdd(&out[1], h); }
-}
-
 // ---- plain newline count (FASTQ multi-GPU phase pass) ----------------------------------------
 __global__ void count_newlines_kernel(const uint8_t *file, int64_t n, unsigned long long *out) {
     const int64_t nvec = n / 16;
@@ -839,42 +804,6 @@ __global__ void count_newlines_kernel(const uint8_t *file, int64_t n, unsigned l
 // =============================================================================================
 using namespace fxg;
 
-static int scan_launch_config(fxg_ctx *ctx, int mode, int *grid, size_t *smem) {
-    *smem = (size_t)RING * STAGE_BYTES + 16;     // + slack for word-wise header reads
-    int per_sm = 0;
-    if (mode == 0) {
-        FXG_CUDA(cudaFuncSetAttribute(scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<0>, CTA_THREADS, *smem));
-    } else {
-        FXG_CUDA(cudaFuncSetAttribute(scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-        FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<1>, CTA_THREADS, *smem));
-    }
-    if (per_sm < 1) per_sm = 1;
-    *grid = ctx->sm_count * per_sm;
-    return FXG_OK;
-}
-
-// estimate (#newlines, #headers) of the whole buffer from 256 evenly spaced 16 KiB windows
-static int sample_density(fxg_ctx *ctx, const fxg_file *f, double *nl_per_byte, double *hdr_per_byte) {
-    const int64_t n = f->size;
-    const int64_t win = 16384;
-    int64_t nwin = n / win;
-    if (nwin > 256) nwin = 256;
-    if (nwin < 1) nwin = 1;
-    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
-    ctx->launches += 1;
-    sample_density_kernel<<<(unsigned)nwin, 256, 0, ctx->stream>>>(f->d, n, nwin, win < n ? win : n,
-                                                                  (unsigned long long *)ctx->counters.ptr);
-    FXG_CUDA(cudaGetLastError());
-    unsigned long long h[2];
-    FXG_CUDA(cudaMemcpyAsync(h, ctx->counters.ptr, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-    const double sampled = (double)nwin * (double)(win < n ? win : n);
-    *nl_per_byte = sampled > 0 ? (double)h[0] / sampled : 0;
-    *hdr_per_byte = sampled > 0 ? (double)h[1] / sampled : 0;
-    return FXG_OK;
-}
-
 static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offset, int64_t first_line, int flags,
                     void **d_rows_out, fxg_scan_stats *stats) {
     FXG_CHECK_ARG(ctx && f && stats, "null ctx/file/stats");
@@ -883,96 +812,105 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
     const int64_t n = f->size;
     if (d_rows_out) *d_rows_out = nullptr;
     if (n == 0) return FXG_OK;
-    const int64_t ntiles = (n + 1 + TILE - 1) / TILE;   // room for a virtual newline at n
+    const int64_t nreg = (n + 1 + REGION - 1) / REGION;     // room for a virtual newline at n
+    const int64_t nb = (nreg + PS_BLOCK - 1) / PS_BLOCK;
+    const int64_t nreg_pad = nb * PS_BLOCK;
     int rc;
-    if ((rc = ctx->counters.reserve(256))) return rc;
-    if ((rc = ctx->tile_desc.reserve((size_t)ntiles * 2 * sizeof(ulonglong2)))) return rc;
+    if ((rc = ctx->counters.reserve(512))) return rc;
+    // tile_desc: rc[nreg_pad] | bs[nb] | ex[nreg] | rec2[nreg] (FASTA)
+    const size_t off_bs = fxg_round_up((int64_t)nreg_pad * 8, 256);
+    const size_t off_ex = off_bs + fxg_round_up(nb * (int64_t)sizeof(ulonglong2), 256);
+    const size_t off_r2 = off_ex + fxg_round_up(nreg * (int64_t)sizeof(ulonglong2), 256);
+    if ((rc = ctx->tile_desc.reserve(off_r2 + (mode == 0 ? (size_t)nreg * sizeof(uint4) : 0)))) return rc;
+    if ((rc = ctx->seg.reserve((size_t)nreg * SEGCAP * sizeof(uint16_t)))) return rc;
 
-    double nlpb = 0, hpb = 0;
-    if ((rc = sample_density(ctx, f, &nlpb, &hpb))) return rc;
-    int64_t cap;
-    if (mode == 0) cap = (int64_t)(hpb * (double)n * 1.5) + 4096;
-    else cap = (int64_t)(nlpb * (double)n * 1.25 / 4.0) + 4096;
+    ScanParams P;
+    memset(&P, 0, sizeof(P));
+    P.file = f->d; P.n = n; P.capacity = f->capacity & ~(int64_t)15; P.nreg = nreg;
+    P.base_offset = base_offset; P.first_line = first_line; P.flags = flags;
+    P.rc = (uint2 *)ctx->tile_desc.ptr;
+    P.bs = (ulonglong2 *)((uint8_t *)ctx->tile_desc.ptr + off_bs);
+    P.ex = (ulonglong2 *)((uint8_t *)ctx->tile_desc.ptr + off_ex);
+    P.rec2 = (uint4 *)((uint8_t *)ctx->tile_desc.ptr + off_r2);
+    P.seg = (uint16_t *)ctx->seg.ptr;
+    P.totals = (ScanTotals *)((uint8_t *)ctx->counters.ptr + 64);
 
-    int grid = 0; size_t smem = 0;
-    if ((rc = scan_launch_config(ctx, mode, &grid, &smem))) return rc;
-    if ((int64_t)grid > ntiles) grid = (int)ntiles;
+    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 512, ctx->stream));
+    if (nreg_pad > nreg) FXG_CUDA(cudaMemsetAsync(P.rc + nreg, 0, (size_t)(nreg_pad - nreg) * 8, ctx->stream));
+    const unsigned grid = (unsigned)((nreg + MARK_WARPS - 1) / MARK_WARPS);
+    {
+        FxgProfScope prof(ctx, FXG_PROF_SCAN);
+        if (mode == 0) mark_kernel<0><<<grid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+        else mark_kernel<1><<<grid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+    }
+    FXG_CUDA(cudaGetLastError());
+    {
+        FxgProfScope prof(ctx, FXG_PROF_PREFIX, 3);
+        prefix_reduce_kernel<<<(unsigned)nb, PS_THREADS, 0, ctx->stream>>>(P.rc, P.bs);
+        prefix_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(P.bs, nb, P.file, n, mode, P.totals);
+        prefix_expand_kernel<<<(unsigned)nb, PS_THREADS, 0, ctx->stream>>>(P.rc, P.bs, P.ex, nreg);
+    }
+    FXG_CUDA(cudaGetLastError());
 
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    ScanTotals tot;
+    FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    // exact row count is known before any row is written: no capacity estimate, no rerun
+    const int64_t nrows = mode == 0 ? (int64_t)tot.hdr
+                                    : (int64_t)((first_line + (int64_t)tot.nl + 3) / 4 - first_line / 4);
+    if (mode == 0) {
+        if ((rc = ctx->row_tmp.reserve((size_t)(nrows + 2) * sizeof(FastaTmp)))) return rc;
+        FXG_CUDA(cudaMemsetAsync(ctx->row_tmp.ptr, 0, (size_t)(nrows + 2) * sizeof(FastaTmp), ctx->stream));
+        P.tmp = (FastaTmp *)ctx->row_tmp.ptr; P.tmp_cap = nrows + 1;
+    } else {
+        if ((rc = ctx->rows.reserve((size_t)(nrows + 2) * sizeof(fxg_fastq_row)))) return rc;
+        // rows are fully overwritten except the partially-owned boundary rows
+        FXG_CUDA(cudaMemsetAsync(ctx->rows.ptr, 0, sizeof(fxg_fastq_row), ctx->stream));
+        if (nrows > 1)
+            FXG_CUDA(cudaMemsetAsync((fxg_fastq_row *)ctx->rows.ptr + (nrows - 1), 0, sizeof(fxg_fastq_row), ctx->stream));
+        P.qrows = (fxg_fastq_row *)ctx->rows.ptr; P.qrows_cap = nrows;
+    }
+    {
+        FxgProfScope prof(ctx, FXG_PROF_LINES);
         if (mode == 0) {
-            if ((rc = ctx->row_tmp.reserve((size_t)(cap + 2) * sizeof(FastaTmp)))) return rc;
-            FXG_CUDA(cudaMemsetAsync(ctx->row_tmp.ptr, 0, (size_t)(cap + 2) * sizeof(FastaTmp), ctx->stream));
+            const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * 32 - 1) / (MARK_WARPS * 32));
+            fasta_lines_kernel<<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
         } else {
-            if ((rc = ctx->rows.reserve((size_t)(cap + 2) * sizeof(fxg_fastq_row)))) return rc;
-            // rows are fully overwritten except partially-owned boundary rows
-            FXG_CUDA(cudaMemsetAsync(ctx->rows.ptr, 0, sizeof(fxg_fastq_row), ctx->stream));
+            const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * LG - 1) / (MARK_WARPS * LG));
+            lines_kernel<1><<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
         }
-        FXG_CUDA(cudaMemsetAsync(ctx->tile_desc.ptr, 0, (size_t)ntiles * 2 * sizeof(ulonglong2), ctx->stream));
-        FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 256, ctx->stream));
+    }
+    FXG_CUDA(cudaGetLastError());
 
-        ScanParams P;
-        memset(&P, 0, sizeof(P));
-        P.file = f->d; P.n = n; P.capacity = f->capacity & ~(int64_t)15; P.ntiles = ntiles;
-        P.base_offset = base_offset; P.first_line = first_line; P.flags = flags;
-        P.cnt = (ulonglong2 *)ctx->tile_desc.ptr; P.pos = P.cnt + ntiles;
-        P.tile_counter = (uint32_t *)ctx->counters.ptr;
-        P.totals = (ScanTotals *)((uint8_t *)ctx->counters.ptr + 64);
-        P.tmp = (FastaTmp *)ctx->row_tmp.ptr; P.tmp_cap = cap + 1;
-        P.qrows = (fxg_fastq_row *)ctx->rows.ptr; P.qrows_cap = cap;
-        const bool dbg = getenv("FXG_SCAN_DEBUG") != nullptr;
-        P.dbg = dbg ? (unsigned long long *)((uint8_t *)ctx->counters.ptr + 128) : nullptr;
-
+    stats->n_lines = (int64_t)tot.nl;
+    stats->end_position = tot.n_eff;
+    if (mode == 0) {
+        stats->n_rows = nrows;
+        if ((rc = ctx->rows.reserve((size_t)(nrows + 1) * sizeof(fxg_fasta_row)))) return rc;
+        const int64_t work = nrows > 0 ? nrows : 1;
         {
-            FxgProfScope prof(ctx, FXG_PROF_SCAN);
-            if (mode == 0) scan_kernel<0><<<grid, CTA_THREADS, smem, ctx->stream>>>(P);
-            else scan_kernel<1><<<grid, CTA_THREADS, smem, ctx->stream>>>(P);
+            FxgProfScope prof(ctx, FXG_PROF_FINALIZE);
+            fasta_finalize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(
+                P.tmp, nrows, base_offset, P.totals, (fxg_fasta_row *)ctx->rows.ptr);
         }
         FXG_CUDA(cudaGetLastError());
-
-        ScanTotals tot;
         FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
         FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-
-        if (dbg) {
-            unsigned long long h[8];
-            cudaMemcpy(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[fxg scan dbg] grid=%d tiles=%lld | worker cycles/tile: wait_data=%.0f phaseA=%.0f wait_pref=%.0f phaseC=%.0f | prefix warp: lookback=%.0f cyc/tile, windows=%.2f/tile, wait_mail=%.0f\n",
-                    grid, (long long)ntiles, (double)h[0] / ntiles, (double)h[1] / ntiles, (double)h[2] / ntiles, (double)h[3] / ntiles,
-                    (double)h[4] / (h[6] ? h[6] : 1), (double)h[5] / (h[6] ? h[6] : 1), (double)h[7] / (h[6] ? h[6] : 1));
-        }
-        const int64_t nrows = mode == 0 ? (int64_t)tot.hdr
-                                        : (int64_t)((first_line + (int64_t)tot.nl + 3) / 4 - first_line / 4);
-        if (nrows > cap) { cap = nrows + 16; continue; }   // estimate too small: exact rerun
-
-        stats->n_lines = (int64_t)tot.nl;
-        stats->end_position = tot.n_eff;
-        if (mode == 0) {
-            stats->n_rows = nrows;
-            if ((rc = ctx->rows.reserve((size_t)(nrows + 1) * sizeof(fxg_fasta_row)))) return rc;
-            const int64_t work = nrows > 0 ? nrows : 1;
-            {
-                FxgProfScope prof(ctx, FXG_PROF_FINALIZE);
-                fasta_finalize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(
-                    P.tmp, nrows, base_offset, P.totals, (fxg_fasta_row *)ctx->rows.ptr);
-            }
-            FXG_CUDA(cudaGetLastError());
-            FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
-            FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-            stats->total_len = (int64_t)tot.sum_len;
-            stats->lead_llen = tot.lead_llen;
-            if (nrows > 0) { stats->lead_lines = tot.lead_lines; stats->lead_bytes = tot.lead_bytes; }
-            else { stats->lead_lines = (int64_t)tot.nl; stats->lead_bytes = n; }
-        } else {
-            // complete reads only (fastq.c:132-146,159); rows owned partially by this buffer are
-            // still present in the array for the shard merge
-            stats->n_rows = (first_line + (int64_t)tot.nl) / 4 - first_line / 4;
-            stats->total_len = (int64_t)tot.sum_len;
-        }
-        if (d_rows_out) *d_rows_out = ctx->rows.ptr;
-        return FXG_OK;
+        stats->total_len = (int64_t)tot.sum_len;
+        stats->lead_llen = tot.lead_llen;
+        if (nrows > 0) { stats->lead_lines = tot.lead_lines; stats->lead_bytes = tot.lead_bytes; }
+        else { stats->lead_lines = (int64_t)tot.nl; stats->lead_bytes = n; }
+    } else {
+        FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+        FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+        // complete reads only (fastq.c:132-146,159); rows owned partially by this buffer are
+        // still present in the array for the shard merge
+        stats->n_rows = (first_line + (int64_t)tot.nl) / 4 - first_line / 4;
+        stats->total_len = (int64_t)tot.sum_len;
     }
-    fxg_set_error("scan: row capacity estimate failed to converge");
-    return FXG_ECUDA;
+    if (d_rows_out) *d_rows_out = ctx->rows.ptr;
+    return FXG_OK;
 }
 
 extern "C" int fxg_fasta_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int flags,
@@ -990,7 +928,7 @@ extern "C" int fxg_count_lines(fxg_ctx *ctx, const fxg_file *f, int64_t *n_newli
     FXG_CHECK_ARG(ctx && f && n_newlines, "null argument");
     FXG_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    if ((rc = ctx->counters.reserve(256))) return rc;
+    if ((rc = ctx->counters.reserve(512))) return rc;
     FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
     unsigned long long h = 0;
     uint8_t last = '\n';
