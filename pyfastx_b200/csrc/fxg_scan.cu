@@ -108,11 +108,15 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, 6) mark_kernel(const ScanPara
     const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
 
     uint4 v[4];
+    if (base + REGION <= n) {
+        const uint8_t *src = file + base + lane * 16;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t o = base + j * 512 + lane * 16;
-        if (o + 16 <= n) v[j] = ld_stream16(file + o);
-        else {
+        for (int j = 0; j < 4; ++j) v[j] = ld_stream16(src + j * 512);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t o = base + j * 512 + lane * 16;
+            if (o + 16 <= n) { v[j] = ld_stream16(file + o); continue; }
             // the chunk that contains EOF (or lies past it): bytes >= n read as 0, and a file that does
             // not end in '\n' gets a virtual newline at n (kseq returns the last line all the same)
             const bool virt = n > 0 && file[n - 1] != '\n';
@@ -129,23 +133,40 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, 6) mark_kernel(const ScanPara
     // ---- pass 1: positions, ranked in file order (chunk-major, lane-minor) ------------------
     uint32_t m[4];
     uint32_t nlc = 0;
-    bool multi = false;
+    int cmax = 0;
     uint16_t *ent = s_ent[warp];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         s_data[warp][j * 32 + lane] = v[j];
         m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80);
-        const int c = __popc(m[j]);
-        multi |= c > 1;
-        const uint32_t bn = __ballot_sync(0xffffffffu, c != 0);
-        if (c) {
-            const uint32_t idx = nlc + __popc(bn & lt_mask);
-            if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(j * 512 + lane * 16 + chunk_bit_to_off(__ffs(m[j]) - 1));
-        }
-        nlc += __popc(bn);
+        cmax = max(cmax, __popc(m[j]));
     }
-    if (__any_sync(0xffffffffu, multi)) {
-        // short lines: several newlines inside one lane's 16 bytes -> shuffle scan per chunk, then each lane
+    const bool any2 = __any_sync(0xffffffffu, cmax >= 2);          // e.g. the "+" line of a FASTQ record
+    const bool multi = any2 && __any_sync(0xffffffffu, cmax >= 3);
+    if (!multi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = __popc(m[j]);
+            const uint32_t bn1 = __ballot_sync(0xffffffffu, c >= 1);
+            const uint32_t bn2 = any2 ? __ballot_sync(0xffffffffu, c >= 2) : 0u;
+            if (c) {
+                const uint32_t idx = nlc + __popc(bn1 & lt_mask) + __popc(bn2 & lt_mask);
+                const int xo = j * 512 + lane * 16;
+                int oa = chunk_bit_to_off(__ffs(m[j]) - 1);
+                if (c == 2) {
+                    const uint32_t m2 = m[j] & (m[j] - 1);
+                    const int ob = chunk_bit_to_off(__ffs(m2) - 1);
+                    const int hi = max(oa, ob);
+                    oa = min(oa, ob);
+                    if (idx + 1 < (uint32_t)SEGCAP) ent[idx + 1] = (uint16_t)(xo + hi);
+                }
+                if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(xo + oa);
+            }
+            nlc += __popc(bn1) + __popc(bn2);
+        }
+    }
+    if (multi) {
+        // short lines: three or more newlines inside one lane's 16 bytes -> shuffle scan per chunk, then each lane
         // walks its own newlines in byte order (word, then byte within the word)
         nlc = 0;
 #pragma unroll 1
