@@ -700,6 +700,138 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams
     }
 }
 
+// FASTQ fast path: one LANE per read.  A warp takes RG consecutive regions, flattens their newline lists
+// (plus two look-ahead regions) into shared memory, and every lane assembles the whole 32-byte row of one
+// read from five consecutive newline positions -- straight-line code, one row store, the name cut searched
+// by all lanes at once.  Ownership: a warp covers every line inside its span (the up-to-three leading lines
+// of a read that began earlier are written field by field) and completes the reads that START in its span
+// as far as its window reaches; lines past the window are (also) covered by the warp that owns their
+// region, which writes identical values.  Spans containing a dense region use the general path.
+constexpr int RG = 8;                          // regions per warp
+constexpr int RWIN = RG + 2;                   // + look-ahead
+static_assert(RWIN * REGION <= 32768, "window positions must fit 15 bits");
+
+__global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const ScanParams P) {
+    __shared__ uint16_t s_flat[MARK_WARPS][RWIN * SEGCAP];      // position in window | '\r' before << 15
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r0 = ((int64_t)blockIdx.x * MARK_WARPS + warp) * RG;
+    if (r0 >= P.nreg) return;
+    unsigned long long my_size = 0;
+    const uint8_t *file = P.file;
+
+    // lane l <-> region r0 - 1 + l  (l = 0: the region before the span; 1..RG: the span; then the look-ahead)
+    const int64_t rl = r0 - 1 + lane;
+    uint2 rec = make_uint2(0u, 0u);
+    uint64_t exl = 0;
+    if (lane <= RWIN && rl >= 0 && rl < P.nreg) { rec = P.rc[rl]; exl = P.ex[rl].x; }
+    const uint32_t nll = rec.x & 0xffffu;
+    const uint32_t densem = __ballot_sync(0xffffffffu, nll > (uint32_t)SEGCAP);
+    if (densem & (((1u << RG) - 1u) << 1)) {                       // a dense region inside the span
+        for (int i = 0; i < RG; ++i)
+            if (r0 + i < P.nreg) full_region<1>(P, r0 + i, my_size);
+    } else {
+        const uint64_t ex0 = (uint64_t)shfl_i64((int64_t)exl, 1);    // lines before the span
+        // ---- flatten the window ----
+        uint16_t *flat = s_flat[warp];
+        int W = 0, Ls = 0;                                           // entries in the window / in the span
+#pragma unroll 1
+        for (int i = 0; i < RWIN; ++i) {
+            const int nl = (int)__shfl_sync(0xffffffffu, nll, i + 1);
+            if (nl > SEGCAP) break;                                  // dense look-ahead region: the window ends here
+            const uint16_t *sg = P.seg + (r0 + i) * SEGCAP;
+            for (int k = lane; k < nl; k += 32) {
+                const uint32_t e = sg[k];
+                flat[W + k] = (uint16_t)((i * REGION + (int)(e & E_POS)) | ((e & E_CR) ? 0x8000u : 0u));
+            }
+            W += nl;
+            if (i == RG - 1) Ls = W;
+        }
+        __syncwarp();
+        // ---- the newline before the span ----
+        int64_t carry;
+        {
+            const uint32_t pn = __shfl_sync(0xffffffffu, nll, 0), py = __shfl_sync(0xffffffffu, rec.y, 0);
+            if (r0 == 0) carry = -1;
+            else if (pn >= 1 && pn <= (uint32_t)SEGCAP) carry = (r0 - 1) * REGION + (int64_t)(py & E_POS);
+            else { Prev2 cy; carry_walk<1>(P, r0, cy); carry = cy.pos1; }
+        }
+        const int64_t span_base = r0 * REGION;
+        auto POS = [&](int f) -> int64_t { return f < 0 ? carry : span_base + (int64_t)(flat[f] & 0x7fffu); };
+        auto CR = [&](int f) -> bool { return (flat[f] & 0x8000u) != 0; };
+        const int64_t g0 = P.first_line + (int64_t)ex0;              // global line index of flat[0]
+        const int64_t row0 = P.first_line >> 2;
+        int lead = (int)((4 - (g0 & 3)) & 3);
+        if (lead > Ls) lead = Ls;
+        // ---- (a) leading lines of a read that started before the span: field by field ----
+        if (lane < lead) {
+            const int f = lane;
+            const int64_t g = g0 + f;
+            const int ph = (int)(g & 3);
+            const int64_t row = (g >> 2) - row0;
+            const int64_t pm1 = POS(f - 1), p = POS(f);
+            if (ph == 1) {
+                const int64_t len = p - pm1 - 1;
+                const int64_t rlen = (len > 0 && CR(f)) ? len - 1 : len;
+                my_size += (unsigned long long)rlen;
+                if (row < P.qrows_cap) { P.qrows[row].soff = P.base_offset + pm1 + 1; P.qrows[row].rlen = rlen; }
+            } else if (ph == 3) {
+                if (row < P.qrows_cap) P.qrows[row].qoff = P.base_offset + pm1 + 1;
+            }
+        }
+        // ---- (b) reads that start inside the span: one lane each ----
+        for (int fb = lead; fb < Ls; fb += 128) {
+            const int f = fb + 4 * lane;
+            if (f < Ls) {
+                const int64_t row = ((g0 + f) >> 2) - row0;
+                const bool have1 = f + 1 < W, have3 = f + 3 < W;
+                const int64_t pm1 = POS(f - 1), p0 = POS(f);
+                const int64_t len = p0 - pm1 - 1;                    // name line incl. '@' and '\r'
+                int64_t l = len - 1;
+                if (l > 0 && CR(f)) --l;
+                if (l < 0) l = 0;
+                const int64_t s = pm1 + 1;
+                int64_t k = 0;
+                if (s + 1 + l + 20 <= P.capacity) {
+                    int which;
+                    k = find_first_of2(file + s + 1, l, 0x20202020u, 0x00000000u, &which);
+                    if (which == 2) k = l;          // a NUL before any space: strchr() finds nothing (fastq.c:112)
+                } else {
+                    for (; k < l; ++k) {
+                        const uint8_t ch = file[s + 1 + k];
+                        if (ch == 0) { k = l; break; }
+                        if (ch == ' ') break;
+                    }
+                }
+                int64_t soff = 0, rlen = 0, qoff = 0;
+                if (have1) {
+                    const int64_t p1 = POS(f + 1);
+                    const int64_t len1 = p1 - p0 - 1;
+                    soff = P.base_offset + p0 + 1;
+                    rlen = (len1 > 0 && CR(f + 1)) ? len1 - 1 : len1;
+                    if (f + 1 < Ls) my_size += (unsigned long long)rlen;
+                }
+                if (have3) qoff = P.base_offset + POS(f + 2) + 1;
+                if (row < P.qrows_cap) {
+                    fxg_fastq_row *q = &P.qrows[row];
+                    if (have3) {
+                        longlong2 a, b;
+                        a.x = soff; a.y = qoff;
+                        b.x = rlen; b.y = (long long)(((unsigned long long)(uint32_t)(int)k << 32) | (uint32_t)(int)len);
+                        reinterpret_cast<longlong2 *>(q)[0] = a;
+                        reinterpret_cast<longlong2 *>(q)[1] = b;
+                    } else {
+                        *reinterpret_cast<int2 *>(&q->dlen) = make_int2((int)len, (int)k);
+                        if (have1) { q->soff = soff; q->rlen = rlen; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_size += (unsigned long long)shfl_down_i64((int64_t)my_size, d);
+    if (lane == 0 && my_size) atomicAdd((unsigned long long *)&P.totals->sum_len, my_size);
+}
+
 // FASTA: almost no line does work (only header lines, the line after a header, and lines whose length
 // differs from the previous line's).  One LANE per region screens it from the region records the mark
 // kernel left behind and then walks just those lines; regions the records cannot settle (more than 32
@@ -898,8 +1030,13 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
             const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * 32 - 1) / (MARK_WARPS * 32));
             fasta_lines_kernel<<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
         } else {
-            const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * LG - 1) / (MARK_WARPS * LG));
-            lines_kernel<1><<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+            if (getenv("FXG_FASTQ_LINES_GENERIC")) {      // lane-per-line path for every region (A/B, debugging)
+                const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * LG - 1) / (MARK_WARPS * LG));
+                lines_kernel<1><<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+            } else {
+                const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * RG - 1) / (MARK_WARPS * RG));
+                fastq_records_kernel<<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+            }
         }
     }
     FXG_CUDA(cudaGetLastError());
