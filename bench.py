@@ -39,6 +39,19 @@ def log(*a):
 # ---------------------------------------------------------------------------------------------
 # helpers
 # ---------------------------------------------------------------------------------------------
+def ncu_traffic(kernel, alg_bytes):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum next to the algorithmic bytes of the captured launch).  The
+    capture is of this same workload; a different --records / --queries scales it by the algorithmic bytes."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        ratio = t["dram_bytes"] / t["algorithmic_bytes"]
+        return {"traffic": ratio * alg_bytes, "traffic_over_algorithmic": ratio,
+                "traffic_source": "profiles/r01_traffic.json (%s)" % t["capture"]}
+    except Exception:
+        return {"traffic": None}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -299,7 +312,8 @@ def run_b200(args):
                      "unit": "GB/s", "frac": scan_achieved / peak_gbs, "frac_of_nominal_8TBs": scan_achieved / 8000.0,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": scan_alg_bytes,
                      "kernel_ms": scan_kernel_ms, "prefix_kernels_ms": float(np.mean(pre_ms)),
-                     "lines_kernel_ms": float(np.mean(lin_ms)), "finalize_kernel_ms": float(np.mean(fin_ms)), "traffic": None},
+                     "lines_kernel_ms": float(np.mean(lin_ms)), "finalize_kernel_ms": float(np.mean(fin_ms)),
+                     **ncu_traffic("mark_kernel", scan_alg_bytes)},
     }
 
     # ---- extraction (C3): device-resident ---------------------------------------------------
@@ -353,7 +367,8 @@ def run_b200(args):
         "gpu_launches": int(x_launches),
         "roofline": {"bound": "hbm", "kernel": "extract_kernel", "achieved": ext_achieved, "peak": peak_gbs,
                      "unit": "GB/s", "frac": ext_achieved / peak_gbs, "frac_of_nominal_8TBs": ext_achieved / 8000.0,
-                     "algorithmic_bytes_per_launch": ext_alg_bytes, "kernel_ms": g_ms, "traffic": None},
+                     "algorithmic_bytes_per_launch": ext_alg_bytes, "kernel_ms": g_ms,
+                     **ncu_traffic("extract_kernel", ext_alg_bytes)},
     }
 
     # ---- end-to-end through the C-ABI with HOST buffers (rank-local, N=1 semantics per rank) ---

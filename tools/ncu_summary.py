@@ -39,8 +39,10 @@ def main():
     hdr, unit_row = raw[0], raw[1]
     idx = {h: i for i, h in enumerate(hdr)}
     print("# %s  (ncu --set full --clock-control none; times under the profiler are NOT bench values)" % args.report)
+    inst_total = {}
     for r in raw[2:]:
         name = r[idx["Kernel Name"]]
+        inst_total[name.replace("void ", "").strip()] = float(r[idx["smsp__inst_executed.sum"]])
         print("\n== %s" % name)
         for k in KEYS:
             if k in idx:
@@ -75,6 +77,10 @@ def main():
             n = float(r[ie])
             ops[op] = ops.get(op, 0.0) + n
             tot += n
+        # the source page can list an instruction more than once (inlined copies); rescale to the raw counter
+        want = inst_total.get(name.replace("void ", "").replace("fxg::", "").replace("(int)", "").replace("(bool)", "").strip(), tot)
+        scale = want / tot if tot else 1.0
+        div = div / scale
         print("\n== SASS opcode histogram, %s: %s  [%d SASS instructions, %.1f warp-instructions %s]"
               % (name, label, len(rows), tot / div, label))
         print("  " + ", ".join("%s %.1f" % (k, v / div) for k, v in sorted(ops.items(), key=lambda x: -x[1])[:18]))
