@@ -15,6 +15,7 @@
 // at their output position (mirrored for reverse strands), then flushed with aligned
 // 16-byte stores; only the ragged first/last words of a round use byte stores.
 #include "fxg_common.cuh"
+#include <stdlib.h>
 
 namespace fxg {
 
@@ -331,8 +332,49 @@ __device__ __forceinline__ void init_luts(uint8_t (*s_lut)[256]) {
     }
 }
 
+// ---- whole-warp service of one query: the uniform-line pull path, else the general strip path ----
 template <bool WANT_ACGT>
-__global__ void __launch_bounds__(XTHREADS, 4) extract_kernel(
+__device__ void serve_query_warp(const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity,
+                                 const fxg_fasta_row &r, bool row_ok, int64_t s, int64_t e, int flags, uint8_t *dst,
+                                 const uint8_t (*__restrict__ s_lut)[256], uint8_t *__restrict__ stage, int lane,
+                                 int64_t *acgt_q) {
+    GatherJob job;
+    job.flags = flags;
+    job.dst = dst;
+    job.skip = 0;
+    job.src = 0; job.src_len = 0;
+    job.out_len = e > s ? e - s : 0;
+    bool done = false;
+    if (row_ok && job.out_len > 0) {
+        const int64_t bpl = r.llen - (int64_t)r.elen;
+        const bool whole = (s == 0 && e == r.slen);
+        const bool uniform = (r.pad[0] & 1) != 0;
+        // fast path: uniform lines, sane sizes, source window inside the buffer
+        if (r.norm && uniform && bpl >= 16 && bpl < (1ll << 30) && job.out_len < (1ll << 30) && e <= r.slen &&
+            r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW)) {
+            done = pull_one<WANT_ACGT>(file, r.boff, s, job.out_len, (uint32_t)bpl, (int)r.elen, flags, job.dst, s_lut,
+                                       lane, acgt_q);
+        }
+        if (!done) {
+            const bool formula_ok = !(flags & FXG_X_WHOLE) || uniform;
+            if (r.norm && bpl > 0 && !whole && formula_ok) {
+                const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
+                job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
+                job.src_len = (e - s) + (be - bs) * (int64_t)r.elen;            // sequence.c:509
+            } else {
+                job.src = r.boff; job.src_len = r.blen; job.skip = s;           // sequence.c:100-102,108-110
+            }
+        }
+    }
+    if (!done) {
+        if (job.out_len > 0) gather_one<WANT_ACGT>(file, fsize, job, s_lut[0], stage, lane, acgt_q);
+        else if (WANT_ACGT && lane == 0) { acgt_q[0] = acgt_q[1] = acgt_q[2] = acgt_q[3] = 0; }
+    }
+}
+
+// One warp per query (used when per-query A/C/G/T counts are requested).
+template <bool WANT_ACGT>
+__global__ void __launch_bounds__(XTHREADS, 3) extract_kernel(
     const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fasta_row *__restrict__ rows,
     int64_t n_rows, const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s,
     const int64_t *__restrict__ q_e, const int32_t *__restrict__ q_flags, int64_t nq,
@@ -367,43 +409,177 @@ __global__ void __launch_bounds__(XTHREADS, 4) extract_kernel(
     for (; q < nq; q += nwarps) {
         const Desc d2 = load_desc(q + 2 * nwarps);
         const RowU r1 = load_row(d1.rid);
-        const int64_t rid = d0.rid, s = d0.s, e = d0.e;
-        const int flags = d0.flags;
-        GatherJob job;
-        job.flags = flags;
-        job.dst = out + d0.off;
-        job.skip = 0;
-        job.src = 0; job.src_len = 0;
-        job.out_len = e > s ? e - s : 0;
-        bool done = false;
-        if (rid >= 0 && rid < n_rows && job.out_len > 0) {
-            const fxg_fasta_row &r = r0.r;
-            const int64_t bpl = r.llen - (int64_t)r.elen;
-            const bool whole = (s == 0 && e == r.slen);
-            const bool uniform = (r.pad[0] & 1) != 0;
-            // fast path: uniform lines, sane sizes, source window inside the buffer
-            if (r.norm && uniform && bpl >= 16 && bpl < (1ll << 30) && job.out_len < (1ll << 30) && e <= r.slen &&
-                r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW)) {
-                done = pull_one<WANT_ACGT>(file, r.boff, s, job.out_len, (uint32_t)bpl, (int)r.elen, flags, job.dst, s_lut,
-                                           lane, WANT_ACGT ? acgt + 4 * q : nullptr);
+        serve_query_warp<WANT_ACGT>(file, fsize, capacity, r0.r, d0.rid >= 0 && d0.rid < n_rows, d0.s, d0.e, d0.flags,
+                                    out + d0.off, s_lut, s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
+        d0 = d1; d1 = d2; r0 = r1;
+    }
+}
+
+// ---- eight lanes per query ---------------------------------------------------------------------------
+// The per-query bookkeeping of the pull path (descriptor, index row, slice -> byte-range arithmetic) is
+// warp-uniform work when a warp serves one query; with a query per 8-lane group the same instructions
+// serve four queries, and every lane still assembles whole aligned 16-byte output words.
+constexpr int QG = 8;                 // lanes per query
+constexpr int QPW = 32 / QG;          // queries per warp and step
+
+// The 16 output bytes [j0, j0+16) of a query (0 <= j0 <= out_len-16) as four little-endian words.
+// fq = file + boff + s + elen*(s/bpl): source address of kept rank 0;  rem_s = s % bpl;  inv = 2^32 / bpl.
+// Returns false if the bytes contradict the uniform-line layout (the query is then redone by the general path).
+__device__ __forceinline__ bool outword16(const uint8_t *__restrict__ fq, uint32_t rem_s, uint32_t bpl, uint32_t inv,
+                                          int elen, uint32_t out_len, bool rev, bool xform,
+                                          const uint8_t *__restrict__ tbl, uint32_t j0, uint32_t o[4]) {
+    const uint32_t r = rev ? out_len - 16u - j0 : j0;               // first kept rank of the word (source order)
+    const uint32_t t = rem_s + r;
+    uint32_t dq = __umulhi(t, inv);                                  // t / bpl: one below at most
+    uint32_t rr = t - dq * bpl;
+    if (rr >= bpl) { ++dq; rr -= bpl; }
+    const uint32_t c = bpl - rr;                                     // bytes left on this line
+    const uint8_t *p = fq + (r + (uint32_t)elen * dq);              // slice formula, sequence.c:498-510
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    const int o1 = (int)(reinterpret_cast<uintptr_t>(p) & 3);
+    uint32_t W[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) W[i] = wp[i];
+    uint32_t V[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) V[i] = __funnelshift_r(W[i], W[i + 1], o1 * 8);
+    bool ok = true;
+    if (c < 16u) {                                                   // one line break inside the word
+        if (elen == 2) {                                             // the first skipped byte must be '\r'
+            const uint32_t vw = c < 8u ? (c < 4u ? V[0] : V[1]) : (c < 12u ? V[2] : V[3]);
+            ok = ((vw >> (8 * (c & 3u))) & 0xffu) == 0x0du;
+        }
+        const int o2 = o1 + elen, ws2 = o2 >> 2, bs2 = (o2 & 3) * 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t lo_w = ws2 ? W[i + 1] : W[i], hi_w = ws2 ? W[(i + 2 < 6) ? i + 2 : 5] : W[i + 1];
+            const uint32_t e2 = __funnelshift_r(lo_w, hi_w, bs2);
+            const int rel = (int)c - 4 * i;                          // bytes of this word taken before the break
+            const uint32_t m = rel <= 0 ? 0xffffffffu : (rel >= 4 ? 0u : (0xffffffffu << (8 * rel)));
+            V[i] = (V[i] & ~m) | (e2 & m);
+        }
+    }
+    // conservative layout check: every kept byte must be >= 0x40 (letters); see pull_one
+    const uint32_t all = (V[0] | (V[0] >> 1)) & (V[1] | (V[1] >> 1)) & (V[2] | (V[2] >> 1)) & (V[3] | (V[3] >> 1));
+    ok = ok && (all & 0x40404040u) == 0x40404040u;
+    if (xform) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = V[i];
+            V[i] = (uint32_t)tbl[x & 0xff] | ((uint32_t)tbl[(x >> 8) & 0xff] << 8) |
+                   ((uint32_t)tbl[(x >> 16) & 0xff] << 16) | ((uint32_t)tbl[x >> 24] << 24);
+        }
+    }
+    if (rev) {
+        o[0] = __byte_perm(V[3], 0, 0x0123); o[1] = __byte_perm(V[2], 0, 0x0123);
+        o[2] = __byte_perm(V[1], 0, 0x0123); o[3] = __byte_perm(V[0], 0, 0x0123);
+    } else { o[0] = V[0]; o[1] = V[1]; o[2] = V[2]; o[3] = V[3]; }
+    return ok;
+}
+
+__global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
+    const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fasta_row *__restrict__ rows,
+    int64_t n_rows, const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s,
+    const int64_t *__restrict__ q_e, const int32_t *__restrict__ q_flags, int64_t nq,
+    const int64_t *__restrict__ out_off, uint8_t *__restrict__ out) {
+    __shared__ uint8_t s_lut[3][256];
+    __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
+    init_luts(s_lut);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / QG, li = lane % QG;
+    const int64_t step = (int64_t)gridDim.x * XWARPS * QPW;
+    for (int64_t qb = ((int64_t)blockIdx.x * XWARPS + warp) * QPW; qb < nq; qb += step) {
+        const int64_t q = qb + grp;
+        const bool valid = q < nq;
+        int64_t rid = -1, s = 0, e = 0, off = 0;
+        int flags = 0;
+        if (valid) { rid = q_row[q]; s = q_s[q]; e = q_e[q]; off = out_off[q]; flags = q_flags ? q_flags[q] : 0; }
+        const bool row_ok = rid >= 0 && rid < n_rows;
+        union RowU { fxg_fasta_row r; uint4 v[3]; } ru;
+        ru.v[0] = ru.v[1] = ru.v[2] = make_uint4(0, 0, 0, 0);
+        if (row_ok) {
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(rows + rid);
+            ru.v[0] = p4[0]; ru.v[1] = p4[1]; ru.v[2] = p4[2];
+        }
+        const fxg_fasta_row &r = ru.r;
+        const int64_t out_len64 = e > s ? e - s : 0;
+        const int64_t bpl64 = r.llen - (int64_t)r.elen;
+        const bool fast = row_ok && out_len64 >= 16 && out_len64 < (1ll << 30) && r.norm && (r.pad[0] & 1) != 0 &&
+                          bpl64 >= 16 && bpl64 < (1ll << 30) && s >= 0 && s < (1ll << 32) && e <= r.slen &&
+                          r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW);
+        bool bad = false;
+        if (fast) {
+            const uint32_t bpl = (uint32_t)bpl64, out_len = (uint32_t)out_len64;
+            const int elen = (int)r.elen;
+            const uint32_t q_s32 = (uint32_t)s / bpl, rem_s = (uint32_t)s - q_s32 * bpl;
+            const uint32_t inv = (uint32_t)(0x100000000ull / bpl);
+            const uint8_t *fq = file + r.boff + s + (int64_t)elen * (int64_t)q_s32;
+            const bool rev = (flags & FXG_X_REVERSE) != 0;
+            const bool upper = (flags & FXG_X_UPPER) != 0, comp = (flags & FXG_X_COMPLEMENT) != 0;
+            const uint8_t *tbl = comp ? (upper ? s_lut[2] : s_lut[0]) : s_lut[1];
+            const bool xform = upper || comp;
+            uint8_t *dst = out + off;
+            const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15);
+            const uint32_t total = a + out_len;
+            const uint32_t nwords = (total + 15u) >> 4, hi_last = total & 15u;
+            const uint32_t w_begin = a ? 1u : 0u, w_end = nwords - (hi_last ? 1u : 0u);
+            uint8_t *dst0 = dst - a;                                     // 16-byte aligned
+            // interior words: all 16 slots belong to the query
+            for (uint32_t w = w_begin + (uint32_t)li; w < w_end; w += QG) {
+                uint32_t o[4];
+                if (!outword16(fq, rem_s, bpl, inv, elen, out_len, rev, xform, tbl, 16u * w - a, o)) bad = true;
+                *reinterpret_cast<uint4 *>(dst0 + 16u * w) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            if (!done) {
-                const bool formula_ok = !(flags & FXG_X_WHOLE) || uniform;
-                if (r.norm && bpl > 0 && !whole && formula_ok) {
-                    const int64_t bs = s / bpl, be = e / bpl;                       // sequence.c:500-503
-                    job.src = r.boff + s + (int64_t)r.elen * bs;                    // sequence.c:508
-                    job.src_len = (e - s) + (be - bs) * (int64_t)r.elen;            // sequence.c:509
+            // ragged first / last word: take the nearest complete 16 output bytes and shift them into place
+            const bool first = li == 0;
+            if (li < 2 && (first ? a != 0u : hi_last != 0u)) {
+                uint32_t o[4];
+                if (!outword16(fq, rem_s, bpl, inv, elen, out_len, rev, xform, tbl, first ? 0u : out_len - 16u, o)) bad = true;
+                uint64_t lo = (uint64_t)o[0] | ((uint64_t)o[1] << 32), hi = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
+                uint32_t b_lo, b_hi;                                     // slots [b_lo, b_hi) of the word are ours
+                uint8_t *gw;
+                if (first) {
+                    const uint32_t sh = 8u * a;                          // outputs 0.. move up to slot a
+                    if (sh < 64u) { hi = (hi << sh) | (lo >> (64u - sh)); lo <<= sh; } else { hi = lo << (sh - 64u); lo = 0; }
+                    b_lo = a; b_hi = 16u; gw = dst0;
                 } else {
-                    job.src = r.boff; job.src_len = r.blen; job.skip = s;           // sequence.c:100-102,108-110
+                    const uint32_t sh = 8u * (16u - hi_last);            // the last hi_last outputs move down to slot 0
+                    if (sh < 64u) { lo = (lo >> sh) | (hi << (64u - sh)); hi >>= sh; } else { lo = hi >> (sh - 64u); hi = 0; }
+                    b_lo = 0u; b_hi = hi_last; gw = dst0 + 16u * (nwords - 1u);
+                }
+                const uint32_t x[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i) {
+                    const uint32_t b0 = 4u * i;
+                    if (b_lo <= b0 && b0 + 4u <= b_hi) *reinterpret_cast<uint32_t *>(gw + b0) = x[i];
+                    else {
+#pragma unroll
+                        for (uint32_t b = 0; b < 4; ++b)
+                            if (b0 + b >= b_lo && b0 + b < b_hi) gw[b0 + b] = (uint8_t)(x[i] >> (8u * b));
+                    }
                 }
             }
         }
-        if (!done) {
-            if (job.out_len > 0)
-                gather_one<WANT_ACGT>(file, fsize, job, s_lut[0], s_stage[warp], lane, WANT_ACGT ? acgt + 4 * q : nullptr);
-            else if (WANT_ACGT && lane == 0) { acgt[4 * q] = acgt[4 * q + 1] = acgt[4 * q + 2] = acgt[4 * q + 3] = 0; }
+        // queries the group path could not serve (or that failed its layout check): whole warp, one at a time
+        const uint32_t badm = __ballot_sync(0xffffffffu, bad);
+        const bool group_bad = ((badm >> (grp * QG)) & ((1u << QG) - 1u)) != 0;
+        uint32_t fb = __ballot_sync(0xffffffffu, li == 0 && valid && out_len64 > 0 && (!fast || group_bad));
+        while (fb) {
+            const int src = __ffs(fb) - 1;
+            fb &= fb - 1;
+            const int64_t b_rid = shfl_i64(rid, src), b_s = shfl_i64(s, src), b_e = shfl_i64(e, src), b_off = shfl_i64(off, src);
+            const int b_flags = __shfl_sync(0xffffffffu, flags, src);
+            const bool b_ok = b_rid >= 0 && b_rid < n_rows;
+            RowU bu;
+            bu.v[0] = bu.v[1] = bu.v[2] = make_uint4(0, 0, 0, 0);
+            if (b_ok) {
+                const uint4 *p4 = reinterpret_cast<const uint4 *>(rows + b_rid);
+                bu.v[0] = p4[0]; bu.v[1] = p4[1]; bu.v[2] = p4[2];
+            }
+            serve_query_warp<false>(file, fsize, capacity, bu.r, b_ok, b_s, b_e, b_flags, out + b_off, s_lut, s_stage[warp],
+                                    lane, nullptr);
         }
-        d0 = d1; d1 = d2; r0 = r1;
     }
 }
 
@@ -602,9 +778,16 @@ extern "C" int fxg_extract_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_
     if (d_acgt)
         extract_kernel<true><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e,
                                                                 d_flags, nq, d_out_off, d_out, d_acgt);
-    else
+    else if (getenv("FXG_EXTRACT_WARP_PER_QUERY"))          // A/B and debugging
         extract_kernel<false><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e,
                                                                  d_flags, nq, d_out_off, d_out, nullptr);
+    else {
+        int64_t blocks = (nq + XWARPS * QPW - 1) / (XWARPS * QPW);
+        const int64_t maxb = (int64_t)ctx->sm_count * 6;
+        if (blocks > maxb) blocks = maxb;
+        extract_group_kernel<<<(unsigned)blocks, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id,
+                                                                            d_s, d_e, d_flags, nq, d_out_off, d_out);
+    }
     FXG_CUDA(cudaGetLastError());
     return FXG_OK;
 }
