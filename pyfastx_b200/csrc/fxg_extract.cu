@@ -419,27 +419,44 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_kernel(
 // The per-query bookkeeping of the pull path (descriptor, index row, slice -> byte-range arithmetic) is
 // warp-uniform work when a warp serves one query; with a query per 8-lane group the same instructions
 // serve four queries, and every lane still assembles whole aligned 16-byte output words.
-constexpr int QG = 8;                 // lanes per query
+#ifndef FXG_QG
+#define FXG_QG 8
+#endif
+constexpr int QG = FXG_QG;            // lanes per query
 constexpr int QPW = 32 / QG;          // queries per warp and step
+#ifndef FXG_XU
+#define FXG_XU 4
+#endif
+constexpr int XU = FXG_XU;            // output words per lane and step
 
-// The 16 output bytes [j0, j0+16) of a query (0 <= j0 <= out_len-16) as four little-endian words.
+// The 16 output bytes [j0, j0+16) of a query (0 <= j0 <= out_len-16) as four little-endian words, in two
+// steps so that the loads of several words can be in flight together.
 // fq = file + boff + s + elen*(s/bpl): source address of kept rank 0;  rem_s = s % bpl;  inv = 2^32 / bpl.
-// Returns false if the bytes contradict the uniform-line layout (the query is then redone by the general path).
-__device__ __forceinline__ bool outword16(const uint8_t *__restrict__ fq, uint32_t rem_s, uint32_t bpl, uint32_t inv,
-                                          int elen, uint32_t out_len, bool rev, bool xform,
-                                          const uint8_t *__restrict__ tbl, uint32_t j0, uint32_t o[4]) {
+struct WordReq { const uint32_t *wp; int o1; uint32_t c; };
+
+__device__ __forceinline__ WordReq ow_locate(const uint8_t *__restrict__ fq, uint32_t rem_s, uint32_t bpl, uint32_t inv,
+                                             int elen, uint32_t out_len, bool rev, uint32_t j0) {
     const uint32_t r = rev ? out_len - 16u - j0 : j0;               // first kept rank of the word (source order)
     const uint32_t t = rem_s + r;
     uint32_t dq = __umulhi(t, inv);                                  // t / bpl: one below at most
     uint32_t rr = t - dq * bpl;
     if (rr >= bpl) { ++dq; rr -= bpl; }
-    const uint32_t c = bpl - rr;                                     // bytes left on this line
+    WordReq q;
+    q.c = bpl - rr;                                                  // bytes left on this line
     const uint8_t *p = fq + (r + (uint32_t)elen * dq);              // slice formula, sequence.c:498-510
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
-    const int o1 = (int)(reinterpret_cast<uintptr_t>(p) & 3);
-    uint32_t W[6];
+    q.wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+    q.o1 = (int)(reinterpret_cast<uintptr_t>(p) & 3);
+    return q;
+}
+__device__ __forceinline__ void ow_load(const WordReq &q, uint32_t W[6]) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) W[i] = wp[i];
+    for (int i = 0; i < 6; ++i) W[i] = __ldg(q.wp + i);
+}
+// Returns false if the bytes contradict the uniform-line layout (the query is then redone by the general path).
+__device__ __forceinline__ bool ow_finish(const uint32_t W[6], const WordReq &q, int elen, bool rev, bool xform,
+                                          const uint8_t *__restrict__ tbl, uint32_t o[4]) {
+    const int o1 = q.o1;
+    const uint32_t c = q.c;
     uint32_t V[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) V[i] = __funnelshift_r(W[i], W[i + 1], o1 * 8);
@@ -526,16 +543,33 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
             const uint32_t w_begin = a ? 1u : 0u, w_end = nwords - (hi_last ? 1u : 0u);
             uint8_t *dst0 = dst - a;                                     // 16-byte aligned
             // interior words: all 16 slots belong to the query
-            for (uint32_t w = w_begin + (uint32_t)li; w < w_end; w += QG) {
-                uint32_t o[4];
-                if (!outword16(fq, rem_s, bpl, inv, elen, out_len, rev, xform, tbl, 16u * w - a, o)) bad = true;
-                *reinterpret_cast<uint4 *>(dst0 + 16u * w) = make_uint4(o[0], o[1], o[2], o[3]);
+            // (XU words per lane and step: 6 * XU loads in flight)
+            for (uint32_t w = w_begin + (uint32_t)li; w < w_end; w += XU * QG) {
+                WordReq rq[XU];
+                uint32_t WW[XU][6], o[4];
+#pragma unroll
+                for (int u = 0; u < XU; ++u) {
+                    const uint32_t wu = w + u * QG;
+                    rq[u] = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, 16u * (wu < w_end ? wu : w) - a);
+                }
+#pragma unroll
+                for (int u = 0; u < XU; ++u) ow_load(rq[u], WW[u]);
+#pragma unroll
+                for (int u = 0; u < XU; ++u) {
+                    const uint32_t wu = w + u * QG;
+                    if (u == 0 || wu < w_end) {
+                        if (!ow_finish(WW[u], rq[u], elen, rev, xform, tbl, o)) bad = true;
+                        *reinterpret_cast<uint4 *>(dst0 + 16u * wu) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
             }
             // ragged first / last word: take the nearest complete 16 output bytes and shift them into place
             const bool first = li == 0;
             if (li < 2 && (first ? a != 0u : hi_last != 0u)) {
-                uint32_t o[4];
-                if (!outword16(fq, rem_s, bpl, inv, elen, out_len, rev, xform, tbl, first ? 0u : out_len - 16u, o)) bad = true;
+                uint32_t o[4], WE[6];
+                const WordReq re = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, first ? 0u : out_len - 16u);
+                ow_load(re, WE);
+                if (!ow_finish(WE, re, elen, rev, xform, tbl, o)) bad = true;
                 uint64_t lo = (uint64_t)o[0] | ((uint64_t)o[1] << 32), hi = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
                 uint32_t b_lo, b_hi;                                     // slots [b_lo, b_hi) of the word are ours
                 uint8_t *gw;
