@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_kernel(
 // warp-uniform work when a warp serves one query; with a query per 8-lane group the same instructions
 // serve four queries, and every lane still assembles whole aligned 16-byte output words.
 #ifndef FXG_QG
-#define FXG_QG 8
+#define FXG_QG 4
 #endif
 constexpr int QG = FXG_QG;            // lanes per query
 constexpr int QPW = 32 / QG;          // queries per warp and step
