@@ -404,6 +404,27 @@ def run_b200(args):
     result["e2e"] = {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": shard_bytes, "d2h_bytes_per_step": n_rows * 48,
                      "steps": e2e_steps, "api": "fxg_fasta_build_index_host (pinned host file -> HBM -> rows on host)"}
 
+    # .fxi write (SURVEY 8d scope E, its own line): names gathered on the GPU, rows + names -> sqlite file with
+    # the reference's schema and UNIQUE index.  CPU-bound, single-threaded sqlite; not part of `e2e`.
+    if rank == 0 and world == 1 and args.e2e_steps > 0:
+        from pyfastx_b200 import fxi
+        t0 = time.perf_counter()
+        name_off = rows["boff"] - rows["elen"].astype(np.int64) - rows["dlen"]
+        nbuf, noff = eng.gather_ranges(dfile, name_off, rows["nlen"].astype(np.int64))
+        raw = nbuf.tobytes()
+        names = [raw[noff[i]:noff[i + 1]] for i in range(n_rows)]
+        t1 = time.perf_counter()
+        fxi_path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir(), "bench_%d.fxi" % os.getpid())
+        if os.path.exists(fxi_path):
+            os.remove(fxi_path)
+        con = fxi.write_fasta_index(fxi_path, rows, names, int(st["total_len"]))
+        con.close()
+        t2 = time.perf_counter()
+        result["fxi_write"] = {"seconds": t2 - t0, "name_gather_seconds": t1 - t0, "sqlite_seconds": t2 - t1, "rows": int(n_rows),
+                               "file_bytes": os.path.getsize(fxi_path), "GB_of_fasta_per_s": shard_bytes / (t2 - t0) / 1e9,
+                               "note": "reference schema (seq + stat tables, UNIQUE chromidx), tmpfs; python sqlite3 executemany"}
+        os.remove(fxi_path)
+
     # extraction e2e: host queries -> host output
     out_host, hp2 = pinned_array(bases + 64, np.uint8)
     q_pinned = []
