@@ -33,6 +33,9 @@
 
 namespace fxg {
 
+#ifndef FXG_MARK_MINB
+#define FXG_MARK_MINB 6
+#endif
 constexpr int REGION   = 2048;            // bytes per warp
 constexpr int SEGCAP   = 128;             // newline-list entries kept per region (lines >= 16 B on average)
 constexpr int MARK_WARPS = 8;             // warps per CTA of the mark / lines kernels
@@ -95,7 +98,7 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
 // mark: newline list + counts of one 2 KiB region per warp
 // =============================================================================================
 template <int MODE>   // 0 = FASTA, 1 = FASTQ
-__global__ void __launch_bounds__(MARK_WARPS * 32, 6) mark_kernel(const ScanParams P) {
+__global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(const ScanParams P) {
     __shared__ uint4    s_data[MARK_WARPS][REGION / 16];   // the region's bytes (neighbour-byte lookups)
     __shared__ uint16_t s_ent[MARK_WARPS][SEGCAP];         // newline positions, then complete entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,12 +146,23 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, 6) mark_kernel(const ScanPara
     }
     const bool any2 = __any_sync(0xffffffffu, cmax >= 2);          // e.g. the "+" line of a FASTQ record
     const bool multi = any2 && __any_sync(0xffffffffu, cmax >= 3);
-    if (!multi) {
+    if (!any2) {
+        // the usual FASTA case: no lane holds two newlines in its 16 bytes -> one ballot per chunk
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t bn = __ballot_sync(0xffffffffu, m[j] != 0);
+            if (m[j]) {
+                const uint32_t idx = nlc + __popc(bn & lt_mask);
+                if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(j * 512 + lane * 16 + chunk_bit_to_off(__ffs(m[j]) - 1));
+            }
+            nlc += __popc(bn);
+        }
+    } else if (!multi) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = __popc(m[j]);
             const uint32_t bn1 = __ballot_sync(0xffffffffu, c >= 1);
-            const uint32_t bn2 = any2 ? __ballot_sync(0xffffffffu, c >= 2) : 0u;
+            const uint32_t bn2 = __ballot_sync(0xffffffffu, c >= 2);
             if (c) {
                 const uint32_t idx = nlc + __popc(bn1 & lt_mask) + __popc(bn2 & lt_mask);
                 const int xo = j * 512 + lane * 16;
