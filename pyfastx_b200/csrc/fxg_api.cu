@@ -74,14 +74,6 @@ extern "C" int fxg_ctx_create(int device, fxg_ctx **out) {
         fxg_set_error("device %d is sm_%d%d; libfxg is built for sm_100a only", device, prop.major, prop.minor);
         return FXG_ENODEV;
     }
-    if (const char *g = getenv("FXG_L2_FETCH_BYTES")) {       // experiment hook: 32 / 64 / 128
-        const size_t want = (size_t)atoi(g);
-        size_t got = 0;
-        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want);
-        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        fprintf(stderr, "[fxg] L2 fetch granularity: asked %zu, have %zu\n", want, got);
-        cudaGetLastError();
-    }
     fxg_ctx *c = new fxg_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
