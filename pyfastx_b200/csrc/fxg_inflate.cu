@@ -18,22 +18,42 @@
 
 namespace fxg {
 
-constexpr int IW = 8;                 // warps (members in flight) per CTA
+constexpr int SHORT_MATCH = 24;        // matches up to this length are copied by the decoding lane itself
+constexpr int IW = 6;                 // warps (members in flight) per CTA
 constexpr int LIT_BITS = 10, DIST_BITS = 9;
 
 struct __align__(8) WarpTables {
-    uint16_t lit[1 << LIT_BITS];      // (len << 9) | symbol, 0 = code longer than LIT_BITS
+    uint32_t lit[1 << LIT_BITS];      // low half: (len << 9) | symbol, 0 = code longer than LIT_BITS;
+                                      // high half (TWO_LIT set): a second literal decodable from the same bits:
+                                      // TWO_LIT | total length << 24 | second symbol << 16
     uint16_t dist[1 << DIST_BITS];    // (len << 5) | symbol
     uint16_t litcnt[16], litsym[288];     // canonical tables for the slow path (long codes)
     uint16_t distcnt[16], distsym[32];
     uint8_t  lens[320];
 };
 
+constexpr uint32_t TWO_LIT = 1u << 31;
+
 struct BitReader {
     const uint8_t *in;
     int64_t pos, end;      // next byte to load / one past the member's deflate data
+    int64_t lim;           // readable bytes at `in` (whole compressed buffer)
     uint64_t buf;
     int nbits;
+    // at least 32 valid bits afterwards: one unaligned 32-bit fetch (two aligned words + funnel shift).
+    // Bytes past `end` are whatever follows in the buffer (trailer, next header); overrun() catches a
+    // stream that really consumes them.
+    __device__ __forceinline__ void refill32() {
+        if (nbits < 32) {
+            if (pos + 8 <= lim) {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(in + (pos & ~(int64_t)3));
+                const uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (int)(pos & 3) * 8);
+                buf |= (uint64_t)v << nbits;
+                nbits += 32;
+                pos += 4;
+            } else refill();
+        }
+    }
     __device__ __forceinline__ void refill() {
         while (nbits <= 56) {
             const uint64_t b = pos < end ? in[pos] : 0;
@@ -67,7 +87,8 @@ __device__ int slow_decode(BitReader &br, const uint16_t *cnt, const uint16_t *s
 
 // Build primary + canonical tables for `n` symbols with code lengths lens[0..n) (all lanes).
 // Returns false on an over-subscribed code.
-__device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_bits, int sym_shift, uint16_t *cnt,
+template <typename E>
+__device__ bool build_table(const uint8_t *lens, int n, E *tab, int tab_bits, int sym_shift, uint16_t *cnt,
                             uint16_t *sym, int lane) {
     // counts / offsets by lane 0 (n <= 288)
     int ok = 1;
@@ -111,7 +132,7 @@ __device__ bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_b
             const int s = sym[base + k];
             const uint32_t code = (uint32_t)(next[len] + k);
             const uint32_t r = bitrev(code, len);
-            const uint16_t e = (uint16_t)((len << sym_shift) | s);
+            const E e = (E)((len << sym_shift) | s);
             for (uint32_t j = r; j < (1u << tab_bits); j += (1u << len)) tab[j] = e;
         }
         base += c;
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restr
             if (p > c1 - 8) err = INF_BAD_HEADER;
         }
         BitReader br;
-        br.in = in; br.pos = p; br.end = c1 - 8; br.buf = 0; br.nbits = 0;
+        br.in = in; br.pos = p; br.end = c1 - 8; br.lim = in_size; br.buf = 0; br.nbits = 0;
         int64_t opos = o0;
         bool last = false;
         while (!err && !last) {
@@ -241,6 +262,19 @@ __global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restr
             ok = build_table(T.lens + hlit, hdist, T.dist, DIST_BITS, 5, T.distcnt, T.distsym, lane) && ok;
             // an incomplete distance code with a single symbol is legal; over-subscription is not
             if (!ok) { err = INF_BAD_CODE; break; }
+            // second literal: where the bits left over after a literal decode another literal completely, one
+            // table lookup yields both (DNA text: ~2-bit codes, so most lookups)
+            for (int i = lane; i < (1 << LIT_BITS); i += 32) {
+                const uint32_t e1 = T.lit[i] & 0xffffu;
+                const uint32_t l1 = e1 >> 9;
+                if (e1 && (e1 & 511u) < 256u) {
+                    const uint32_t e2 = T.lit[i >> l1] & 0xffffu;       // low halves never change in this pass
+                    const uint32_t l2 = e2 >> 9;
+                    if (e2 && (e2 & 511u) < 256u && l1 + l2 <= (uint32_t)LIT_BITS)
+                        T.lit[i] = e1 | TWO_LIT | ((l1 + l2) << 24) | ((e2 & 255u) << 16);
+                }
+            }
+            __syncwarp();
             // ---- symbol loop: lane 0 decodes literals until a match / end of block, matches are copied by
             //      the whole warp ---------------------------------------------------------------------------------
             bool eob = false;
@@ -248,9 +282,39 @@ __global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restr
                 int mlen = 0, mdist = 0;
                 if (lane == 0) {
                     while (true) {
-                        br.refill();
+                        // fast path: one or two literals per table lookup
+                        {
+                            uint64_t buf = br.buf;
+                            int nbits = br.nbits;
+                            int64_t pos = br.pos;
+                            const int64_t olim = (o1 < out_cap ? o1 : out_cap) - 2;
+                            while (opos <= olim) {
+                                if (nbits < 32) {
+                                    if (pos + 8 > br.lim) break;
+                                    const uint32_t *w = reinterpret_cast<const uint32_t *>(in + (pos & ~(int64_t)3));
+                                    const uint32_t v = __funnelshift_r(__ldg(w), __ldg(w + 1), (int)(pos & 3) * 8);
+                                    buf |= (uint64_t)v << nbits;
+                                    nbits += 32;
+                                    pos += 4;
+                                }
+                                const uint32_t e = T.lit[(uint32_t)buf & ((1u << LIT_BITS) - 1u)];
+                                if (e & TWO_LIT) {
+                                    out[opos] = (uint8_t)e;
+                                    out[opos + 1] = (uint8_t)(e >> 16);
+                                    opos += 2;
+                                    const int l = (int)((e >> 24) & 15u);
+                                    buf >>= l; nbits -= l;
+                                } else if ((e & 0xffffu) != 0u && (e & 511u) < 256u) {
+                                    out[opos++] = (uint8_t)e;
+                                    const int l = (int)((e >> 9) & 15u);
+                                    buf >>= l; nbits -= l;
+                                } else break;
+                            }
+                            br.buf = buf; br.nbits = nbits; br.pos = pos;
+                        }
+                        br.refill32();
                         int sym;
-                        const uint16_t e = T.lit[br.peek(LIT_BITS)];
+                        const uint32_t e = T.lit[br.peek(LIT_BITS)] & 0xffffu;
                         if (e) { br.drop(e >> 9); sym = e & 511; }
                         else sym = slow_decode(br, T.litcnt, T.litsym);
                         if (sym < 0) { err = INF_BAD_CODE; break; }
@@ -262,20 +326,52 @@ __global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restr
                         if (sym == 256) { eob = true; break; }
                         sym -= 257;
                         if (sym >= 29) { err = INF_BAD_CODE; break; }
-                        br.refill();
+                        br.refill32();
                         mlen = LEN_BASE[sym] + (int)br.peek(LEN_EXTRA[sym]);
                         br.drop(LEN_EXTRA[sym]);
-                        br.refill();
+                        br.refill32();
                         int ds;
                         const uint16_t de = T.dist[br.peek(DIST_BITS)];
                         if (de) { br.drop(de >> 5); ds = de & 31; }
                         else ds = slow_decode(br, T.distcnt, T.distsym);
                         if (ds < 0 || ds >= 30) { err = INF_BAD_CODE; break; }
-                        br.refill();
+                        br.refill32();
                         mdist = DIST_BASE[ds] + (int)br.peek(DIST_EXTRA[ds]);
                         br.drop(DIST_EXTRA[ds]);
                         if (mdist > opos - o0) { err = INF_BAD_CODE; break; }        // BGZF members are self-contained
                         if (opos + mlen > o1 || opos + mlen > out_cap) { err = INF_OVERRUN; break; }
+                        if (mlen <= SHORT_MATCH) {                                       // short match: copied right here
+                            const int64_t src = opos - mdist;
+                            if (mdist >= mlen && (src & ~(int64_t)7) + 32 <= out_cap) {
+                                // no overlap: fetch the whole source with four aligned 8-byte loads issued together
+                                // (ONE L2 round trip per match instead of one per byte), then store from registers
+                                const uint64_t *w = reinterpret_cast<const uint64_t *>(out + (src & ~(int64_t)7));
+                                const uint64_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
+                                const int sh = (int)(src & 7) * 8;
+                                uint64_t v0 = a0, v1 = a1, v2 = a2;
+                                if (sh) {
+                                    v0 = (a0 >> sh) | (a1 << (64 - sh));
+                                    v1 = (a1 >> sh) | (a2 << (64 - sh));
+                                    v2 = (a2 >> sh) | (a3 << (64 - sh));
+                                }
+                                uint8_t *o = out + opos;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) if (i < mlen) o[i] = (uint8_t)(v0 >> (8 * i));
+                                if (mlen > 8) {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) if (8 + i < mlen) o[8 + i] = (uint8_t)(v1 >> (8 * i));
+                                    if (mlen > 16) {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) if (16 + i < mlen) o[16 + i] = (uint8_t)(v2 >> (8 * i));
+                                    }
+                                }
+                            } else {
+                                for (int i = 0; i < mlen; ++i) out[opos + i] = out[src + i];   // in order: overlap repeats
+                            }
+                            opos += mlen;
+                            mlen = 0;
+                            continue;
+                        }
                         break;
                     }
                     if (br.overrun()) err = INF_OVERRUN;
