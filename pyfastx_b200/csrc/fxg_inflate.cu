@@ -14,6 +14,8 @@
 // Plain (non-BGZF) gzip streams are not handled here (no independent entry points without a
 // previous serial pass); the host layer inflates those while staging.
 #include "fxg_common.cuh"
+#include "fxg_inflate_core.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace fxg {
@@ -150,7 +152,7 @@ __constant__ uint8_t CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12
 // status codes per member: 0 ok, >0 error class
 enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_OVERRUN = 4, INF_SIZE = 5 };
 
-__global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restrict__ in, int64_t in_size,
+__global__ void __launch_bounds__(IW * 32) inflate_warp_kernel(const uint8_t *__restrict__ in, int64_t in_size,
                                                          const int64_t *__restrict__ cmp_off,
                                                          const int64_t *__restrict__ ucmp_off, int64_t n_members,
                                                          uint8_t *__restrict__ out, int64_t out_cap,
@@ -398,6 +400,55 @@ __global__ void __launch_bounds__(IW * 32) inflate_kernel(const uint8_t *__restr
     }
 }
 
+// ---- a thread per member -----------------------------------------------------------------------------
+// The Huffman decode of one member is serial, so the warp-per-member kernel above issues every instruction
+// for ONE useful lane.  Here 32 members share a warp: each lane runs fxi::inflate_member on its own member
+// with its own 2.2 KB of decode tables; up to 1,024 members are in flight per SM.
+__device__ const uint16_t D_LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__device__ const uint8_t D_LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__device__ const uint16_t D_DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__device__ const uint8_t D_DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__device__ const uint8_t D_CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+constexpr int MT_THREADS = 64;                                      // members per CTA
+constexpr int MT_WARPS_PER_SM = 32;                                 // resident warps the launch aims for (64 registers)
+constexpr int SYM_BATCH = 32;                                      // symbols per lane between member / block checks
+
+__global__ void __launch_bounds__(MT_THREADS) inflate_thread_kernel(const uint8_t *__restrict__ in, int64_t in_size,
+                                                                   const int64_t *__restrict__ cmp_off,
+                                                                   const int64_t *__restrict__ ucmp_off, int64_t n_members,
+                                                                   uint8_t *out, int64_t out_cap, int32_t *__restrict__ status,
+                                                                   fxi::MemberTables *tables) {
+    // decode tables live in global memory (2.2 KB per lane, L1/L2 resident where hot): shared memory would
+    // cap the SM at ~96 members in flight, far too few to hide the latency of the serial decode chains
+    fxi::MemberTables &T = tables[(size_t)blockIdx.x * MT_THREADS + threadIdx.x];
+    const fxi::DeflateConsts K = {D_LEN_BASE, D_LEN_EXTRA, D_DIST_BASE, D_DIST_EXTRA, D_CL_ORDER};
+    const int64_t step = (int64_t)gridDim.x * MT_THREADS;
+    int64_t m = (int64_t)blockIdx.x * MT_THREADS + threadIdx.x;
+    fxi::Decoder d;
+    d.state = fxi::Decoder::DONE; d.status = 0;
+    bool have = false, finished = false;
+    // All lanes advance in lock step -- one symbol per lane and step, reconverging after every step -- so
+    // the warp never splits into fragments that the scheduler would run one after the other.
+    for (;;) {
+        if (d.state == fxi::Decoder::DONE) {                       // next member for this lane
+            if (have) { status[m] = d.status; m += step; have = false; }
+            if (!finished) {
+                if (m < n_members) { d.begin(in, in_size, cmp_off[m], cmp_off[m + 1], out_cap, ucmp_off[m], ucmp_off[m + 1]); have = true; }
+                else finished = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, finished)) break;
+        if (d.state == fxi::Decoder::NEED_BLOCK) d.begin_block(out, T, K);
+        __syncwarp();
+#pragma unroll 1
+        for (int k = 0; k < SYM_BATCH; ++k) {
+            if (d.state == fxi::Decoder::SYMBOLS) d.step_symbol(out, out_cap, T, K);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace fxg
 
 using namespace fxg;
@@ -453,12 +504,23 @@ extern "C" int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed,
     if (n_members == 0) return FXG_OK;
     FXG_CHECK_ARG(d_cmp_off && d_ucmp_off && d_out && d_status, "null device pointer");
     FXG_CUDA(cudaSetDevice(ctx->device));
-    int64_t blocks = (n_members + IW - 1) / IW;
-    const int64_t maxb = (int64_t)ctx->sm_count * 6;
-    if (blocks > maxb) blocks = maxb;
     FxgProfScope prof(ctx, FXG_PROF_GATHER);
-    inflate_kernel<<<(unsigned)blocks, IW * 32, 0, ctx->stream>>>(compressed->d, compressed->size, d_cmp_off, d_ucmp_off,
-                                                                  n_members, d_out, out_cap, d_status);
+    if (getenv("FXG_INFLATE_WARP_PER_MEMBER")) {                 // A/B and debugging
+        int64_t blocks = (n_members + IW - 1) / IW;
+        const int64_t maxb = (int64_t)ctx->sm_count * 6;
+        if (blocks > maxb) blocks = maxb;
+        inflate_warp_kernel<<<(unsigned)blocks, IW * 32, 0, ctx->stream>>>(compressed->d, compressed->size, d_cmp_off, d_ucmp_off,
+                                                                           n_members, d_out, out_cap, d_status);
+    } else {
+        int64_t blocks = (n_members + MT_THREADS - 1) / MT_THREADS;
+        const int64_t maxb = (int64_t)ctx->sm_count * (MT_WARPS_PER_SM * 32 / MT_THREADS);
+        if (blocks > maxb) blocks = maxb;
+        int rc = ctx->misc.reserve((size_t)blocks * MT_THREADS * sizeof(fxi::MemberTables));
+        if (rc) return rc;
+        inflate_thread_kernel<<<(unsigned)blocks, MT_THREADS, 0, ctx->stream>>>(compressed->d, compressed->size, d_cmp_off, d_ucmp_off,
+                                                                                n_members, d_out, out_cap, d_status,
+                                                                                (fxi::MemberTables *)ctx->misc.ptr);
+    }
     FXG_CUDA(cudaGetLastError());
     return FXG_OK;
 }
