@@ -217,7 +217,7 @@ int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows,
  * Replaces zlib's gzread during the scan (src/kseq.c:70), the second full inflate pass that builds
  * the zran checkpoints (zran_build_index, src/index.c:381-387) and zran_seek + zran_read per random
  * access (src/index.c:685-686, src/read.c:39-40): the whole file is inflated once into HBM (one
- * warp per <= 64 KiB member) and every later access works on the uncompressed bytes.
+ * thread per <= 64 KiB member) and every later access works on the uncompressed bytes.
  * fxg_bgzf_members_host walks the member headers only ('BC' extra field, ISIZE trailer); cmp_off
  * and ucmp_off receive n_members + 1 entries (pass NULL / cap 0 to just count).  FXG_EFORMAT if the
  * stream is plain gzip rather than BGZF (the caller then inflates on the host while staging).

@@ -59,7 +59,7 @@ def reverse_complement(seq):
 
 class _Staged:
     """file bytes resident in HBM.  Plain files are staged with pinned-chunk copies; BGZF files are
-    inflated on the GPU (one warp per member); other gzip streams are inflated by zlib on the host
+    inflated on the GPU (one thread per member); other gzip streams are inflated by zlib on the host
     while staging (a single deflate stream has no independent entry points)."""
 
     def __init__(self, path):
