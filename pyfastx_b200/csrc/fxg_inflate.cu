@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(IW * 32) inflate_warp_kernel(const uint8_t *__
 // ---- a thread per member -----------------------------------------------------------------------------
 // The Huffman decode of one member is serial, so the warp-per-member kernel above issues every instruction
 // for ONE useful lane.  Here 32 members share a warp: each lane runs fxi::inflate_member on its own member
-// with its own 2.2 KB of decode tables; up to 1,024 members are in flight per SM.
+// with its own 2.2 KB of decode tables; up to 1,152 members are in flight per SM.
 __device__ const uint16_t D_LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 __device__ const uint8_t D_LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
 __device__ const uint16_t D_DIST_BASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -411,10 +411,11 @@ __device__ const uint8_t D_DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4,
 __device__ const uint8_t D_CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 constexpr int MT_THREADS = 64;                                      // members per CTA
-constexpr int MT_WARPS_PER_SM = 32;                                 // resident warps the launch aims for (64 registers)
+constexpr int MT_WARPS_PER_SM = 36;                                 // resident warps the launch aims for (56 registers):
+                                                                    // 148 SMs x 36 x 32 lanes cover the 155,577 members of C5 in ONE round
 constexpr int SYM_BATCH = 32;                                      // symbols per lane between member / block checks
 
-__global__ void __launch_bounds__(MT_THREADS) inflate_thread_kernel(const uint8_t *__restrict__ in, int64_t in_size,
+__global__ void __launch_bounds__(MT_THREADS, MT_WARPS_PER_SM * 32 / MT_THREADS) inflate_thread_kernel(const uint8_t *__restrict__ in, int64_t in_size,
                                                                    const int64_t *__restrict__ cmp_off,
                                                                    const int64_t *__restrict__ ucmp_off, int64_t n_members,
                                                                    uint8_t *out, int64_t out_cap, int32_t *__restrict__ status,
