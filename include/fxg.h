@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FXG_ABI_VERSION 1
+#define FXG_ABI_VERSION 2
 
 enum {
     FXG_OK       = 0,
@@ -78,6 +78,24 @@ typedef struct fxg_scan_stats {
     int64_t reserved;
 } fxg_scan_stats;
 
+/* What one shard tells the others in the multi-GPU index build: the fixed struct of the
+ * one small all-gather.  128 bytes.  Filled on the device by fxg_scan_begin.
+ *   n_rows / n_lines     FASTA header lines / lines (incl. an unterminated last line) of this shard
+ *   edge_*               the first (up to 3) lines of the shard: global offset of the line start and line length
+ *                        without '\r' -- what the PREVIOUS shard needs to complete a FASTQ read whose four lines
+ *                        straddle the boundary (soff/rlen from line 2, qoff from line 4: fastq.c:122-133) */
+typedef struct fxg_shard_info {
+    int64_t n_rows;
+    int64_t n_lines;
+    int64_t bytes;         /* shard size                                            */
+    int64_t base_offset;   /* file offset of the shard's first byte                 */
+    int64_t end_position;  /* bytes, +1 when the last line has no '\n'              */
+    int64_t edge_n;        /* valid entries in edge_off / edge_len (<= 3)           */
+    int64_t edge_off[3];
+    int64_t edge_len[3];
+    int64_t reserved[4];
+} fxg_shard_info;
+
 /* scan flags */
 enum {
     FXG_SCAN_FULL_NAME = 1   /* Fasta(full_name=True): name = whole header (index.c:282-285) */
@@ -94,8 +112,13 @@ enum {
                              * (pad[0] bit 0, set by the scan) still take the formula, which is then exact */
 };
 
-typedef struct fxg_ctx  fxg_ctx;    /* one per (process, GPU)                    */
+typedef struct fxg_ctx  fxg_ctx;    /* one per (process, GPU).  NOT thread-safe: a context owns grow-only scratch
+                                     * buffers and one stream; every entry point taking a ctx locks the context's
+                                     * own mutex, so concurrent callers are serialised (never corrupted), and
+                                     * device pointers returned from context scratch (scan rows) stay valid only
+                                     * until the next scan on the same context.                                   */
 typedef struct fxg_file fxg_file;   /* a FASTA/FASTQ byte stream resident in HBM */
+typedef struct fxg_comm fxg_comm;   /* NCCL communicator of the ranks that share one index build */
 
 /* ---- library / context ----------------------------------------------------------------- */
 int         fxg_abi_version(void);
@@ -148,16 +171,52 @@ int fxg_fasta_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int fla
                    fxg_fasta_row **d_rows_out, fxg_scan_stats *stats);
 
 /* ---- K2: FASTQ index scan -----------------------------------------------------------------
- * Replaces the scan loop of pyfastx_fastq_create_index (src/fastq.c:84-171).
- *   first_line  : global 0-based line number of the first line of `f` (0 for a whole
- *                 file; the shard's line-count prefix in a multi-GPU build, section 8e)
- * Rows are indexed by global read id minus first_line/4; a read whose four lines straddle
- * two shards gets its fields from both (fields not owned are left zero). */
-int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int64_t first_line,
+ * Replaces the scan loop of pyfastx_fastq_create_index (src/fastq.c:84-171): strict 4-line records by
+ * line number (fastq.c:93); n_rows = complete reads (fastq.c:132-146,159). */
+int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset,
                    fxg_fastq_row **d_rows_out, fxg_scan_stats *stats);
 
-/* newline count of a resident buffer (FASTQ multi-GPU phase pass, section 8e) */
-int fxg_count_lines(fxg_ctx *ctx, const fxg_file *f, int64_t *n_newlines, int *ends_with_newline);
+/* ---- multi-GPU index build: split-phase scan + ONE small all-gather ----
+ * Every rank holds a contiguous byte range of the file that starts at a line start (FASTQ) or at a header
+ * line (FASTA); see fxg_split_point_* below.  The scan is split where the only cross-shard dependency sits:
+ *   fxg_scan_begin     mark + prefix over the shard (all of the file traffic); leaves the shard's
+ *                      fxg_shard_info on the device.  No host synchronisation.
+ *   fxg_shard_exchange ncclAllGather of the fxg_shard_info structs on the context's stream (NVLink/NVSwitch;
+ *                      latency bound, 128 B per rank).  comm == NULL: single rank, a device copy.
+ *   fxg_scan_finish    global line phase (fastq.c:93: line_num % 4 counts from the start of the FILE) and ID
+ *                      base from the gathered counts, rows kernel, and for FASTQ the boundary-row merge: a
+ *                      read is owned by the shard holding its name line and completed from the next shards'
+ *                      edge lines.  ONE host synchronisation at the end.  d_rows_out = this shard's rows
+ *                      (FASTQ: owned complete reads only), stats = this shard's totals, all_host (may be NULL)
+ *                      receives the nranks gathered structs.
+ * fxg_fasta_scan / fxg_fastq_scan are begin + finish with one rank.  mode: 0 = FASTA, 1 = FASTQ. */
+int fxg_scan_begin(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offset, int flags,
+                   fxg_shard_info *d_info_out /* device, 128 B */);
+int fxg_shard_exchange(fxg_ctx *ctx, fxg_comm *comm, const void *d_send, void *d_recv, int64_t bytes_per_rank);
+int fxg_scan_finish(fxg_ctx *ctx, const fxg_shard_info *d_all /* device, nranks entries */, int nranks, int rank,
+                    void **d_rows_out, fxg_scan_stats *stats, fxg_shard_info *all_host);
+/* the three steps in one call (what a rank of the multi-GPU build runs) */
+int fxg_scan_sharded(fxg_ctx *ctx, fxg_comm *comm, const fxg_file *f, int mode, int64_t base_offset, int flags,
+                     void **d_rows_out, fxg_scan_stats *stats, fxg_shard_info *all_host);
+
+/* communicator: rank 0 creates the id (ncclGetUniqueId), the host layer broadcasts its FXG_COMM_ID_BYTES
+ * bytes by any means (torch.distributed, MPI, a file), every rank calls fxg_comm_create (ncclCommInitRank).
+ * NCCL is loaded at run time (libnccl.so.2, the copy already in the process if there is one). */
+#define FXG_COMM_ID_BYTES 128
+int  fxg_comm_unique_id(void *id_out);
+int  fxg_comm_create(fxg_ctx *ctx, const void *id, int nranks, int rank, fxg_comm **out);
+int  fxg_comm_nranks(const fxg_comm *comm);
+int  fxg_comm_rank(const fxg_comm *comm);
+void fxg_comm_destroy(fxg_comm *comm);
+
+/* split points found ON THE DATA: first offset >= from at which a line starts (want_header = 0) or a FASTA
+ * header line starts (want_header = 1: '>' at offset 0 or right after '\n', index.c:234); the buffer / file
+ * size if there is none.  _dev searches a resident buffer (synchronises), _path reads the file with pread. */
+int fxg_split_point_dev(fxg_ctx *ctx, const fxg_file *f, int64_t from, int want_header, int64_t *pos);
+int fxg_split_point_path(const char *path, int64_t from, int want_header, int64_t *pos, int64_t *file_size);
+/* stage the byte range [begin, end) of a file / of a resident buffer as a shard of its own */
+int fxg_file_from_path_range(fxg_ctx *ctx, const char *path, int64_t begin, int64_t end, fxg_file **out);
+int fxg_file_slice(fxg_ctx *ctx, const fxg_file *src, int64_t begin, int64_t end, fxg_file **out);
 
 /* copy rows device -> host (row_bytes = 48 or 32) */
 int fxg_rows_download(fxg_ctx *ctx, const void *d_rows, int64_t n_rows, int row_bytes, void *host_rows);
@@ -229,6 +288,45 @@ int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed, const int6
                             int32_t *d_status);
 int fxg_file_from_bgzf_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, fxg_file **out,
                             int64_t *n_members_out);
+
+/* ---- `.fxi` bulk writer (host side, no GPU needed) ------------------------------
+ * Replaces the per-row INSERT loops and the CREATE UNIQUE INDEX of the reference index build
+ * (src/index.c:223-251,363-372; src/fastq.c:81-156): rows (from the scan) and names (one packed buffer,
+ * name i = names[name_off[i], name_off[i+1])) are written straight into a SQLite-format file with the
+ * reference's schema (src/index.c:178-207, src/fastq.c:29-60) -- table b-trees and the UNIQUE name index
+ * are built bottom-up, in parallel, without going through an SQL engine.  Duplicate names: no UNIQUE index
+ * is created (the reference ignores that error too, src/index.c:366).  An existing file is replaced.
+ *   gz     gzindex rows for a gzip input, in the row-per-field layout of pyfastx_gzip_index_export
+ *          (src/util.c:442-540); NULL for plain files
+ *   comp   full-index composition rows (src/fasta.c:851-961), NULL / 0 if not computed
+ *   meta   FASTQ base / meta rows (src/fastq.c:663-795), NULL if not computed */
+typedef struct fxg_gzindex {
+    int64_t  compressed_size, uncompressed_size;
+    uint32_t spacing, window_size;       /* import requires window_size >= 32768, spacing >= window_size */
+    int64_t  npoints;
+    const int64_t *cmp_offset;           /* per point: offset of the deflate data in the compressed file  */
+    const int64_t *uncmp_offset;         /* per point: offset in the uncompressed stream                  */
+} fxg_gzindex;
+typedef struct fxg_comp_row { int64_t seqid, abc, num; } fxg_comp_row;      /* seqid 0 = whole file        */
+typedef struct fxg_fastq_meta { int64_t a, c, g, t, n, maxlen, minlen, minqs, maxqs, phred; } fxg_fastq_meta;
+int fxg_fxi_write_fasta(const char *path, const fxg_fasta_row *rows, int64_t n_rows, const uint8_t *names,
+                        const int64_t *name_off, int64_t total_slen, const fxg_gzindex *gz,
+                        const fxg_comp_row *comp, int64_t n_comp);
+int fxg_fxi_write_fastq(const char *path, const fxg_fastq_row *rows, int64_t n_rows, const uint8_t *names,
+                        const int64_t *name_off, int64_t n_lines, int64_t total_size, const fxg_gzindex *gz,
+                        const fxg_fastq_meta *meta);
+
+/* ---- batched name -> row resolution (host side) --------------------------------
+ * Replaces one sqlite probe per query (pyfastx_index_get_seq_by_name, src/index.c:527-566;
+ * pyfastx_fastq_get_read_by_name, src/fastq.c:487-519) by a hash table over the packed names
+ * (name i = names[name_off[i], name_off[i+1]); the table BORROWS both arrays: keep them alive).
+ * Lookup of a batch runs on several threads; ids_out[i] = 0-based row, -1 if the name does not exist.
+ * Duplicate names resolve to the first row. */
+typedef struct fxg_nametab fxg_nametab;
+int     fxg_nametab_build(const uint8_t *names, const int64_t *name_off, int64_t n, fxg_nametab **out);
+int64_t fxg_nametab_find(const fxg_nametab *t, const uint8_t *name, int64_t len);
+int     fxg_nametab_lookup(const fxg_nametab *t, const uint8_t *q, const int64_t *q_off, int64_t nq, int64_t *ids_out);
+void    fxg_nametab_free(fxg_nametab *t);
 
 /* ---- synthetic inputs generated directly in HBM (bench / test tooling) -------------------
  * Byte-identical to pyfastx_b200/synth.py.  rec_off has n_records+1 entries (device). */

@@ -30,6 +30,32 @@ class ScanStats(C.Structure):
                 ("lead_llen", C.c_int64), ("reserved", C.c_int64)]
 
 
+class ShardInfo(C.Structure):
+    """fxg_shard_info: what one shard tells the others (the struct of the one small all-gather)"""
+    _fields_ = [("n_rows", C.c_int64), ("n_lines", C.c_int64), ("bytes", C.c_int64), ("base_offset", C.c_int64),
+                ("end_position", C.c_int64), ("edge_n", C.c_int64), ("edge_off", C.c_int64 * 3),
+                ("edge_len", C.c_int64 * 3), ("reserved", C.c_int64 * 4)]
+
+
+SHARD_INFO = np.dtype([("n_rows", "<i8"), ("n_lines", "<i8"), ("bytes", "<i8"), ("base_offset", "<i8"),
+                       ("end_position", "<i8"), ("edge_n", "<i8"), ("edge_off", "<i8", (3,)), ("edge_len", "<i8", (3,)),
+                       ("reserved", "<i8", (4,))])
+COMM_ID_BYTES = 128
+
+
+class GzIndex(C.Structure):
+    _fields_ = [("compressed_size", C.c_int64), ("uncompressed_size", C.c_int64), ("spacing", C.c_uint32),
+                ("window_size", C.c_uint32), ("npoints", C.c_int64), ("cmp_offset", C.c_void_p),
+                ("uncmp_offset", C.c_void_p)]
+
+
+class FastqMeta(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("a", "c", "g", "t", "n", "maxlen", "minlen", "minqs", "maxqs", "phred")]
+
+
+COMP_ROW = np.dtype([("seqid", "<i8"), ("abc", "<i8"), ("num", "<i8")])
+
+
 class FxgError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libfxg error %d: %s" % (code, msg))
@@ -68,8 +94,20 @@ SIGNATURES = {
     "fxg_file_size": (i64, [vp]),
     "fxg_file_free": (None, [vp]),
     "fxg_fasta_scan": (i32, [vp, vp, i64, i32, P(vp), P(ScanStats)]),
-    "fxg_fastq_scan": (i32, [vp, vp, i64, i64, P(vp), P(ScanStats)]),
-    "fxg_count_lines": (i32, [vp, vp, P(i64), P(i32)]),
+    "fxg_fastq_scan": (i32, [vp, vp, i64, P(vp), P(ScanStats)]),
+    "fxg_scan_begin": (i32, [vp, vp, i32, i64, i32, vp]),
+    "fxg_shard_exchange": (i32, [vp, vp, vp, vp, i64]),
+    "fxg_scan_finish": (i32, [vp, vp, i32, i32, P(vp), P(ScanStats), vp]),
+    "fxg_scan_sharded": (i32, [vp, vp, vp, i32, i64, i32, P(vp), P(ScanStats), vp]),
+    "fxg_comm_unique_id": (i32, [vp]),
+    "fxg_comm_create": (i32, [vp, vp, i32, i32, P(vp)]),
+    "fxg_comm_nranks": (i32, [vp]),
+    "fxg_comm_rank": (i32, [vp]),
+    "fxg_comm_destroy": (None, [vp]),
+    "fxg_split_point_dev": (i32, [vp, vp, i64, i32, P(i64)]),
+    "fxg_split_point_path": (i32, [C.c_char_p, i64, i32, P(i64), P(i64)]),
+    "fxg_file_from_path_range": (i32, [vp, C.c_char_p, i64, i64, P(vp)]),
+    "fxg_file_slice": (i32, [vp, vp, i64, i64, P(vp)]),
     "fxg_rows_download": (i32, [vp, vp, i64, i32, vp]),
     "fxg_rows_upload": (i32, [vp, vp, i64, i32, P(vp)]),
     "fxg_dev_free": (None, [vp]),
@@ -84,6 +122,12 @@ SIGNATURES = {
     "fxg_bgzf_members_host": (i32, [vp, i64, vp, vp, i64, P(i64), P(i64)]),
     "fxg_inflate_members_dev": (i32, [vp, vp, vp, vp, i64, vp, i64, vp]),
     "fxg_file_from_bgzf_host": (i32, [vp, vp, i64, P(vp), P(i64)]),
+    "fxg_fxi_write_fasta": (i32, [C.c_char_p, vp, i64, vp, vp, i64, vp, vp, i64]),
+    "fxg_fxi_write_fastq": (i32, [C.c_char_p, vp, i64, vp, vp, i64, i64, vp, vp]),
+    "fxg_nametab_build": (i32, [vp, vp, i64, P(vp)]),
+    "fxg_nametab_find": (i64, [vp, C.c_char_p, i64]),
+    "fxg_nametab_lookup": (i32, [vp, vp, vp, i64, vp]),
+    "fxg_nametab_free": (None, [vp]),
     "fxg_synth_fasta_dev": (i32, [vp, u64, vp, vp, i64, i64, i32, vp]),
     "fxg_synth_fastq_dev": (i32, [vp, u64, i64, i64, i32, vp, vp]),
 }

@@ -57,6 +57,22 @@ def reverse_complement(seq):
     return out.tobytes().decode("latin-1")
 
 
+def _gzip_header_len(comp):
+    """bytes of the gzip member header (RFC 1952) in front of the deflate data"""
+    flg = int(comp[3])
+    p = 10
+    if flg & 4:
+        p += 2 + (int(comp[p]) | (int(comp[p + 1]) << 8))
+    for bit in (8, 16):
+        if flg & bit:
+            while comp[p] != 0:
+                p += 1
+            p += 1
+    if flg & 2:
+        p += 2
+    return p
+
+
 class _Staged:
     """file bytes resident in HBM.  Plain files are staged with pinned-chunk copies; BGZF files are
     inflated on the GPU (one thread per member); other gzip streams are inflated by zlib on the host
@@ -66,16 +82,23 @@ class _Staged:
         self.engine = get_engine()
         self.is_gzip = gzip_check(path)
         self.bgzf_members = 0
+        self.gzindex = None          # zran-format checkpoints for the .fxi (reference src/util.c:442-540)
         if self.is_gzip:
             with open(path, "rb") as fh:
-                comp = fh.read()
+                comp = np.frombuffer(fh.read(), dtype=np.uint8)
             try:
-                self.dfile = self.engine.stage_bgzf(np.frombuffer(comp, dtype=np.uint8))
+                cmp_off, ucmp_off = self.engine.bgzf_members(comp)
+                self.dfile = self.engine.stage_bgzf(comp)
                 self.bgzf_members = self.dfile.n_members
+                self.gzindex = fxi.bgzf_gzindex(comp, cmp_off, ucmp_off)
             except _cabi.FxgError as ex:
                 if ex.code != _cabi.FXG_EFORMAT:
                     raise
-                self.dfile = self.engine.stage_bytes(np.frombuffer(_gzip.decompress(comp), dtype=np.uint8))
+                self.dfile = self.engine.stage_bytes(np.frombuffer(_gzip.decompress(comp.tobytes()), dtype=np.uint8))
+                # a single deflate stream: one checkpoint at its start (no window needed there)
+                hdr = _gzip_header_len(comp)
+                self.gzindex = {"compressed_size": int(comp.size), "uncompressed_size": int(self.dfile.size),
+                                "cmp_offset": np.array([hdr], dtype=np.int64), "uncmp_offset": np.zeros(1, dtype=np.int64)}
         else:
             self.dfile = self.engine.stage_path(path)
 
@@ -86,11 +109,15 @@ class _Staged:
                 return c
         return None
 
+    def ranges_packed(self, offsets, lengths):
+        """(packed uint8, offsets[n+1]) of the given file ranges (batched GPU gather) -- no Python objects"""
+        if len(offsets) == 0:
+            return np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
+        return self.engine.gather_ranges(self.dfile, offsets, lengths)
+
     def ranges(self, offsets, lengths):
         """list of bytes objects for the given file ranges (batched GPU gather)"""
-        if len(offsets) == 0:
-            return []
-        buf, off = self.engine.gather_ranges(self.dfile, offsets, lengths)
+        buf, off = self.ranges_packed(offsets, lengths)
         raw = buf.tobytes()
         return [raw[off[i]:off[i + 1]] for i in range(len(offsets))]
 
@@ -126,7 +153,6 @@ class Fasta:
         self.index_file = ":memory:" if memory_index else (os.fspath(index_file) if index_file else file_name + ".fxi")
         self._rows = None
         self._names = None
-        self._name2id = None
         self._drows = None
         self._con = None
         self._comp_cache = None
@@ -145,32 +171,40 @@ class Fasta:
             self._total = int(stat[1]) if stat else int(self._rows["slen"].sum())
             self.index_matches_file = self._verify_loaded_index()
         else:
-            eng = self._st.engine
-            rows, st = eng.fasta_scan(self._st.dfile, full_name=self.full_name)
-            name_off = rows["boff"] - rows["elen"].astype(np.int64) - rows["dlen"]
-            if self.key_func is None:
-                names = self._st.ranges(name_off, rows["nlen"].astype(np.int64))
-            else:
-                # key_func receives the header text after '>' exactly as the reference passes it
-                # (NUL-terminated line, i.e. including a trailing '\r'), src/index.c:304-318
-                hdrs = self._st.ranges(name_off, rows["dlen"].astype(np.int64) + rows["elen"].astype(np.int64) - 1)
-                names = [str(self.key_func(h.decode("latin-1"))).encode("utf-8") for h in hdrs]
-            self._rows, self._total = rows, int(st["total_len"])
-            self._con = fxi.write_fasta_index(self.index_file, rows, names, self._total)
-            self._names = [fxi._text(b) for b in names]
-        self._name2id = {}
-        for i, nm in enumerate(self._names):
-            self._name2id.setdefault(nm, i)
+            self._scan_and_write(self.index_file)
         self._drows = self._st.engine.upload_rows(self._rows)
 
+    def _scan_names(self, rows):
+        """names of the scanned records as PackedNames (GPU gather of the header spans)"""
+        name_off = rows["boff"] - rows["elen"].astype(np.int64) - rows["dlen"]
+        if self.key_func is None:
+            blob, off = self._st.ranges_packed(name_off, rows["nlen"].astype(np.int64))
+            return fxi.PackedNames(blob, off)
+        # key_func receives the header text after '>' exactly as the reference passes it
+        # (NUL-terminated line, i.e. including a trailing '\r'), src/index.c:304-318
+        hdrs = self._st.ranges(name_off, rows["dlen"].astype(np.int64) + rows["elen"].astype(np.int64) - 1)
+        return fxi.PackedNames.from_list([str(self.key_func(h.decode("latin-1"))).encode("utf-8") for h in hdrs])
+
+    def _scan_and_write(self, index_file):
+        eng = self._st.engine
+        rows, st = eng.fasta_scan(self._st.dfile, full_name=self.full_name)
+        self._names = self._scan_names(rows)
+        self._rows, self._total = rows, int(st["total_len"])
+        self._con = fxi.write_fasta_index_packed(index_file, rows, self._names.blob, self._names.off, self._total,
+                                                 gz=self._st.gzindex)
+
     def _verify_loaded_index(self):
-        """A loaded .fxi carries no line-uniformity bits; one GPU scan (milliseconds) recovers them
-        and doubles as a staleness check of the index against the file."""
-        rows, _ = self._st.engine.fasta_scan(self._st.dfile, full_name=self.full_name)
+        """A loaded .fxi carries no line-uniformity bits; one GPU scan (milliseconds) recovers them and doubles
+        as a staleness check.  Rows that disagree with the file never reach the kernels: the scan's own rows
+        (and names) replace them in memory, and the stale file is left alone."""
+        rows, st = self._st.engine.fasta_scan(self._st.dfile, full_name=self.full_name)
         same = len(rows) == len(self._rows) and all(
             np.array_equal(rows[f], self._rows[f]) for f in ("boff", "blen", "slen", "llen", "elen", "norm", "dlen"))
         if same:
             self._rows["pad"] = rows["pad"]
+        else:
+            self._names = self._scan_names(rows)
+            self._rows, self._total = rows, int(st["total_len"])
         return same
 
     def _need_index(self):
@@ -189,11 +223,11 @@ class Fasta:
 
     def __contains__(self, name):
         self._need_index()
-        return name in self._name2id
+        return isinstance(name, str) and self._names.find(name) >= 0
 
     def keys(self):
         self._need_index()
-        return list(self._names)
+        return self._names.tolist()
 
     def _row_id(self, key):
         self._need_index()
@@ -205,8 +239,8 @@ class Fasta:
                 raise IndexError("index out of range")
             return i
         if isinstance(key, str):
-            i = self._name2id.get(key)
-            if i is None:
+            i = self._names.find(key)
+            if i < 0:
                 raise KeyError("%s does not exist in fasta file" % key)
             return i
         raise KeyError("the key must be index number or sequence name")
@@ -246,10 +280,15 @@ class Fasta:
         """Batched form of fetch(): 1-based inclusive (start, end) per query, strand '+'/'-'.
         Returns a list of str."""
         self._need_index()
-        try:
-            rid = np.fromiter((self._name2id[n] if isinstance(n, str) else self._row_id(n) for n in names), dtype=np.int64)
-        except KeyError as ex:
-            raise NameError("Sequence %s does not exists" % ex.args[0])
+        names = list(names) if not isinstance(names, (list, fxi.PackedNames)) else names
+        if isinstance(names, fxi.PackedNames) or all(isinstance(n, str) for n in names):
+            rid = self._names.lookup(names)          # native batched name -> row (one call, many threads)
+            bad = np.nonzero(rid < 0)[0]
+            if bad.size:
+                k = int(bad[0])
+                raise NameError("Sequence %s does not exists" % (names.get(k) if isinstance(names, fxi.PackedNames) else names[k]))
+        else:
+            rid = np.fromiter((self._row_id(n) for n in names), dtype=np.int64)
         s = np.asarray(starts, dtype=np.int64)
         e = np.asarray(ends, dtype=np.int64)
         if (s > e).any():
@@ -270,8 +309,8 @@ class Fasta:
         if not isinstance(intervals, (list, tuple)):
             raise ValueError("intervals must be list or tuple")
         self._need_index()
-        i = self._name2id.get(chrom)
-        if i is None:
+        i = self._names.find(chrom) if isinstance(chrom, str) else -1
+        if i < 0:
             raise NameError("Sequence %s does not exists" % chrom)
         if intervals and isinstance(intervals[0], (int, np.integer)):
             if len(intervals) != 2:
@@ -296,8 +335,8 @@ class Fasta:
         if flank_length < 0:
             raise ValueError("Flank length must be non-negative")
         self._need_index()
-        i = self._name2id.get(chrom)
-        if i is None:
+        i = self._names.find(chrom) if isinstance(chrom, str) else -1
+        if i < 0:
             raise NameError("sequence %s does not exists" % chrom)
         slen = int(self._rows["slen"][i])
         ls, le = max(0, start - flank_length - 1), max(0, start - 1)
@@ -400,7 +439,7 @@ class Sequence:
         self._fa, self.id = fasta, row_id + 1
         self._i, self._s, self._e = row_id, s, e
         self._complete = complete
-        self.name = fasta._names[row_id]
+        self.name = fasta._names.get(row_id)
         self.start, self.end = s + 1, e
 
     def __len__(self):
@@ -543,21 +582,28 @@ class Fastq:
         if os.path.exists(self.index_file):
             self._con, self._rows, self._names, stat = fxi.load_fastq_index(self.index_file)
             self._counts, self.size, self.avglen = int(stat[0]), int(stat[1]), stat[2]
+            self._validate_loaded_rows()
         else:
             eng = self._st.engine
             rows, st = eng.fastq_scan(self._st.dfile)
-            names = self._st.ranges(rows["soff"] - rows["dlen"], rows["nlen"].astype(np.int64))
+            blob, off = self._st.ranges_packed(rows["soff"] - rows["dlen"], rows["nlen"].astype(np.int64))
+            self._names = fxi.PackedNames(blob, off)
             self._rows = rows
             self._counts = st["n_lines"] // 4
             self.size = int(st["total_len"])
             self.avglen = self.size * 1.0 / self._counts if self._counts else float("nan")
-            self._con = fxi.write_fastq_index(self.index_file, rows, names, st["n_lines"], self.size)
-            self._names = [fxi._text(b) for b in names]
-        self._name2id = {}
-        for i, nm in enumerate(self._names):
-            self._name2id.setdefault(nm, i)
+            self._con = fxi.write_fastq_index_packed(self.index_file, rows, blob, off, st["n_lines"], self.size,
+                                                     gz=self._st.gzindex)
         self._drows = self._st.engine.upload_rows(self._rows)
         return True
+
+    def _validate_loaded_rows(self):
+        """rows of a loaded .fxi must address bytes inside the staged file before they reach the kernels"""
+        r, n = self._rows, self._st.dfile.size
+        ok = ((r["soff"] >= 0) & (r["qoff"] >= 0) & (r["rlen"] >= 0) & (r["soff"] + r["rlen"] <= n) &
+              (r["qoff"] + r["rlen"] <= n) & (r["dlen"] >= 0) & (r["soff"] - r["dlen"] >= 0)).all()
+        if not ok:
+            raise RuntimeError("the index file %s does not match %s" % (self.index_file, self.file_name))
 
     def __len__(self):
         self.build_index()
@@ -565,11 +611,11 @@ class Fastq:
 
     def __contains__(self, name):
         self.build_index()
-        return name in self._name2id
+        return isinstance(name, str) and self._names.find(name) >= 0
 
     def keys(self):
         self.build_index()
-        return list(self._names)
+        return self._names.tolist()
 
     def _row_id(self, key):
         self.build_index()
@@ -581,8 +627,8 @@ class Fastq:
                 raise IndexError("index out of range")
             return i
         if isinstance(key, str):
-            i = self._name2id.get(key)
-            if i is None:
+            i = self._names.find(key)
+            if i < 0:
                 raise KeyError("%s does not exist in fastq file" % key)
             return i
         raise KeyError("the key must be index number or read name")
@@ -617,7 +663,7 @@ class Read:
     def __init__(self, fq, i):
         self._fq, self._i = fq, i
         self.id = i + 1
-        self.name = fq._names[i]
+        self.name = fq._names.get(i)
 
     def __len__(self):
         return int(self._fq._rows["rlen"][self._i])

@@ -87,13 +87,14 @@ extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
     for (int i = 0; i < 2; ++i) {
         if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
         if (c->pinned_ev[i]) cudaEventDestroy(c->pinned_ev[i]);
     }
     for (int i = 0; i < FXG_PROF_SLOTS; ++i)
         for (int j = 0; j < 2; ++j) if (c->prof_ev[i][j]) cudaEventDestroy(c->prof_ev[i][j]);
-    c->tile_desc.release(); c->seg.release(); c->row_tmp.release(); c->rows.release();
+    c->tile_desc.release(); c->seg.release(); c->cut.release(); c->row_tmp.release(); c->rows.release();
     c->counters.release(); c->plan.release(); c->misc.release(); c->stage_file.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -101,6 +102,7 @@ extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
 
 extern "C" int fxg_ctx_set_stream(fxg_ctx *c, void *cuda_stream) {
     FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_LOCK(c);
     FXG_CUDA(cudaSetDevice(c->device));
     FXG_CUDA(cudaStreamSynchronize(c->stream));
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -111,6 +113,7 @@ extern "C" int fxg_ctx_set_stream(fxg_ctx *c, void *cuda_stream) {
 
 extern "C" int fxg_ctx_sync(fxg_ctx *c) {
     FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_LOCK(c);
     FXG_CUDA(cudaSetDevice(c->device));
     FXG_CUDA(cudaStreamSynchronize(c->stream));
     return FXG_OK;
@@ -120,6 +123,7 @@ extern "C" int fxg_ctx_sm_count(fxg_ctx *c) { return c ? c->sm_count : 0; }
 
 extern "C" int fxg_profile_enable(fxg_ctx *c, int on) {
     FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_LOCK(c);
     FXG_CUDA(cudaSetDevice(c->device));
     if (on && !c->prof_ev[0][0])
         for (int i = 0; i < FXG_PROF_SLOTS; ++i)
@@ -130,6 +134,7 @@ extern "C" int fxg_profile_enable(fxg_ctx *c, int on) {
 }
 extern "C" int fxg_profile_last_ms(fxg_ctx *c, int slot, float *ms) {
     FXG_CHECK_ARG(c && ms && slot >= 0 && slot < FXG_PROF_SLOTS, "bad arguments");
+    FXG_LOCK(c);
     FXG_CHECK_ARG(c->prof_valid[slot], "no measurement recorded for this slot");
     FXG_CUDA(cudaEventSynchronize(c->prof_ev[slot][1]));
     FXG_CUDA(cudaEventElapsedTime(ms, c->prof_ev[slot][0], c->prof_ev[slot][1]));
@@ -150,6 +155,7 @@ extern "C" void fxg_host_free(void *p) {
 // ---- device file buffers ------------------------------------------------------------------
 extern "C" int fxg_file_alloc(fxg_ctx *c, int64_t nbytes, fxg_file **out) {
     FXG_CHECK_ARG(c && out && nbytes >= 0, "bad arguments");
+    FXG_LOCK(c);
     *out = nullptr;
     FXG_CUDA(cudaSetDevice(c->device));
     fxg_file *f = new fxg_file();
@@ -207,6 +213,7 @@ static void parallel_memcpy(void *dst, const void *src, size_t n) {
 
 extern "C" int fxg_file_upload(fxg_ctx *c, fxg_file *f, int64_t dst_off, const void *host, int64_t nbytes) {
     FXG_CHECK_ARG(c && f && (host || nbytes == 0), "bad arguments");
+    FXG_LOCK(c);
     FXG_CHECK_ARG(dst_off >= 0 && nbytes >= 0 && dst_off + nbytes <= f->size, "upload range outside file");
     FXG_CUDA(cudaSetDevice(c->device));
     if (nbytes == 0) return FXG_OK;
@@ -234,6 +241,8 @@ extern "C" int fxg_file_upload(fxg_ctx *c, fxg_file *f, int64_t dst_off, const v
 }
 
 extern "C" int fxg_file_from_host(fxg_ctx *c, const void *host, int64_t nbytes, fxg_file **out) {
+    if (!c) { fxg_set_error("invalid argument: ctx == NULL"); return FXG_EINVAL; }
+    FXG_LOCK(c);
     int rc = fxg_file_alloc(c, nbytes, out);
     if (rc) return rc;
     rc = fxg_file_upload(c, *out, 0, host, nbytes);
@@ -241,14 +250,18 @@ extern "C" int fxg_file_from_host(fxg_ctx *c, const void *host, int64_t nbytes, 
     return rc;
 }
 
-extern "C" int fxg_file_from_path(fxg_ctx *c, const char *path, fxg_file **out) {
-    FXG_CHECK_ARG(c && path && out, "bad arguments");
+// bytes [begin, end) of `path` (end < 0: to the end of the file) -> a device buffer of their own:
+// 8 pread threads fill two 64 MiB pinned buffers in turn while the copy engine drains the other
+static int stage_path_range(fxg_ctx *c, const char *path, int64_t begin, int64_t end, fxg_file **out) {
+    FXG_CHECK_ARG(c && path && out && begin >= 0, "bad arguments");
     *out = nullptr;
     int fd = open(path, O_RDONLY);
     if (fd < 0) { fxg_set_error("cannot open %s", path); return FXG_EIO; }
     struct stat st;
     if (fstat(fd, &st) != 0) { close(fd); fxg_set_error("cannot stat %s", path); return FXG_EIO; }
-    const int64_t n = (int64_t)st.st_size;
+    if (end < 0 || end > (int64_t)st.st_size) end = (int64_t)st.st_size;
+    if (begin > end) begin = end;
+    const int64_t n = end - begin;
     int rc = fxg_file_alloc(c, n, out);
     if (rc) { close(fd); return rc; }
     rc = ensure_pinned(c);
@@ -269,7 +282,7 @@ extern "C" int fxg_file_from_path(fxg_ctx *c, const char *path, fxg_file **out) 
             if (lo >= len) break;
             const int64_t cnt = (lo + per <= len) ? per : len - lo;
             char *dst = (char *)c->pinned[which] + lo;
-            const int64_t fo = o + lo;
+            const int64_t fo = begin + o + lo;
             th.emplace_back([=, &bad] {
                 int64_t done = 0;
                 while (done < cnt) {
@@ -291,8 +304,73 @@ extern "C" int fxg_file_from_path(fxg_ctx *c, const char *path, fxg_file **out) 
     return FXG_OK;
 }
 
+extern "C" int fxg_file_from_path(fxg_ctx *c, const char *path, fxg_file **out) {
+    FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_LOCK(c);
+    return stage_path_range(c, path, 0, -1, out);
+}
+
+extern "C" int fxg_file_from_path_range(fxg_ctx *c, const char *path, int64_t begin, int64_t end, fxg_file **out) {
+    FXG_CHECK_ARG(c, "ctx == NULL");
+    FXG_LOCK(c);
+    return stage_path_range(c, path, begin, end, out);
+}
+
+extern "C" int fxg_file_slice(fxg_ctx *c, const fxg_file *src, int64_t begin, int64_t end, fxg_file **out) {
+    FXG_CHECK_ARG(c && src && out && begin >= 0 && end >= begin && end <= src->size, "bad arguments");
+    FXG_LOCK(c);
+    int rc = fxg_file_alloc(c, end - begin, out);
+    if (rc) return rc;
+    if (end > begin)
+        FXG_CUDA(cudaMemcpyAsync((*out)->d, src->d + begin, (size_t)(end - begin), cudaMemcpyDeviceToDevice, c->stream));
+    return FXG_OK;
+}
+
+// Split point on a host file: first offset >= from where a line (or a FASTA header line,
+// index.c:234) starts; the file size if there is none.  Reads 1 MiB windows with pread.
+extern "C" int fxg_split_point_path(const char *path, int64_t from, int want_header, int64_t *pos, int64_t *file_size) {
+    FXG_CHECK_ARG(path && pos && from >= 0, "bad arguments");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { fxg_set_error("cannot open %s", path); return FXG_EIO; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); fxg_set_error("cannot stat %s", path); return FXG_EIO; }
+    const int64_t n = (int64_t)st.st_size;
+    if (file_size) *file_size = n;
+    *pos = n;
+    if (from >= n) { close(fd); return FXG_OK; }
+    std::vector<char> buf((size_t)1 << 20);
+    if (from == 0) {
+        char c0 = 0;
+        if (!want_header || (pread(fd, &c0, 1, 0) == 1 && c0 == '>')) { *pos = 0; close(fd); return FXG_OK; }
+        from = 1;
+    }
+    // candidates: x in [from-1, n) with byte[x] == '\n' (and byte[x+1] == '>'), answer x + 1
+    for (int64_t o = from - 1; o < n;) {
+        const ssize_t got = pread(fd, buf.data(), buf.size(), (off_t)o);
+        if (got <= 0) { close(fd); fxg_set_error("read error on %s", path); return FXG_EIO; }
+        const char *b = buf.data();
+        const char *p = b;
+        const char *e = b + got;
+        while ((p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr) {
+            const int64_t x = o + (p - b);
+            if (!want_header) { *pos = x + 1; close(fd); return FXG_OK; }
+            if (p + 1 < e) {
+                if (p[1] == '>') { *pos = x + 1; close(fd); return FXG_OK; }
+            } else if (x + 1 < n) {
+                char c1 = 0;
+                if (pread(fd, &c1, 1, (off_t)(x + 1)) == 1 && c1 == '>') { *pos = x + 1; close(fd); return FXG_OK; }
+            }
+            ++p;
+        }
+        o += got;
+    }
+    close(fd);
+    return FXG_OK;
+}
+
 extern "C" int fxg_file_wrap(fxg_ctx *c, void *dev_ptr, int64_t nbytes, int64_t capacity, fxg_file **out) {
     FXG_CHECK_ARG(c && out && dev_ptr && nbytes >= 0 && capacity >= nbytes, "bad arguments");
+    FXG_LOCK(c);
     FXG_CHECK_ARG(((uintptr_t)dev_ptr & 15) == 0, "device pointer must be 16-byte aligned");
     FXG_CHECK_ARG(capacity >= fxg_round_up(nbytes, 16), "capacity must cover nbytes rounded up to 16");
     fxg_file *f = new fxg_file();
@@ -303,6 +381,7 @@ extern "C" int fxg_file_wrap(fxg_ctx *c, void *dev_ptr, int64_t nbytes, int64_t 
 
 extern "C" int fxg_file_download(fxg_ctx *c, const fxg_file *f, int64_t src_off, void *host, int64_t nbytes) {
     FXG_CHECK_ARG(c && f && host && src_off >= 0 && nbytes >= 0 && src_off + nbytes <= f->size, "bad arguments");
+    FXG_LOCK(c);
     FXG_CUDA(cudaSetDevice(c->device));
     FXG_CUDA(cudaMemcpyAsync(host, f->d + src_off, (size_t)nbytes, cudaMemcpyDeviceToHost, c->stream));
     FXG_CUDA(cudaStreamSynchronize(c->stream));
@@ -320,6 +399,7 @@ extern "C" void fxg_file_free(fxg_file *f) {
 // ---- rows up/down ------------------------------------------------------------------------------
 extern "C" int fxg_rows_download(fxg_ctx *c, const void *d_rows, int64_t n_rows, int row_bytes, void *host_rows) {
     FXG_CHECK_ARG(c && (n_rows == 0 || (d_rows && host_rows)) && n_rows >= 0 && row_bytes > 0, "bad arguments");
+    FXG_LOCK(c);
     FXG_CUDA(cudaSetDevice(c->device));
     if (n_rows) {
         FXG_CUDA(cudaMemcpyAsync(host_rows, d_rows, (size_t)n_rows * row_bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -330,6 +410,7 @@ extern "C" int fxg_rows_download(fxg_ctx *c, const void *d_rows, int64_t n_rows,
 
 extern "C" int fxg_rows_upload(fxg_ctx *c, const void *host_rows, int64_t n_rows, int row_bytes, void **d_rows_out) {
     FXG_CHECK_ARG(c && d_rows_out && n_rows >= 0 && row_bytes > 0 && (n_rows == 0 || host_rows), "bad arguments");
+    FXG_LOCK(c);
     FXG_CUDA(cudaSetDevice(c->device));
     *d_rows_out = nullptr;
     void *d = nullptr;
@@ -365,6 +446,7 @@ static int stage_into_ctx(fxg_ctx *c, const void *host_buf, int64_t nbytes, fxg_
 extern "C" int fxg_fasta_build_index_host(fxg_ctx *c, const void *host_buf, int64_t nbytes, int flags,
                                           fxg_fasta_row *rows, int64_t rows_cap, fxg_scan_stats *stats) {
     FXG_CHECK_ARG(c && stats && (host_buf || nbytes == 0), "bad arguments");
+    FXG_LOCK(c);
     fxg_file f;
     int rc = stage_into_ctx(c, host_buf, nbytes, &f);
     if (rc) return rc;
@@ -380,11 +462,12 @@ extern "C" int fxg_fasta_build_index_host(fxg_ctx *c, const void *host_buf, int6
 extern "C" int fxg_fastq_build_index_host(fxg_ctx *c, const void *host_buf, int64_t nbytes,
                                           fxg_fastq_row *rows, int64_t rows_cap, fxg_scan_stats *stats) {
     FXG_CHECK_ARG(c && stats && (host_buf || nbytes == 0), "bad arguments");
+    FXG_LOCK(c);
     fxg_file f;
     int rc = stage_into_ctx(c, host_buf, nbytes, &f);
     if (rc) return rc;
     fxg_fastq_row *d_rows = nullptr;
-    rc = fxg_fastq_scan(c, &f, 0, 0, &d_rows, stats);
+    rc = fxg_fastq_scan(c, &f, 0, &d_rows, stats);
     if (rc == FXG_OK) {
         if (stats->n_rows > rows_cap) { fxg_set_error("rows_cap %lld < n_rows %lld", (long long)rows_cap, (long long)stats->n_rows); rc = FXG_ECAP; }
         else rc = fxg_rows_download(c, d_rows, stats->n_rows, (int)sizeof(fxg_fastq_row), rows);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <mutex>
 #include "../../include/fxg.h"
 
 // ---------------------------------------------------------------------------------------
@@ -43,7 +44,17 @@ struct fxg_file {
     int      device = 0;
 };
 
+// state of a split-phase scan between fxg_scan_begin and fxg_scan_finish
+struct FxgScanRun {
+    bool     active = false;
+    int      mode = 0, flags = 0;
+    const fxg_file *file = nullptr;
+    int64_t  base_offset = 0;
+};
+
 struct fxg_ctx {
+    std::recursive_mutex mu;             // every entry point that touches scratch or the stream holds it
+    FxgScanRun   run;
     int          device = 0;
     int          sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -53,14 +64,17 @@ struct fxg_ctx {
     size_t       pinned_bytes = 0;
     cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
     // scan scratch
-    FxgScratch   tile_desc, seg, row_tmp, rows, counters, plan, misc, stage_file;
+    FxgScratch   tile_desc, seg, cut, row_tmp, rows, counters, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small
     // measurement hooks
     bool         profiling = false;
     cudaEvent_t  prof_ev[FXG_PROF_SLOTS][2] = {};
     bool         prof_valid[FXG_PROF_SLOTS] = {};
     int64_t      launches = 0;
+    int64_t      collectives = 0;
 };
+
+#define FXG_LOCK(ctx) std::lock_guard<std::recursive_mutex> fxg_lock__((ctx)->mu)
 
 // brackets a kernel launch with events when profiling is on; always counts the launch
 struct FxgProfScope {

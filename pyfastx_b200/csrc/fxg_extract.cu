@@ -788,6 +788,7 @@ static int prefix_lengths(fxg_ctx *ctx, const int64_t *d_s, const int64_t *d_e, 
 extern "C" int fxg_extract_plan_dev(fxg_ctx *ctx, const int64_t *d_s, const int64_t *d_e, int64_t nq,
                                     int64_t *d_out_off, int64_t *total_bytes) {
     FXG_CHECK_ARG(ctx && d_out_off && nq >= 0 && (nq == 0 || (d_s && d_e)), "bad arguments");
+    FXG_LOCK(ctx);
     return prefix_lengths(ctx, d_s, d_e, nullptr, nullptr, 0, nq, d_out_off, total_bytes);
 }
 
@@ -804,6 +805,7 @@ extern "C" int fxg_extract_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_
                                const int32_t *d_flags, int64_t nq, const int64_t *d_out_off, uint8_t *d_out,
                                int64_t *d_acgt) {
     FXG_CHECK_ARG(ctx && f && nq >= 0, "bad arguments");
+    FXG_LOCK(ctx);
     if (nq == 0) return FXG_OK;
     FXG_CHECK_ARG(d_rows && d_row_id && d_s && d_e && d_out_off && d_out, "null device pointer");
     FXG_CUDA(cudaSetDevice(ctx->device));
@@ -831,6 +833,7 @@ extern "C" int fxg_extract_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta
                                 int64_t nq, int64_t *out_off_host, uint8_t *out_host, int64_t out_cap,
                                 int64_t *acgt_host) {
     FXG_CHECK_ARG(ctx && f && nq >= 0, "bad arguments");
+    FXG_LOCK(ctx);
     if (nq == 0) { if (out_off_host) out_off_host[0] = 0; return FXG_OK; }
     FXG_CHECK_ARG(row_id && s && e && out_off_host && out_host, "null host pointer");
     FXG_CUDA(cudaSetDevice(ctx->device));
@@ -866,6 +869,7 @@ extern "C" int fxg_reads_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_ro
                              const int64_t *d_ids, int64_t nq, int32_t flags, int64_t *d_out_off,
                              uint8_t *d_seq_out, uint8_t *d_qual_out, int64_t out_cap, int64_t *total_bytes) {
     FXG_CHECK_ARG(ctx && f && nq >= 0 && d_out_off, "bad arguments");
+    FXG_LOCK(ctx);
     FXG_CUDA(cudaSetDevice(ctx->device));
     int64_t total = 0;
     int rc = prefix_lengths(ctx, nullptr, nullptr, d_rows, d_ids, n_rows, nq, d_out_off, &total);
@@ -884,6 +888,7 @@ extern "C" int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_r
                               const int64_t *ids, int64_t nq, int32_t flags, int64_t *out_off_host,
                               uint8_t *seq_host, uint8_t *qual_host, int64_t out_cap) {
     FXG_CHECK_ARG(ctx && f && nq >= 0 && out_off_host, "bad arguments");
+    FXG_LOCK(ctx);
     if (nq == 0) { out_off_host[0] = 0; return FXG_OK; }
     FXG_CUDA(cudaSetDevice(ctx->device));
     int rc = ctx->misc.reserve((size_t)nq * 8 + (size_t)(nq + 1) * 8 + 64);
@@ -912,6 +917,7 @@ extern "C" int fxg_composition_host(fxg_ctx *ctx, const fxg_file *f, const fxg_f
                                     const int64_t *row_id, const int64_t *s, const int64_t *e, const int32_t *flags,
                                     int64_t nq, int64_t *hist_host) {
     FXG_CHECK_ARG(ctx && f && nq >= 0 && (nq == 0 || (row_id && s && e && hist_host)), "bad arguments");
+    FXG_LOCK(ctx);
     if (nq == 0) return FXG_OK;
     FXG_CUDA(cudaSetDevice(ctx->device));
     const size_t qb = (size_t)nq * sizeof(int64_t);

@@ -502,6 +502,7 @@ extern "C" int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed,
                                        const int64_t *d_ucmp_off, int64_t n_members, uint8_t *d_out, int64_t out_cap,
                                        int32_t *d_status) {
     FXG_CHECK_ARG(ctx && compressed && n_members >= 0, "bad arguments");
+    FXG_LOCK(ctx);
     if (n_members == 0) return FXG_OK;
     FXG_CHECK_ARG(d_cmp_off && d_ucmp_off && d_out && d_status, "null device pointer");
     FXG_CUDA(cudaSetDevice(ctx->device));
@@ -530,6 +531,7 @@ extern "C" int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed,
 extern "C" int fxg_file_from_bgzf_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, fxg_file **out,
                                        int64_t *n_members_out) {
     FXG_CHECK_ARG(ctx && host_buf && out, "bad arguments");
+    FXG_LOCK(ctx);
     *out = nullptr;
     int64_t n = 0, total = 0;
     int rc = fxg_bgzf_members_host(host_buf, nbytes, nullptr, nullptr, 0, &n, &total);

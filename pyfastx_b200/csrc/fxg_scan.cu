@@ -30,6 +30,8 @@
 // waiting on L2 round trips.  Splitting the dependency out of the streaming kernel removes that wait.
 #include "fxg_common.cuh"
 #include <stdlib.h>
+#include <string.h>
+#include <limits.h>
 
 namespace fxg {
 
@@ -57,14 +59,21 @@ struct __align__(16) FastaTmp {   // per header slot (slot 0 = lines before the 
 };
 static_assert(sizeof(FastaTmp) == 64, "FastaTmp layout");
 
-struct ScanTotals {
+struct ScanTotals {     // device, 128 bytes; every phase-B kernel reads its sizes from here (no host round trip)
     uint64_t nl;        // newlines (incl. the virtual one at n)
     uint64_t hdr;       // header starts
     int64_t  n_eff;     // n + 1 if the last line has no '\n'
     uint64_t sum_len;   // FASTA: sum(slen) (finalize); FASTQ: sum(rlen)
     int64_t  lead_lines, lead_bytes, lead_llen;
-    uint64_t pad;
+    int64_t  first_line;   // FASTQ: global index of this shard's first line (shard_prefix_kernel)
+    int64_t  nrows;        // row slots phase B writes: FASTA header count; FASTQ incl. partially owned rows
+    int64_t  row0;         // FASTQ: index of the first row whose name line lies in this shard (0 or 1)
+    int64_t  n_owned;      // FASTQ: complete reads whose name line lies in this shard
+    int64_t  total_lines;  // lines of all shards
+    int64_t  pad[4];
 };
+static_assert(sizeof(ScanTotals) == 128, "ScanTotals layout");
+static_assert(sizeof(fxg_shard_info) == 128, "fxg_shard_info layout");
 
 struct ScanParams {
     const uint8_t *file;
@@ -72,12 +81,14 @@ struct ScanParams {
     int64_t   capacity;     // readable bytes at file (multiple of 16)
     int64_t   nreg;         // regions that can hold a newline: ceil((n + 1) / REGION)
     int64_t   base_offset;  // added to every file offset written to rows
-    int64_t   first_line;   // FASTQ: global index of the first line of this buffer
+    int64_t   first_line;   // FASTQ: global index of the first line of this buffer (kernels load it from totals)
     int       flags;
     uint2    *rc;           // per region: {newlines | header starts << 16, last entry | the one before << 16}
                             // (padded to PS_BLOCK with zeros)
     uint4    *rec2;         // FASTA, per region: {first entry | second << 16, interesting-line mask, header mask, 0}
     uint16_t *seg;          // per region: SEGCAP entries, file order
+    uint8_t  *cut;          // FASTQ, per entry: name cut of the line FOLLOWING that newline if it starts with '@'
+                            // (offset of the first ' ' after the '@'; 254 = no blank in the line; 255 = not examined)
     ulonglong2 *ex;         // per region: exclusive {newlines, header starts}
     ulonglong2 *bs;         // per prefix block
     ScanTotals *totals;
@@ -92,6 +103,40 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+
+// FASTQ name cut (fastq.c:104-117: the name ends at the first ' ', strchr semantics) of a line that begins
+// with '@' at region byte a-1, searched in the region's shared-memory copy: the first byte below 0x21 in a
+// NAMEWIN-byte window decides -- ' ' -> its offset; '\n', NUL or "\r\n" -> 254 (no blank: the whole line);
+// anything else (tab, lone '\r', window or region end reached) -> 255 = the rows kernel searches the file.
+// Measured on C4 (126M reads): the rows kernel gets 1.2 ms faster, mark 3.5 ms slower (it is issue bound) -- so the
+// side list is compiled out by default and the rows kernel searches the name line in the file (FXG_MARK_CUT=1 for A/B).
+#ifndef FXG_MARK_CUT
+#define FXG_MARK_CUT 0
+#endif
+constexpr int NAMEWIN = 96;
+__device__ __forceinline__ uint32_t name_cut_smem(const uint8_t *sb, uint32_t a) {
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(sb);
+    const uint32_t end = min(a + (uint32_t)NAMEWIN, (uint32_t)REGION);
+    uint32_t wi = a >> 2;
+    uint32_t w = w32[wi];
+    // 0x80 per byte below 0x21 (bytes >= 0x80 never match)
+    uint32_t lt = ~((((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w)) & 0x80808080u & (0xffffffffu << (8u * (a & 3u)));
+    while (!lt) {
+        ++wi;
+        if (wi * 4u >= end) return 255u;
+        w = w32[wi];
+        lt = ~((((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w)) & 0x80808080u;
+    }
+    const uint32_t idx = (uint32_t)(__ffs(lt) - 1) >> 3;
+    const uint32_t p = wi * 4u + idx;
+    if (p >= end) return 255u;
+    const uint32_t b = (w >> (8u * idx)) & 0xffu;
+    const uint32_t c = p - a;
+    if (b == ' ') return c < 254u ? c : 255u;
+    if (b == '\n' || b == 0u) return 254u;
+    if (b == '\r' && p + 1u < (uint32_t)REGION && sb[p + 1u] == '\n') return 254u;
+    return 255u;
 }
 
 // =============================================================================================
@@ -219,10 +264,11 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
         uint32_t imask = 0, hmask = 0;
         for (uint32_t k0 = 0; k0 < nround; k0 += 32) {
             const uint32_t k = k0 + lane;
-            uint32_t e = 0;
+            uint32_t e = 0, cutv = 255u;
             if (k < nlc) {
                 const uint32_t pos = ent[k];
                 e = pos;
+                if (FXG_MARK_CUT && MODE == 1 && pos + 2u < (uint32_t)REGION && sb[pos + 1u] == '@') cutv = name_cut_smem(sb, pos + 2u);
                 if (MODE == 0) {
                     const uint32_t next = pos < (uint32_t)(REGION - 1) ? (uint32_t)sb[pos + 1]
                                                                       : (base + REGION < n ? (uint32_t)file[base + REGION] : 0u);
@@ -246,6 +292,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
                 }
             }
             if (k < nround) dst[k] = (uint16_t)e;
+            if (FXG_MARK_CUT && MODE == 1) P.cut[r * SEGCAP + k] = (uint8_t)cutv;   // one whole 32-byte sector per batch
             if (k < nlc) ent[k] = (uint16_t)e;                   // complete entries (for the region records)
         }
         __syncwarp();
@@ -417,7 +464,7 @@ __device__ __forceinline__ bool nl_at(const ScanParams &P, int64_t x) {         
 //      header; hcount: header starts up to and including the one after pm1 (= record ordinal + 1);
 //      cr: the byte before p is '\r' (FASTQ entries carry it; FASTA looks it up for header lines only) ----
 template <int MODE>
-__device__ __forceinline__ void do_line(const ScanParams &P, int64_t p, int64_t pm1, int64_t pm2, bool h1, bool h2,
+__device__ __forceinline__ void do_line(const ScanParams &P, int64_t first_line, int64_t p, int64_t pm1, int64_t pm2, bool h1, bool h2,
                                         int64_t hcount, int64_t lineidx, bool cr, unsigned long long &my_size) {
     const uint8_t *file = P.file;
     const int64_t s = pm1 + 1;
@@ -465,9 +512,9 @@ __device__ __forceinline__ void do_line(const ScanParams &P, int64_t p, int64_t 
             }
         }
     } else {
-        const int64_t gline = P.first_line + lineidx;
+        const int64_t gline = first_line + lineidx;
         const int ph = (int)(gline & 3);
-        const int64_t row = (gline >> 2) - (P.first_line >> 2);
+        const int64_t row = (gline >> 2) - (first_line >> 2);
         const int64_t len = L - 1;
         if (ph == 1) {
             const int64_t rlen = (len > 0 && cr) ? len - 1 : len;
@@ -535,7 +582,7 @@ __device__ __noinline__ void carry_walk(const ScanParams &P, int64_t r, Prev2 &c
 
 // ---- dense region (more than SEGCAP newlines in 2 KiB): re-read the bytes; every lane owns 64 of them ----
 template <int MODE>
-__device__ __noinline__ void dense_region(const ScanParams &P, int64_t r, const Prev2 &cy, ulonglong2 exv,
+__device__ __noinline__ void dense_region(const ScanParams &P, int64_t first_line, int64_t r, const Prev2 &cy, ulonglong2 exv,
                                           unsigned long long &my_size) {
     const int lane = threadIdx.x & 31;
     const uint8_t *file = P.file;
@@ -580,7 +627,7 @@ __device__ __noinline__ void dense_region(const ScanParams &P, int64_t r, const 
         const int64_t x = b0 + i;
         if (!nl_at(P, x)) continue;
         const bool cr = x > 0 && file[x - 1] == '\r';
-        do_line<MODE>(P, x, pv.pos1, pv.pos0, pv.h1 != 0, pv.h0 != 0, hcount, idx, cr, my_size);
+        do_line<MODE>(P, first_line, x, pv.pos1, pv.pos0, pv.h1 != 0, pv.h0 != 0, hcount, idx, cr, my_size);
         const uint32_t hh = is_hdr_at<MODE>(P, x + 1);
         hcount += hh; ++idx;
         pv.pos0 = pv.pos1; pv.h0 = pv.h1; pv.pos1 = x; pv.h1 = hh;
@@ -590,7 +637,7 @@ __device__ __noinline__ void dense_region(const ScanParams &P, int64_t r, const 
 // ---- the lines of one region with at most SEGCAP newlines, warp-cooperative: batches of 32 entries.
 //      E0 / E1: the first two batches (entry k0 + lane), loaded by the caller. ----
 template <int MODE>
-__device__ __forceinline__ void region_batches(const ScanParams &P, int64_t r, int nl, Prev2 cy, ulonglong2 X,
+__device__ __forceinline__ void region_batches(const ScanParams &P, int64_t first_line, int64_t r, int nl, Prev2 cy, ulonglong2 X,
                                                uint32_t E0, uint32_t E1, unsigned long long &my_size) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -611,7 +658,7 @@ __device__ __forceinline__ void region_batches(const ScanParams &P, int64_t r, i
             if (lane >= 2) { pm2 = base + (e2 & E_POS); h2 = (e2 & E_HDR) != 0; }
             else if (lane == 1) { pm2 = cy.pos1; h2 = cy.h1 != 0; }
             else { pm2 = cy.pos0; h2 = cy.h0 != 0; }
-            do_line<MODE>(P, base + (e & E_POS), pm1, pm2, h1, h2, hrun + __popc(hb & lt_mask), (int64_t)X.x + k,
+            do_line<MODE>(P, first_line, base + (e & E_POS), pm1, pm2, h1, h2, hrun + __popc(hb & lt_mask), (int64_t)X.x + k,
                           (e & E_CR) != 0, my_size);
         }
         // carry for the next batch (only reached when this one was full)
@@ -624,7 +671,7 @@ __device__ __forceinline__ void region_batches(const ScanParams &P, int64_t r, i
 
 // ---- general path for one region: everything looked up from scratch ----
 template <int MODE>
-__device__ __noinline__ void full_region(const ScanParams &P, int64_t r, unsigned long long &my_size) {
+__device__ __noinline__ void full_region(const ScanParams &P, int64_t first_line, int64_t r, unsigned long long &my_size) {
     const int lane = threadIdx.x & 31;
     const int nl = (int)(P.rc[r].x & 0xffffu);
     if (nl == 0) return;
@@ -632,8 +679,8 @@ __device__ __noinline__ void full_region(const ScanParams &P, int64_t r, unsigne
     Prev2 cy;
     carry_walk<MODE>(P, r, cy);
     if (MODE != 0) cy.h1 = cy.h0 = 0;
-    if (nl <= SEGCAP) region_batches<MODE>(P, r, nl, cy, X, P.seg[r * SEGCAP + lane], P.seg[r * SEGCAP + 32 + lane], my_size);
-    else dense_region<MODE>(P, r, cy, X, my_size);
+    if (nl <= SEGCAP) region_batches<MODE>(P, first_line, r, nl, cy, X, P.seg[r * SEGCAP + lane], P.seg[r * SEGCAP + 32 + lane], my_size);
+    else dense_region<MODE>(P, first_line, r, cy, X, my_size);
 }
 
 constexpr int LG = 4;     // consecutive regions per warp of the lines kernel (all their loads in flight together)
@@ -641,6 +688,7 @@ constexpr int LG = 4;     // consecutive regions per warp of the lines kernel (a
 // Every line does work (FASTQ): one warp per LG regions, lane per line.
 template <int MODE>
 __global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams P) {
+    const int64_t first_line = MODE == 1 ? P.totals->first_line : 0;   // global line phase, known only after the exchange
     const int lane = threadIdx.x & 31;
     const int64_t r0 = ((int64_t)blockIdx.x * MARK_WARPS + (threadIdx.x >> 5)) * LG;
     if (r0 >= P.nreg) return;
@@ -703,8 +751,8 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams
             if (slow) carry_walk<MODE>(P, r, cy);
             if (MODE != 0) cy.h1 = cy.h0 = 0;
         }
-        if (nl <= SEGCAP) region_batches<MODE>(P, r, nl, cy, X[i], E[i][0], E[i][1], my_size);
-        else dense_region<MODE>(P, r, cy, X[i], my_size);
+        if (nl <= SEGCAP) region_batches<MODE>(P, first_line, r, nl, cy, X[i], E[i][0], E[i][1], my_size);
+        else dense_region<MODE>(P, first_line, r, cy, X[i], my_size);
     }
 
     if (MODE == 1) {
@@ -725,8 +773,11 @@ constexpr int RG = 8;                          // regions per warp
 constexpr int RWIN = RG + 2;                   // + look-ahead
 static_assert(RWIN * REGION <= 32768, "window positions must fit 15 bits");
 
-__global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const ScanParams P) {
+__global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const ScanParams Pin) {
     __shared__ uint16_t s_flat[MARK_WARPS][RWIN * SEGCAP];      // position in window | '\r' before << 15
+    __shared__ uint8_t  s_cut[MARK_WARPS][FXG_MARK_CUT ? RWIN * SEGCAP : 1];   // name cut of the line after that newline (mark)
+    const ScanParams &P = Pin;
+    const int64_t first_line = Pin.totals->first_line;          // global line phase, known only after the exchange
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t r0 = ((int64_t)blockIdx.x * MARK_WARPS + warp) * RG;
     if (r0 >= P.nreg) return;
@@ -742,20 +793,23 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
     const uint32_t densem = __ballot_sync(0xffffffffu, nll > (uint32_t)SEGCAP);
     if (densem & (((1u << RG) - 1u) << 1)) {                       // a dense region inside the span
         for (int i = 0; i < RG; ++i)
-            if (r0 + i < P.nreg) full_region<1>(P, r0 + i, my_size);
+            if (r0 + i < P.nreg) full_region<1>(P, first_line, r0 + i, my_size);
     } else {
         const uint64_t ex0 = (uint64_t)shfl_i64((int64_t)exl, 1);    // lines before the span
         // ---- flatten the window ----
         uint16_t *flat = s_flat[warp];
+        uint8_t *cutf = s_cut[warp];
         int W = 0, Ls = 0;                                           // entries in the window / in the span
 #pragma unroll 1
         for (int i = 0; i < RWIN; ++i) {
             const int nl = (int)__shfl_sync(0xffffffffu, nll, i + 1);
             if (nl > SEGCAP) break;                                  // dense look-ahead region: the window ends here
             const uint16_t *sg = P.seg + (r0 + i) * SEGCAP;
+            const uint8_t *cg = P.cut + (r0 + i) * SEGCAP;
             for (int k = lane; k < nl; k += 32) {
                 const uint32_t e = sg[k];
                 flat[W + k] = (uint16_t)((i * REGION + (int)(e & E_POS)) | ((e & E_CR) ? 0x8000u : 0u));
+                if (FXG_MARK_CUT) cutf[W + k] = cg[k];
             }
             W += nl;
             if (i == RG - 1) Ls = W;
@@ -763,17 +817,20 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
         __syncwarp();
         // ---- the newline before the span ----
         int64_t carry;
+        uint32_t carry_cut = 255u;                                   // cut of the line that starts right after `carry`
         {
             const uint32_t pn = __shfl_sync(0xffffffffu, nll, 0), py = __shfl_sync(0xffffffffu, rec.y, 0);
             if (r0 == 0) carry = -1;
-            else if (pn >= 1 && pn <= (uint32_t)SEGCAP) carry = (r0 - 1) * REGION + (int64_t)(py & E_POS);
-            else { Prev2 cy; carry_walk<1>(P, r0, cy); carry = cy.pos1; }
+            else if (pn >= 1 && pn <= (uint32_t)SEGCAP) {
+                carry = (r0 - 1) * REGION + (int64_t)(py & E_POS);
+                if (FXG_MARK_CUT) carry_cut = P.cut[(r0 - 1) * SEGCAP + (pn - 1)];
+            } else { Prev2 cy; carry_walk<1>(P, r0, cy); carry = cy.pos1; }
         }
         const int64_t span_base = r0 * REGION;
         auto POS = [&](int f) -> int64_t { return f < 0 ? carry : span_base + (int64_t)(flat[f] & 0x7fffu); };
         auto CR = [&](int f) -> bool { return (flat[f] & 0x8000u) != 0; };
-        const int64_t g0 = P.first_line + (int64_t)ex0;              // global line index of flat[0]
-        const int64_t row0 = P.first_line >> 2;
+        const int64_t g0 = first_line + (int64_t)ex0;                // global line index of flat[0]
+        const int64_t row0 = first_line >> 2;
         int lead = (int)((4 - (g0 & 3)) & 3);
         if (lead > Ls) lead = Ls;
         // ---- (a) leading lines of a read that started before the span: field by field ----
@@ -805,7 +862,10 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
                 if (l < 0) l = 0;
                 const int64_t s = pm1 + 1;
                 int64_t k = 0;
-                if (s + 1 + l + 20 <= P.capacity) {
+                const uint32_t cv = !FXG_MARK_CUT ? 255u : (f >= 1 ? (uint32_t)cutf[f - 1] : carry_cut);   // found by mark while the bytes were on chip
+                if (cv < 254u) k = (int64_t)cv < l ? (int64_t)cv : l;
+                else if (cv == 254u) k = l;
+                else if (s + 1 + l + 20 <= P.capacity) {
                     int which;
                     k = find_first_of2(file + s + 1, l, 0x20202020u, 0x00000000u, &which);
                     if (which == 2) k = l;          // a NUL before any space: strchr() finds nothing (fastq.c:112)
@@ -889,26 +949,30 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fasta_lines_kernel(const Scan
         if (k >= 2) { e = sg[k]; m1 = sg[k - 1]; m2 = sg[k - 2]; }
         else if (k == 1) { e = f1; m1 = f0; m2 = c1; b2 = base - REGION; }
         else { e = f0; m1 = c1; m2 = c0; b1 = b2 = base - REGION; }
-        do_line<0>(P, base + (e & E_POS), b1 + (m1 & E_POS), b2 + (m2 & E_POS), (m1 & E_HDR) != 0, (m2 & E_HDR) != 0,
+        do_line<0>(P, 0, base + (e & E_POS), b1 + (m1 & E_POS), b2 + (m2 & E_POS), (m1 & E_HDR) != 0, (m2 & E_HDR) != 0,
                    (int64_t)X.y + __popc(q.z & ((1u << k) - 1u)), (int64_t)X.x + k, false, dummy);
     }
     uint32_t fm = __ballot_sync(0xffffffffu, full);
     while (fm) {
         const int f = __ffs(fm) - 1;
         fm &= fm - 1;
-        full_region<0>(P, R0 + f, dummy);
+        full_region<0>(P, 0, R0 + f, dummy);
     }
 }
+
 
 // ---- FASTA finalize: per-record fields from neighbouring headers + event summary ------------
 // blen  = next header start - boff (or end position)                       index.c:243,348
 // slen  = blen - n_lines * elen  (sum over lines of len - elen + 1)        index.c:335-338
 // norm  = [#lines differing from the first <= 1], from the events (DESIGN.md proof)  index.c:325-342
-__global__ void fasta_finalize_kernel(const FastaTmp *tmp, int64_t nrows, int64_t base_offset,
-                                      ScanTotals *tot, fxg_fasta_row *rows) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// The row count comes from the device totals (grid-stride), so the host never waits for it.
+__global__ void __launch_bounds__(256) fasta_finalize_kernel(const FastaTmp *tmp, int64_t tmp_cap, int64_t rows_cap,
+                                                             int64_t base_offset, ScanTotals *tot, fxg_fasta_row *rows) {
+    int64_t nrows = (int64_t)tot->hdr;
+    if (nrows > rows_cap || nrows + 1 > tmp_cap) nrows = 0;        // capacity miss: the host regrows and reruns phase B
     unsigned long long slen_acc = 0;
-    if (r < nrows) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
         const FastaTmp t = tmp[r + 1];
         int64_t next_h, next_line;
         if (r + 1 < nrows) {
@@ -934,12 +998,12 @@ __global__ void fasta_finalize_kernel(const FastaTmp *tmp, int64_t nrows, int64_
         // uniform lines: no length change at all, or a single SHORTER line at the very end
         o.pad[0] = (t.D == 0 || (t.D == 1 && (int64_t)t.evmax == t.lineidx + nlines && (int64_t)t.S < 0)) ? 1 : 0;
         rows[r] = o;
-        slen_acc = (unsigned long long)slen;
+        slen_acc += (unsigned long long)slen;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) slen_acc += (unsigned long long)shfl_down_i64((int64_t)slen_acc, d);
     if ((threadIdx.x & 31) == 0 && slen_acc) atomicAdd((unsigned long long *)&tot->sum_len, slen_acc);
-    if (r == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         // lead part = lines before the first header of this buffer (multi-GPU shard merge)
         const FastaTmp l = tmp[0];
         tot->lead_llen = l.llen;
@@ -951,17 +1015,144 @@ __global__ void fasta_finalize_kernel(const FastaTmp *tmp, int64_t nrows, int64_
     }
 }
 
-// ---- plain newline count (FASTQ multi-GPU phase pass) ----------------------------------------
-__global__ void count_newlines_kernel(const uint8_t *file, int64_t n, unsigned long long *out) {
-    const int64_t nvec = n / 16;
-    unsigned long long cnt = 0;
-    const uint4 *v = reinterpret_cast<const uint4 *>(file);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
-        cnt += __popc(chunk_eq_mask(v[i], 0x0a0a0a0au));
-    if (blockIdx.x == 0)
-        for (int64_t i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) cnt += (file[i] == '\n');
-    for (int d = 16; d > 0; d >>= 1) cnt += (unsigned long long)shfl_down_i64((int64_t)cnt, d);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+// ---- phase A tail: what this shard tells the others (fxg_shard_info), one warp ----------------
+// The first up-to-three lines are read off the newline list (or the bytes of a dense region).
+__global__ void __launch_bounds__(32) edge_kernel(const ScanParams P, int mode, fxg_shard_info *info) {
+    const int lane = threadIdx.x;
+    int found = 0;
+    int64_t pos[3] = {0, 0, 0};
+    for (int64_t r0 = 0; r0 < P.nreg && found < 3; r0 += 32) {
+        const int64_t r = r0 + lane;
+        const uint32_t c = r < P.nreg ? (P.rc[r].x & 0xffffu) : 0u;
+        uint32_t nz = __ballot_sync(0xffffffffu, c != 0);
+        while (nz && found < 3) {
+            const int fl = __ffs(nz) - 1;
+            nz &= nz - 1;
+            const int64_t q = r0 + fl;
+            const int cq = (int)__shfl_sync(0xffffffffu, c, fl);
+            if (cq <= SEGCAP) {
+                for (int i = 0; i < cq && found < 3; ++i) pos[found++] = q * REGION + (int64_t)(P.seg[q * SEGCAP + i] & E_POS);
+            } else {
+                for (int64_t x = q * REGION; x < q * REGION + REGION && found < 3; ++x)
+                    if (nl_at(P, x)) pos[found++] = x;
+            }
+        }
+    }
+    if (lane == 0) {
+        const ScanTotals t = *P.totals;
+        fxg_shard_info o;
+        o.n_rows = mode == 0 ? (int64_t)t.hdr : 0;
+        o.n_lines = (int64_t)t.nl;
+        o.bytes = P.n;
+        o.base_offset = P.base_offset;
+        o.end_position = t.n_eff;
+        o.edge_n = found;
+        int64_t start = 0;
+        for (int j = 0; j < 3; ++j) {
+            o.edge_off[j] = 0; o.edge_len[j] = 0;
+            if (j < found) {
+                const int64_t p = pos[j];
+                const bool cr = p > start && p - 1 < P.n && P.file[p - 1] == '\r';
+                o.edge_off[j] = P.base_offset + start;
+                o.edge_len[j] = p - start - (cr ? 1 : 0);
+                start = p + 1;
+            }
+        }
+        for (int j = 0; j < 4; ++j) o.reserved[j] = 0;
+        *info = o;
+    }
+}
+
+// ---- phase B head: global line phase / row-slot count from the gathered shard infos -------------
+__global__ void shard_prefix_kernel(const fxg_shard_info *all, int nranks, int rank, int mode, ScanTotals *tot) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int64_t F = 0, T = 0;
+    for (int p = 0; p < nranks; ++p) {
+        const int64_t nlp = all[p].n_lines;
+        if (p < rank) F += nlp;
+        T += nlp;
+    }
+    if (mode == 0) F = 0;                       // FASTA line indices stay buffer-local
+    tot->first_line = F;
+    tot->total_lines = T;
+    const int64_t nl = (int64_t)tot->nl;
+    tot->nrows = mode == 0 ? (int64_t)tot->hdr : (F + nl + 3) / 4 - F / 4;
+    tot->sum_len = 0;                           // (re)accumulated by phase B
+}
+
+// zero what phase B accumulates into: FASTA record slots; FASTQ the two possibly partial boundary rows
+__global__ void __launch_bounds__(256) clear_kernel(const ScanParams P, int mode, int64_t tmp_slots) {
+    const int64_t nrows = P.totals->nrows;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 0) {
+        int64_t slots = nrows + 2;
+        if (slots > tmp_slots) slots = tmp_slots;
+        uint4 *p = reinterpret_cast<uint4 *>(P.tmp);
+        for (int64_t i = t0; i < slots * 4; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (t0 < 4) {
+        const int64_t row = t0 < 2 ? 0 : nrows - 1;
+        if (row >= 0 && row < P.qrows_cap) reinterpret_cast<uint4 *>(P.qrows + row)[t0 & 1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// ---- FASTQ boundary-row merge (one thread): a read belongs to the shard that holds its name line; the lines
+//      of the shard's last read that lie in later shards come from those shards' edge lines (fastq.c:122-133) ----
+__global__ void fastq_stitch_kernel(const ScanParams P, const fxg_shard_info *all, int nranks, int rank) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ScanTotals *tot = P.totals;
+    const int64_t F = tot->first_line, n = (int64_t)tot->nl, T = tot->total_lines;
+    const int64_t first_read = (F + 3) / 4;                    // first read whose name line is >= F
+    int64_t last_read = n > 0 ? (F + n - 1) / 4 : first_read - 1;   // last read whose name line is < F + n
+    if (last_read > T / 4 - 1) last_read = T / 4 - 1;          // only complete reads are rows (fastq.c:132-146,159)
+    const int64_t owned = last_read >= first_read ? last_read - first_read + 1 : 0;
+    tot->row0 = first_read - F / 4;
+    tot->n_owned = owned;
+    if (owned == 0) return;
+    const int64_t row = last_read - F / 4;
+    if (row >= P.qrows_cap) return;
+    for (int ph = 1; ph <= 3; ph += 2) {
+        const int64_t g = 4 * last_read + ph;
+        if (g < F + n) continue;                               // the line is ours: already written
+        int64_t Fp = F + n;
+        for (int p = rank + 1; p < nranks; ++p) {
+            const int64_t np = all[p].n_lines;
+            if (g < Fp + np) {
+                const int64_t j = g - Fp;
+                if (j < all[p].edge_n) {
+                    if (ph == 1) { P.qrows[row].soff = all[p].edge_off[j]; P.qrows[row].rlen = all[p].edge_len[j]; }
+                    else P.qrows[row].qoff = all[p].edge_off[j];
+                }
+                break;
+            }
+            Fp += np;
+        }
+    }
+}
+
+// ---- split point on resident data: first line start (or header line start) at or after `from` ----
+__global__ void __launch_bounds__(256) split_point_kernel(const uint8_t *file, int64_t n, int64_t from, int want_header,
+                                                          long long *out) {
+    __shared__ long long s_best;
+    if (threadIdx.x == 0) s_best = LLONG_MAX;
+    __syncthreads();
+    if (from <= 0) {
+        if (!want_header || (n > 0 && file[0] == '>')) { if (threadIdx.x == 0) *out = 0; return; }
+        from = 1;
+    }
+    for (int64_t c0 = from - 1; c0 < n; c0 += 256 * 16) {
+        const int64_t a = c0 + threadIdx.x * 16;
+        long long mine = LLONG_MAX;
+        for (int i = 0; i < 16; ++i) {
+            const int64_t x = a + i;
+            if (x < n && file[x] == '\n' && (!want_header || (x + 1 < n && file[x + 1] == '>'))) { mine = x + 1; break; }
+        }
+        if (mine != LLONG_MAX) atomicMin(&s_best, mine);
+        __syncthreads();
+        if (s_best != LLONG_MAX) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s_best == LLONG_MAX ? n : s_best;
 }
 
 }  // namespace fxg
@@ -971,38 +1162,75 @@ __global__ void count_newlines_kernel(const uint8_t *file, int64_t n, unsigned l
 // =============================================================================================
 using namespace fxg;
 
-static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offset, int64_t first_line, int flags,
-                    void **d_rows_out, fxg_scan_stats *stats) {
-    FXG_CHECK_ARG(ctx && f && stats, "null ctx/file/stats");
-    FXG_CUDA(cudaSetDevice(ctx->device));
-    memset(stats, 0, sizeof(*stats));
+// Row capacity policy: phase B is launched without knowing the row count on the host.  The buffers are
+// grow-only; a first scan of a file sizes them from the byte count (typical records), every kernel bounds
+// checks against the capacity, and a miss (known at the single synchronisation) regrows and reruns phase B.
+static int64_t guess_rows(int mode, int64_t n) { return (mode == 0 ? n / 1024 : n / 200) + 4096; }
+
+static int scan_params(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offset, int flags, bool reserve,
+                       ScanParams *out, int64_t *tmp_slots) {
     const int64_t n = f->size;
-    if (d_rows_out) *d_rows_out = nullptr;
-    if (n == 0) return FXG_OK;
     const int64_t nreg = (n + 1 + REGION - 1) / REGION;     // room for a virtual newline at n
     const int64_t nb = (nreg + PS_BLOCK - 1) / PS_BLOCK;
     const int64_t nreg_pad = nb * PS_BLOCK;
-    int rc;
-    if ((rc = ctx->counters.reserve(512))) return rc;
     // tile_desc: rc[nreg_pad] | bs[nb] | ex[nreg] | rec2[nreg] (FASTA)
     const size_t off_bs = fxg_round_up((int64_t)nreg_pad * 8, 256);
     const size_t off_ex = off_bs + fxg_round_up(nb * (int64_t)sizeof(ulonglong2), 256);
     const size_t off_r2 = off_ex + fxg_round_up(nreg * (int64_t)sizeof(ulonglong2), 256);
-    if ((rc = ctx->tile_desc.reserve(off_r2 + (mode == 0 ? (size_t)nreg * sizeof(uint4) : 0)))) return rc;
-    if ((rc = ctx->seg.reserve((size_t)nreg * SEGCAP * sizeof(uint16_t)))) return rc;
-
+    int rc;
+    if (reserve) {
+        if ((rc = ctx->counters.reserve(1024))) return rc;
+        if ((rc = ctx->tile_desc.reserve(off_r2 + (mode == 0 ? (size_t)nreg * sizeof(uint4) : 0)))) return rc;
+        if ((rc = ctx->seg.reserve((size_t)nreg * SEGCAP * sizeof(uint16_t)))) return rc;
+        if (FXG_MARK_CUT && mode == 1 && (rc = ctx->cut.reserve((size_t)nreg * SEGCAP))) return rc;
+        const int64_t want = guess_rows(mode, n);
+        if (mode == 0) {
+            if (ctx->row_tmp.cap < (size_t)(want + 2) * sizeof(FastaTmp) && (rc = ctx->row_tmp.reserve((size_t)(want + 2) * sizeof(FastaTmp)))) return rc;
+            if (ctx->rows.cap < (size_t)(want + 1) * sizeof(fxg_fasta_row) && (rc = ctx->rows.reserve((size_t)(want + 1) * sizeof(fxg_fasta_row)))) return rc;
+        } else if (ctx->rows.cap < (size_t)(want + 2) * sizeof(fxg_fastq_row)) {
+            if ((rc = ctx->rows.reserve((size_t)(want + 2) * sizeof(fxg_fastq_row)))) return rc;
+        }
+    }
     ScanParams P;
     memset(&P, 0, sizeof(P));
     P.file = f->d; P.n = n; P.capacity = f->capacity & ~(int64_t)15; P.nreg = nreg;
-    P.base_offset = base_offset; P.first_line = first_line; P.flags = flags;
+    P.base_offset = base_offset; P.first_line = 0; P.flags = flags;
     P.rc = (uint2 *)ctx->tile_desc.ptr;
     P.bs = (ulonglong2 *)((uint8_t *)ctx->tile_desc.ptr + off_bs);
     P.ex = (ulonglong2 *)((uint8_t *)ctx->tile_desc.ptr + off_ex);
     P.rec2 = (uint4 *)((uint8_t *)ctx->tile_desc.ptr + off_r2);
     P.seg = (uint16_t *)ctx->seg.ptr;
+    P.cut = (uint8_t *)ctx->cut.ptr;
     P.totals = (ScanTotals *)((uint8_t *)ctx->counters.ptr + 64);
+    *tmp_slots = 0;
+    if (mode == 0) {
+        *tmp_slots = (int64_t)(ctx->row_tmp.cap / sizeof(FastaTmp));
+        P.tmp = (FastaTmp *)ctx->row_tmp.ptr;
+        P.tmp_cap = *tmp_slots - 1;                              // slots 0 .. tmp_cap-1 are written
+    } else {
+        P.qrows = (fxg_fastq_row *)ctx->rows.ptr;
+        P.qrows_cap = (int64_t)(ctx->rows.cap / sizeof(fxg_fastq_row));
+    }
+    *out = P;
+    return FXG_OK;
+}
 
-    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 512, ctx->stream));
+static fxg_shard_info *own_info(fxg_ctx *ctx) { return (fxg_shard_info *)((uint8_t *)ctx->counters.ptr + 256); }
+
+// phase A: mark + prefix + edge.  No host synchronisation.
+extern "C" int fxg_scan_begin(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offset, int flags,
+                              fxg_shard_info *d_info_out) {
+    FXG_CHECK_ARG(ctx && f && (mode == 0 || mode == 1), "null ctx/file or bad mode");
+    FXG_LOCK(ctx);
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    ctx->run.active = false;
+    ScanParams P;
+    int64_t tmp_slots;
+    int rc = scan_params(ctx, f, mode, base_offset, flags, true, &P, &tmp_slots);
+    if (rc) return rc;
+    const int64_t n = f->size, nreg = P.nreg;
+    const int64_t nb = (nreg + PS_BLOCK - 1) / PS_BLOCK, nreg_pad = nb * PS_BLOCK;
+    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 1024, ctx->stream));
     if (nreg_pad > nreg) FXG_CUDA(cudaMemsetAsync(P.rc + nreg, 0, (size_t)(nreg_pad - nreg) * 8, ctx->stream));
     const unsigned grid = (unsigned)((nreg + MARK_WARPS - 1) / MARK_WARPS);
     {
@@ -1012,108 +1240,153 @@ static int run_scan(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t base_offs
     }
     FXG_CUDA(cudaGetLastError());
     {
-        FxgProfScope prof(ctx, FXG_PROF_PREFIX, 3);
+        FxgProfScope prof(ctx, FXG_PROF_PREFIX, 4);
         prefix_reduce_kernel<<<(unsigned)nb, PS_THREADS, 0, ctx->stream>>>(P.rc, P.bs);
         prefix_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(P.bs, nb, P.file, n, mode, P.totals);
         prefix_expand_kernel<<<(unsigned)nb, PS_THREADS, 0, ctx->stream>>>(P.rc, P.bs, P.ex, nreg);
+        edge_kernel<<<1, 32, 0, ctx->stream>>>(P, mode, own_info(ctx));
     }
     FXG_CUDA(cudaGetLastError());
+    if (d_info_out)
+        FXG_CUDA(cudaMemcpyAsync(d_info_out, own_info(ctx), sizeof(fxg_shard_info), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->run.active = true; ctx->run.mode = mode; ctx->run.flags = flags; ctx->run.file = f; ctx->run.base_offset = base_offset;
+    return FXG_OK;
+}
 
-    ScanTotals tot;
-    FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
-    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-
-    // exact row count is known before any row is written: no capacity estimate, no rerun
-    const int64_t nrows = mode == 0 ? (int64_t)tot.hdr
-                                    : (int64_t)((first_line + (int64_t)tot.nl + 3) / 4 - first_line / 4);
-    if (mode == 0) {
-        if ((rc = ctx->row_tmp.reserve((size_t)(nrows + 2) * sizeof(FastaTmp)))) return rc;
-        FXG_CUDA(cudaMemsetAsync(ctx->row_tmp.ptr, 0, (size_t)(nrows + 2) * sizeof(FastaTmp), ctx->stream));
-        P.tmp = (FastaTmp *)ctx->row_tmp.ptr; P.tmp_cap = nrows + 1;
-    } else {
-        if ((rc = ctx->rows.reserve((size_t)(nrows + 2) * sizeof(fxg_fastq_row)))) return rc;
-        // rows are fully overwritten except the partially-owned boundary rows
-        FXG_CUDA(cudaMemsetAsync(ctx->rows.ptr, 0, sizeof(fxg_fastq_row), ctx->stream));
-        if (nrows > 1)
-            FXG_CUDA(cudaMemsetAsync((fxg_fastq_row *)ctx->rows.ptr + (nrows - 1), 0, sizeof(fxg_fastq_row), ctx->stream));
-        P.qrows = (fxg_fastq_row *)ctx->rows.ptr; P.qrows_cap = nrows;
-    }
+static int launch_phase_b(fxg_ctx *ctx, const ScanParams &P, int mode, int64_t tmp_slots, const fxg_shard_info *d_all,
+                          int nranks, int rank) {
+    const int64_t nreg = P.nreg;
     {
-        FxgProfScope prof(ctx, FXG_PROF_LINES);
+        FxgProfScope prof(ctx, FXG_PROF_LINES, 3);
+        shard_prefix_kernel<<<1, 32, 0, ctx->stream>>>(d_all, nranks, rank, mode, P.totals);
+        clear_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(P, mode, tmp_slots);
         if (mode == 0) {
             const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * 32 - 1) / (MARK_WARPS * 32));
             fasta_lines_kernel<<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+        } else if (getenv("FXG_FASTQ_LINES_GENERIC")) {      // lane-per-line path for every region (A/B, debugging)
+            const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * LG - 1) / (MARK_WARPS * LG));
+            lines_kernel<1><<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
         } else {
-            if (getenv("FXG_FASTQ_LINES_GENERIC")) {      // lane-per-line path for every region (A/B, debugging)
-                const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * LG - 1) / (MARK_WARPS * LG));
-                lines_kernel<1><<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
-            } else {
-                const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * RG - 1) / (MARK_WARPS * RG));
-                fastq_records_kernel<<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
-            }
+            const unsigned lgrid = (unsigned)((nreg + MARK_WARPS * RG - 1) / (MARK_WARPS * RG));
+            fastq_records_kernel<<<lgrid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
         }
     }
     FXG_CUDA(cudaGetLastError());
-
-    stats->n_lines = (int64_t)tot.nl;
-    stats->end_position = tot.n_eff;
-    if (mode == 0) {
-        stats->n_rows = nrows;
-        if ((rc = ctx->rows.reserve((size_t)(nrows + 1) * sizeof(fxg_fasta_row)))) return rc;
-        const int64_t work = nrows > 0 ? nrows : 1;
-        {
-            FxgProfScope prof(ctx, FXG_PROF_FINALIZE);
-            fasta_finalize_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(
-                P.tmp, nrows, base_offset, P.totals, (fxg_fasta_row *)ctx->rows.ptr);
-        }
-        FXG_CUDA(cudaGetLastError());
-        FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
-        FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-        stats->total_len = (int64_t)tot.sum_len;
-        stats->lead_llen = tot.lead_llen;
-        if (nrows > 0) { stats->lead_lines = tot.lead_lines; stats->lead_bytes = tot.lead_bytes; }
-        else { stats->lead_lines = (int64_t)tot.nl; stats->lead_bytes = n; }
-    } else {
-        FXG_CUDA(cudaMemcpyAsync(&tot, P.totals, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
-        FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-        // complete reads only (fastq.c:132-146,159); rows owned partially by this buffer are
-        // still present in the array for the shard merge
-        stats->n_rows = (first_line + (int64_t)tot.nl) / 4 - first_line / 4;
-        stats->total_len = (int64_t)tot.sum_len;
+    {
+        FxgProfScope prof(ctx, FXG_PROF_FINALIZE);
+        if (mode == 0)
+            fasta_finalize_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(
+                P.tmp, P.tmp_cap, (int64_t)(ctx->rows.cap / sizeof(fxg_fasta_row)), P.base_offset, P.totals,
+                (fxg_fasta_row *)ctx->rows.ptr);
+        else
+            fastq_stitch_kernel<<<1, 32, 0, ctx->stream>>>(P, d_all, nranks, rank);
     }
-    if (d_rows_out) *d_rows_out = ctx->rows.ptr;
+    FXG_CUDA(cudaGetLastError());
     return FXG_OK;
+}
+
+// phase B + collect: ONE host synchronisation (two when a capacity guess was too small)
+extern "C" int fxg_scan_finish(fxg_ctx *ctx, const fxg_shard_info *d_all, int nranks, int rank, void **d_rows_out,
+                               fxg_scan_stats *stats, fxg_shard_info *all_host) {
+    FXG_CHECK_ARG(ctx && stats && nranks >= 1 && rank >= 0 && rank < nranks, "bad arguments");
+    FXG_LOCK(ctx);
+    FXG_CHECK_ARG(ctx->run.active, "fxg_scan_finish without fxg_scan_begin");
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    ctx->run.active = false;
+    const int mode = ctx->run.mode;
+    const fxg_file *f = ctx->run.file;
+    if (!d_all) { FXG_CHECK_ARG(nranks == 1, "d_all == NULL with more than one rank"); d_all = own_info(ctx); }
+    memset(stats, 0, sizeof(*stats));
+    if (d_rows_out) *d_rows_out = nullptr;
+    if (!ctx->h_counters) FXG_CUDA(cudaHostAlloc(&ctx->h_counters, 4096, cudaHostAllocDefault));
+    FXG_CHECK_ARG((size_t)nranks * sizeof(fxg_shard_info) + 256 <= 4096 || !all_host, "too many ranks for all_host");
+    ScanTotals *ht = (ScanTotals *)ctx->h_counters;
+    fxg_shard_info *hall = (fxg_shard_info *)((uint8_t *)ctx->h_counters + 256);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ScanParams P;
+        int64_t tmp_slots;
+        int rc = scan_params(ctx, f, mode, ctx->run.base_offset, ctx->run.flags, false, &P, &tmp_slots);
+        if (rc) return rc;
+        if ((rc = launch_phase_b(ctx, P, mode, tmp_slots, d_all, nranks, rank))) return rc;
+        FXG_CUDA(cudaMemcpyAsync(ht, P.totals, sizeof(ScanTotals), cudaMemcpyDeviceToHost, ctx->stream));
+        if (all_host)
+            FXG_CUDA(cudaMemcpyAsync(hall, d_all, (size_t)nranks * sizeof(fxg_shard_info), cudaMemcpyDeviceToHost, ctx->stream));
+        FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+        // capacity check (exact, after the fact)
+        bool fits;
+        if (mode == 0) fits = ht->nrows + 2 <= tmp_slots && (size_t)(ht->nrows + 1) * sizeof(fxg_fasta_row) <= ctx->rows.cap;
+        else fits = ht->nrows <= P.qrows_cap;
+        if (fits) break;
+        if (attempt == 1) { fxg_set_error("row buffers still too small after regrowing"); return FXG_ENOMEM; }
+        if (mode == 0) {
+            if ((rc = ctx->row_tmp.reserve((size_t)(ht->nrows + 2) * sizeof(FastaTmp)))) return rc;
+            if ((rc = ctx->rows.reserve((size_t)(ht->nrows + 1) * sizeof(fxg_fasta_row)))) return rc;
+        } else if ((rc = ctx->rows.reserve((size_t)(ht->nrows + 2) * sizeof(fxg_fastq_row)))) return rc;
+    }
+    stats->n_lines = (int64_t)ht->nl;
+    stats->end_position = ht->n_eff;
+    stats->total_len = (int64_t)ht->sum_len;
+    if (mode == 0) {
+        stats->n_rows = ht->nrows;
+        stats->lead_llen = ht->lead_llen;
+        if (ht->nrows > 0) { stats->lead_lines = ht->lead_lines; stats->lead_bytes = ht->lead_bytes; }
+        else { stats->lead_lines = (int64_t)ht->nl; stats->lead_bytes = f->size; }
+        if (d_rows_out) *d_rows_out = ctx->rows.ptr;
+    } else {
+        stats->n_rows = ht->n_owned;                 // complete reads whose name line lies in this shard
+        stats->lead_lines = ht->first_line;          // global index of the shard's first line
+        stats->reserved = ht->total_lines;
+        if (d_rows_out) *d_rows_out = (fxg_fastq_row *)ctx->rows.ptr + ht->row0;
+    }
+    if (all_host) memcpy(all_host, hall, (size_t)nranks * sizeof(fxg_shard_info));
+    return FXG_OK;
+}
+
+extern "C" int fxg_scan_sharded(fxg_ctx *ctx, fxg_comm *comm, const fxg_file *f, int mode, int64_t base_offset, int flags,
+                                void **d_rows_out, fxg_scan_stats *stats, fxg_shard_info *all_host) {
+    FXG_CHECK_ARG(ctx && f && stats, "null ctx/file/stats");
+    FXG_LOCK(ctx);
+    const int nranks = comm ? fxg_comm_nranks(comm) : 1, rank = comm ? fxg_comm_rank(comm) : 0;
+    int rc = ctx->misc.reserve((size_t)nranks * sizeof(fxg_shard_info) + 256);
+    if (rc) return rc;
+    fxg_shard_info *d_all = (fxg_shard_info *)ctx->misc.ptr;
+    if ((rc = fxg_scan_begin(ctx, f, mode, base_offset, flags, nullptr))) return rc;
+    if ((rc = fxg_shard_exchange(ctx, comm, own_info(ctx), d_all, sizeof(fxg_shard_info)))) return rc;
+    return fxg_scan_finish(ctx, d_all, nranks, rank, d_rows_out, stats, all_host);
 }
 
 extern "C" int fxg_fasta_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int flags,
                               fxg_fasta_row **d_rows_out, fxg_scan_stats *stats) {
-    return run_scan(ctx, f, 0, base_offset, 0, flags, (void **)d_rows_out, stats);
+    FXG_CHECK_ARG(ctx && f && stats, "null ctx/file/stats");
+    FXG_LOCK(ctx);
+    int rc = fxg_scan_begin(ctx, f, 0, base_offset, flags, nullptr);
+    if (rc) return rc;
+    return fxg_scan_finish(ctx, nullptr, 1, 0, (void **)d_rows_out, stats, nullptr);
 }
 
-extern "C" int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int64_t first_line,
+extern "C" int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset,
                               fxg_fastq_row **d_rows_out, fxg_scan_stats *stats) {
-    FXG_CHECK_ARG(first_line >= 0, "first_line < 0");
-    return run_scan(ctx, f, 1, base_offset, first_line, 0, (void **)d_rows_out, stats);
+    FXG_CHECK_ARG(ctx && f && stats, "null ctx/file/stats");
+    FXG_LOCK(ctx);
+    int rc = fxg_scan_begin(ctx, f, 1, base_offset, 0, nullptr);
+    if (rc) return rc;
+    return fxg_scan_finish(ctx, nullptr, 1, 0, (void **)d_rows_out, stats, nullptr);
 }
 
-extern "C" int fxg_count_lines(fxg_ctx *ctx, const fxg_file *f, int64_t *n_newlines, int *ends_with_newline) {
-    FXG_CHECK_ARG(ctx && f && n_newlines, "null argument");
+extern "C" int fxg_split_point_dev(fxg_ctx *ctx, const fxg_file *f, int64_t from, int want_header, int64_t *pos) {
+    FXG_CHECK_ARG(ctx && f && pos && from >= 0, "bad arguments");
+    FXG_LOCK(ctx);
     FXG_CUDA(cudaSetDevice(ctx->device));
+    if (from >= f->size) { *pos = f->size; return FXG_OK; }
     int rc;
-    if ((rc = ctx->counters.reserve(512))) return rc;
-    FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 64, ctx->stream));
-    unsigned long long h = 0;
-    uint8_t last = '\n';
-    if (f->size > 0) {
-        ctx->launches += 1;
-        count_newlines_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f->d, f->size,
-                                                                         (unsigned long long *)ctx->counters.ptr);
-        FXG_CUDA(cudaGetLastError());
-        FXG_CUDA(cudaMemcpyAsync(&last, f->d + f->size - 1, 1, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    FXG_CUDA(cudaMemcpyAsync(&h, ctx->counters.ptr, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = ctx->counters.reserve(1024))) return rc;
+    long long *d = (long long *)((uint8_t *)ctx->counters.ptr + 512);
+    ctx->launches += 1;
+    split_point_kernel<<<1, 256, 0, ctx->stream>>>(f->d, f->size, from, want_header, d);
+    FXG_CUDA(cudaGetLastError());
+    long long h = 0;
+    FXG_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
     FXG_CUDA(cudaStreamSynchronize(ctx->stream));
-    *n_newlines = (int64_t)h;
-    if (ends_with_newline) *ends_with_newline = (last == '\n');
+    *pos = (int64_t)h;
     return FXG_OK;
 }

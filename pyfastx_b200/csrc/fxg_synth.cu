@@ -118,6 +118,7 @@ using namespace fxg;
 extern "C" int fxg_synth_fasta_dev(fxg_ctx *ctx, uint64_t seed, const int64_t *d_lengths, const int64_t *d_rec_off,
                                    int64_t n_records, int64_t first_record, int width, uint8_t *d_out) {
     FXG_CHECK_ARG(ctx && d_lengths && d_rec_off && d_out && n_records >= 0 && width > 0, "bad arguments");
+    FXG_LOCK(ctx);
     if (n_records == 0) return FXG_OK;
     FXG_CUDA(cudaSetDevice(ctx->device));
     int64_t grid = n_records < (int64_t)ctx->sm_count * 32 ? n_records : (int64_t)ctx->sm_count * 32;
@@ -130,6 +131,7 @@ extern "C" int fxg_synth_fasta_dev(fxg_ctx *ctx, uint64_t seed, const int64_t *d
 extern "C" int fxg_synth_fastq_dev(fxg_ctx *ctx, uint64_t seed, int64_t n_reads, int64_t first_read, int read_len,
                                    const int64_t *d_rec_off, uint8_t *d_out) {
     FXG_CHECK_ARG(ctx && d_out && n_reads >= 0 && read_len > 0 && first_read >= 0, "bad arguments");
+    FXG_LOCK(ctx);
     if (n_reads == 0) return FXG_OK;
     FXG_CUDA(cudaSetDevice(ctx->device));
     ctx->launches += 1;

@@ -128,6 +128,18 @@ class Engine:
         f.n_members = nm.value
         return f
 
+    def bgzf_members(self, data):
+        """member table of a BGZF byte string (host header walk, no inflation): (cmp_off, ucmp_off), n+1 entries each.
+        Raises FxgError(FXG_EFORMAT) for plain gzip."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        nm, tot = C.c_int64(0), C.c_int64(0)
+        check(lib().fxg_bgzf_members_host(a.ctypes.data, a.size, None, None, 0, C.byref(nm), C.byref(tot)))
+        co = np.zeros(nm.value + 1, dtype=np.int64)
+        uo = np.zeros(nm.value + 1, dtype=np.int64)
+        check(lib().fxg_bgzf_members_host(a.ctypes.data, a.size, co.ctypes.data, uo.ctypes.data, nm.value + 1,
+                                          C.byref(nm), C.byref(tot)))
+        return co, uo
+
     def gather_ranges(self, dfile, offsets, lengths):
         """raw byte ranges of the resident file (e.g. record names) -> (packed uint8, offsets[n+1])"""
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -176,17 +188,15 @@ class Engine:
             return rows, st, self.upload_rows(rows)
         return rows, st
 
-    def fastq_scan_dev(self, dfile, base_offset=0, first_line=0):
+    def fastq_scan_dev(self, dfile, base_offset=0):
         st = ScanStats()
         d_rows = C.c_void_p()
-        check(lib().fxg_fastq_scan(self.ctx, dfile.handle, base_offset, first_line, C.byref(d_rows), C.byref(st)))
+        check(lib().fxg_fastq_scan(self.ctx, dfile.handle, base_offset, C.byref(d_rows), C.byref(st)))
         return d_rows.value, _stats_dict(st)
 
-    def fastq_scan(self, dfile, base_offset=0, first_line=0, keep_device_rows=False, include_partial=False):
-        d_rows, st = self.fastq_scan_dev(dfile, base_offset, first_line)
+    def fastq_scan(self, dfile, base_offset=0, keep_device_rows=False):
+        d_rows, st = self.fastq_scan_dev(dfile, base_offset)
         n = st["n_rows"]
-        if include_partial:
-            n = (first_line + st["n_lines"] + 3) // 4 - first_line // 4
         rows = np.zeros(n, dtype=FASTQ_ROW)
         if n:
             check(lib().fxg_rows_download(self.ctx, d_rows, n, FASTQ_ROW.itemsize, rows.ctypes.data))
@@ -194,11 +204,62 @@ class Engine:
             return rows, st, self.upload_rows(rows)
         return rows, st
 
-    def count_lines(self, dfile):
-        n = C.c_int64(0)
-        e = C.c_int(0)
-        check(lib().fxg_count_lines(self.ctx, dfile.handle, C.byref(n), C.byref(e)))
-        return n.value, bool(e.value)
+    # ---- multi-GPU index build: split-phase scan + the one small exchange --------
+    def scan_begin(self, dfile, mode, base_offset=0, full_name=False, d_info=None):
+        """phase A (mark + prefix); the shard's fxg_shard_info lands at device pointer d_info (optional)"""
+        check(lib().fxg_scan_begin(self.ctx, dfile.handle, mode, base_offset,
+                                   _cabi.SCAN_FULL_NAME if full_name else 0, d_info))
+
+    def scan_finish(self, d_all, nranks, rank, row_dtype):
+        """phase B + boundary-row merge + the single host sync -> (rows, stats, all shard infos)"""
+        st = ScanStats()
+        d_rows = C.c_void_p()
+        infos = np.zeros(nranks, dtype=_cabi.SHARD_INFO)
+        check(lib().fxg_scan_finish(self.ctx, d_all, nranks, rank, C.byref(d_rows), C.byref(st), infos.ctypes.data))
+        rows = np.zeros(st.n_rows, dtype=row_dtype)
+        if st.n_rows:
+            check(lib().fxg_rows_download(self.ctx, d_rows, st.n_rows, row_dtype.itemsize, rows.ctypes.data))
+        return rows, _stats_dict(st), infos
+
+    def scan_sharded_dev(self, comm, dfile, mode, base_offset=0, full_name=False):
+        """begin -> in-stream ncclAllGather -> finish on this rank; rows stay on the device.
+        -> (device pointer to this shard's rows, stats dict, infos of all ranks)"""
+        st = ScanStats()
+        d_rows = C.c_void_p()
+        nranks = lib().fxg_comm_nranks(comm) if comm else 1
+        infos = np.zeros(nranks, dtype=_cabi.SHARD_INFO)
+        check(lib().fxg_scan_sharded(self.ctx, comm, dfile.handle, mode, base_offset,
+                                     _cabi.SCAN_FULL_NAME if full_name else 0, C.byref(d_rows), C.byref(st),
+                                     infos.ctypes.data))
+        return d_rows.value, _stats_dict(st), infos
+
+    def scan_sharded(self, comm, dfile, mode, base_offset=0, full_name=False):
+        d_rows, st, infos = self.scan_sharded_dev(comm, dfile, mode, base_offset, full_name)
+        dt = FASTA_ROW if mode == 0 else FASTQ_ROW
+        rows = np.zeros(st["n_rows"], dtype=dt)
+        if st["n_rows"]:
+            check(lib().fxg_rows_download(self.ctx, d_rows, st["n_rows"], dt.itemsize, rows.ctypes.data))
+        return rows, st, infos
+
+    def split_point(self, dfile, start, want_header=False):
+        """first line start (or FASTA header line start) at or after `start` in a resident buffer"""
+        pos = C.c_int64(0)
+        check(lib().fxg_split_point_dev(self.ctx, dfile.handle, int(start), 1 if want_header else 0, C.byref(pos)))
+        return pos.value
+
+    def slice_file(self, dfile, begin, end):
+        h = C.c_void_p()
+        check(lib().fxg_file_slice(self.ctx, dfile.handle, int(begin), int(end), C.byref(h)))
+        return DeviceFile(self, h)
+
+    def stage_path_range(self, path, begin, end):
+        h = C.c_void_p()
+        check(lib().fxg_file_from_path_range(self.ctx, os.fsencode(path), int(begin), int(end), C.byref(h)))
+        return DeviceFile(self, h)
+
+    def dev_alloc(self, nbytes):
+        """small device scratch (gathered shard infos in tests / single-process emulation)"""
+        return self.upload_rows(np.zeros(max(int(nbytes), 1), dtype=np.uint8))
 
     def upload_rows(self, rows):
         rows = np.ascontiguousarray(rows)

@@ -1,24 +1,29 @@
-"""Multi-GPU sharding of the index build: host-side logic only.
+"""Multi-GPU sharding of the index build: the host-side logic.
 
-One process per GPU; the file is cut into contiguous byte ranges, every rank scans its own range
-with the single-GPU kernels (`base_offset` / `first_line` make the rows global) and ONE small
-all-gather of per-shard counts stitches the result -- no data-path collective.
+One process per GPU.  The file is cut into contiguous byte ranges at nominal offsets ``i * N / G``; every
+range is then moved forward to the next line start (FASTQ) or header-line start (FASTA) FOUND ON THE DATA
+(``fxg_split_point_path`` / ``fxg_split_point_dev``), so a shard always begins a line / a record.  Each rank
+stages its own range (its own PCIe link) and runs the split-phase scan of libfxg.so:
 
-  FASTA  ranges are aligned to header lines ('>' at a line start), so every record lives in exactly
-         one shard; the all-gathered row counts give the global ID base (IDs equal file order,
-         reference src/index.c:240) and the stat row (src/index.c:367-371).
-  FASTQ  ranges are aligned to line starts; records are defined by the GLOBAL line number
-         (reference src/fastq.c:93), so ranks first all-gather their line counts, then scan with
-         `first_line` and fill only the row fields whose lines they own; the (at most one) row that
-         straddles two shards is merged field by field.
+    fxg_scan_begin      mark + prefix over the shard -> {rows, lines, bytes, first three lines}
+    fxg_shard_exchange  ONE ncclAllGather of those 128-byte structs on the context's stream
+    fxg_scan_finish     global line phase (reference src/fastq.c:93) / ID base (src/index.c:240) from the
+                        gathered counts, rows kernel, boundary-row merge on the device
 
-The same functions serve torch.distributed with NCCL (GPU ranks) and gloo (CPU tests).
+No data-path collective: file bytes and rows never cross GPUs.  Rows are then handed to the single sqlite
+writer (rank 0) in rank order.  The functions below are pure host logic and run unchanged under gloo on CPU
+(tests/test_shard_gloo.py) and NCCL on GPUs.
 """
+import ctypes as C
+import os
+
 import numpy as np
 
-from ._cabi import FASTQ_ROW
+from . import _cabi
+from ._cabi import FASTA_ROW, FASTQ_ROW, SHARD_INFO
 
 
+# ---- split points ----------------------------------------------------------------------------------
 def _find(host, pat, start):
     """first index >= start of bytes `pat` in a bytes-like / mmap / memoryview, or -1"""
     if hasattr(host, "find"):
@@ -32,88 +37,164 @@ def _find(host, pat, start):
     return -1
 
 
-def fasta_split_points(host, world):
-    """world+1 byte offsets; shard r = [p[r], p[r+1]) starts at a header line (or is empty)."""
+def split_point_bytes(host, start, want_header):
+    """first offset >= start at which a line (want_header: a FASTA header line) starts; len(host) if none.
+    Same definition as fxg_split_point_dev / fxg_split_point_path."""
     n = len(host)
-    pts = [0]
-    for r in range(1, world):
-        nominal = max(pts[-1], n * r // world)
-        k = _find(host, b"\n>", max(nominal - 1, 0))
-        pts.append(n if k < 0 else k + 1)
-    pts.append(n)
-    return [max(pts[i], pts[i - 1]) if i else 0 for i in range(len(pts))]
+    if start >= n:
+        return n
+    if start <= 0:
+        if not want_header or (n > 0 and host[0:1] == b">"):
+            return 0
+        start = 1
+    k = _find(host, b"\n>" if want_header else b"\n", start - 1)
+    return n if k < 0 else min(n, k + 1)
 
 
-def line_split_points(host, world):
-    """world+1 byte offsets; every shard starts at the beginning of a line."""
-    n = len(host)
-    pts = [0]
-    for r in range(1, world):
-        nominal = max(pts[-1], n * r // world)
-        if nominal == 0:
-            pts.append(0)
-            continue
-        k = _find(host, b"\n", nominal - 1)
-        pts.append(n if k < 0 else min(n, k + 1))
-    pts.append(n)
+def nominal_points(nbytes, world):
+    return [nbytes * r // world for r in range(world)] + [nbytes]
+
+
+def split_points_bytes(host, world, want_header):
+    """world+1 offsets; shard r = [p[r], p[r+1]) starts at a line / header line (or is empty)."""
+    nom = nominal_points(len(host), world)
+    pts = [0] + [split_point_bytes(host, nom[r], want_header) for r in range(1, world)] + [len(host)]
+    for i in range(1, len(pts)):
+        pts[i] = max(pts[i], pts[i - 1])
     return pts
 
 
-def all_gather_counts(values, group=None):
-    """all-gather a short int64 vector over torch.distributed (NCCL or gloo); returns [world, len]."""
-    import torch
+def fasta_split_points(host, world):
+    return split_points_bytes(host, world, True)
+
+
+def line_split_points(host, world):
+    return split_points_bytes(host, world, False)
+
+
+def split_points_path(path, world, want_header):
+    """the same on a file on disk: every rank can compute all world+1 points with a few preads"""
+    size = os.path.getsize(path)
+    nom = nominal_points(size, world)
+    pts = [0]
+    L = _cabi.lib()
+    for r in range(1, world):
+        pos, fs = C.c_int64(0), C.c_int64(0)
+        _cabi.check(L.fxg_split_point_path(os.fsencode(path), nom[r], 1 if want_header else 0, C.byref(pos), C.byref(fs)))
+        pts.append(max(pos.value, pts[-1]))
+    pts.append(size)
+    return pts
+
+
+# ---- what follows from the gathered shard infos ------------------------------------------------------
+def fastq_layout(n_lines):
+    """n_lines[r] = lines of shard r -> per rank (first_line, first_read, n_owned) and the read count.
+    A read belongs to the shard holding its name line; only complete reads (fourth line seen, reference
+    src/fastq.c:132-146,159) are rows.  Same arithmetic as fastq_stitch_kernel."""
+    nl = np.asarray(n_lines, dtype=np.int64)
+    first = np.concatenate([[0], np.cumsum(nl)[:-1]])
+    total = int(nl.sum())
+    n_reads = total // 4
+    first_read = (first + 3) // 4
+    last_read = np.where(nl > 0, (first + nl - 1) // 4, first_read - 1)
+    last_read = np.minimum(last_read, n_reads - 1)
+    owned = np.maximum(last_read - first_read + 1, 0)
+    return first, first_read, owned, n_reads
+
+
+def fasta_layout(n_rows):
+    """n_rows[r] -> ID base per rank (IDs equal file order, reference src/index.c:240) and the total"""
+    nr = np.asarray(n_rows, dtype=np.int64)
+    return np.concatenate([[0], np.cumsum(nr)[:-1]]), int(nr.sum())
+
+
+# ---- communicator ---------------------------------------------------------------------------------------
+class Comm:
+    """fxg_comm of the torch.distributed world (or None for a single process): the NCCL unique id is created on
+    rank 0 by libfxg.so and broadcast through the process group that torchrun already set up."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.handle = None
+        self.rank, self.world = 0, 1
+        if not dist.is_initialized() or dist.get_world_size(group) == 1:
+            return
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        L = _cabi.lib()
+        buf = (C.c_uint8 * _cabi.COMM_ID_BYTES)()
+        if self.rank == 0:
+            _cabi.check(L.fxg_comm_unique_id(buf))
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        ident = bytes(t.cpu().tolist())
+        h = C.c_void_p()
+        _cabi.check(L.fxg_comm_create(engine.ctx, ident, self.world, self.rank, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if self.handle:
+            _cabi.lib().fxg_comm_destroy(self.handle)
+            self.handle = None
+
+
+def gather_objects(obj, group=None):
+    """all ranks' python objects on rank 0 (rows / names travel to the single sqlite writer)"""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return np.asarray([values], dtype=np.int64)
-    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    t = torch.tensor(list(values), dtype=torch.int64, device=dev)
-    out = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
-    dist.all_gather(out, t, group=group)
-    return np.stack([o.cpu().numpy() for o in out])
+        return [obj]
+    out = [None] * dist.get_world_size(group) if dist.get_rank(group) == 0 else None
+    dist.gather_object(obj, out, dst=0, group=group)
+    return out
 
 
-def fasta_global(counts):
-    """counts[r] = (n_rows, total_slen) per rank -> (id_base per rank, total rows, total slen)"""
-    counts = np.asarray(counts, dtype=np.int64)
-    base = np.concatenate([[0], np.cumsum(counts[:, 0])[:-1]])
-    return base, int(counts[:, 0].sum()), int(counts[:, 1].sum())
-
-
-def fastq_first_lines(line_counts):
-    """line_counts[r] = lines in shard r -> global line number of each shard's first line"""
-    lc = np.asarray(line_counts, dtype=np.int64)
-    return np.concatenate([[0], np.cumsum(lc)[:-1]])
-
-
-def fastq_merge(shards):
-    """shards: list of (first_line, n_lines, rows) in rank order, rows = FASTQ_ROW array indexed from
-    row first_line//4 (fields the shard does not own are ignored).  Returns the complete rows
-    (reads whose fourth line exists, reference src/fastq.c:132-146) and the read count."""
-    total_lines = sum(int(s[1]) for s in shards)
-    n_reads = total_lines // 4
-    out = np.zeros(n_reads, dtype=FASTQ_ROW)
-    for first_line, n_lines, rows in shards:
-        first_line, n_lines = int(first_line), int(n_lines)
-        if n_lines == 0:
-            continue
-        r0 = first_line // 4
-        r1 = min(n_reads, (first_line + n_lines + 3) // 4)
-        if r1 <= r0:
-            continue
-        idx = np.arange(r0, r1, dtype=np.int64)
-        local = rows[idx - r0]
-        lo, hi = first_line, first_line + n_lines
-
-        def owned(k):
-            line = 4 * idx + k
-            return (line >= lo) & (line < hi)
-
-        m = owned(0)
-        out["dlen"][idx[m]] = local["dlen"][m]
-        out["nlen"][idx[m]] = local["nlen"][m]
-        m = owned(1)
-        out["soff"][idx[m]] = local["soff"][m]
-        out["rlen"][idx[m]] = local["rlen"][m]
-        m = owned(3)
-        out["qoff"][idx[m]] = local["qoff"][m]
-    return out, n_reads
+# ---- the multi-GPU index build of one file on disk ------------------------------------------------------
+def build_index_sharded(path, fmt, engine=None, comm=None, index_file=None, full_name=False, group=None):
+    """Run by every rank (torchrun): stage this rank's byte range of `path`, split-phase scan with the one
+    small all-gather, rows + names to rank 0, which writes the `.fxi` (reference schema) when `index_file`
+    is given.  fmt: 'fasta' | 'fastq'.  Returns on every rank a dict with the rank's rows, the global
+    counts and (rank 0) the merged rows."""
+    from .engine import get_engine
+    from . import fxi
+    eng = engine or get_engine()
+    own_comm = comm is None
+    if own_comm:
+        comm = Comm(eng, group)
+    mode = 0 if fmt == "fasta" else 1
+    pts = split_points_path(path, comm.world, want_header=(mode == 0))
+    a, b = pts[comm.rank], pts[comm.rank + 1]
+    dfile = eng.stage_path_range(path, a, b)
+    try:
+        rows, st, infos = eng.scan_sharded(comm.handle, dfile, mode, base_offset=a, full_name=full_name)
+        if mode == 0:
+            noff = rows["boff"] - rows["elen"].astype(np.int64) - rows["dlen"] - a
+        else:
+            noff = rows["soff"] - rows["dlen"] - a
+        names, name_off = eng.gather_ranges(dfile, noff, rows["nlen"].astype(np.int64)) if len(rows) else (
+            np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    finally:
+        dfile.free()
+    parts = gather_objects((rows, names, name_off, st), group)
+    res = {"rows": rows, "stats": st, "infos": infos, "range": (a, b)}
+    if comm.rank == 0:
+        all_rows = np.concatenate([p[0] for p in parts])
+        total_len = sum(int(p[3]["total_len"]) for p in parts)
+        n_lines = int(infos["n_lines"].sum())
+        res.update(all_rows=all_rows, total_len=total_len, n_lines=n_lines,
+                   name_parts=[(p[1], p[2]) for p in parts])
+        if index_file is not None:
+            blob = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.uint8)
+            offs = [np.asarray(p[2][:-1], dtype=np.int64) for p in parts]
+            base, acc = [], 0
+            for p in parts:
+                base.append(acc)
+                acc += int(p[2][-1])
+            noffs = np.concatenate([o + bse for o, bse in zip(offs, base)] + [np.array([acc], dtype=np.int64)])
+            if mode == 0:
+                fxi.write_fasta_index_packed(index_file, all_rows, blob, noffs, total_len).close()
+            else:
+                fxi.write_fastq_index_packed(index_file, all_rows, blob, noffs, n_lines, total_len).close()
+    if own_comm:
+        comm.close()
+    return res

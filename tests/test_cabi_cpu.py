@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
     assert set(declared) == set(_cabi.SIGNATURES), set(declared) ^ set(_cabi.SIGNATURES)
-    assert lib.fxg_abi_version() == 1
+    assert lib.fxg_abi_version() == 2
 
 
 def test_row_struct_layouts_match_header():

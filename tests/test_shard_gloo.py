@@ -1,12 +1,16 @@
-"""N>1 host logic (pyfastx_b200/shard.py) on CPU: world_size-2 gloo processes, each scanning its own
-shard with the CPU oracle standing in for the GPU kernels, one all-gather of counts, merged result
-equal to the whole-file oracle."""
+"""N>1 host logic (pyfastx_b200/shard.py) on CPU: world_size-2 and -3 gloo process groups.  Every rank cuts the
+file at split points found on the data, scans its own byte range (a pure-Python stand-in plays the two device
+phases fxg_scan_begin / fxg_scan_finish; the GPU kernels themselves are covered by tests/test_gpu_parity.py and
+by the 2-GPU run of tools/check_sharded.py), ONE all-gather of the 128-byte shard infos, boundary-row merge from
+the gathered edge lines, rows to rank 0 -- and the merged result must equal the whole-file oracle."""
 import os
 import socket
 import sys
+import tempfile
 
 import numpy as np
 import pytest
+import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -23,105 +27,159 @@ def _free_port():
     return p
 
 
-def py_fastq_shard(data, base_offset, first_line):
-    """pure-Python stand-in for fxg_fastq_scan(base_offset, first_line) on a small shard"""
-    from pyfastx_b200._cabi import FASTQ_ROW
-    lines = data.split(b"\n")
-    if lines and lines[-1] == b"":
-        lines.pop()
-    n_lines = len(lines)
-    nrows = (first_line + n_lines + 3) // 4 - first_line // 4
-    rows = np.zeros(max(nrows, 1), dtype=FASTQ_ROW)
-    pos = 0
-    for i, ln in enumerate(lines):
-        g = first_line + i
-        r = g // 4 - first_line // 4
-        if g % 4 == 0:
-            l = len(ln) - 1
-            if l > 0 and ln.endswith(b"\r"):
-                l -= 1
-            name = ln[1:1 + max(l, 0)]
-            k = name.find(b" ")
-            rows[r]["dlen"] = len(ln)
-            rows[r]["nlen"] = len(name) if k < 0 else k
-        elif g % 4 == 1:
-            rows[r]["soff"] = base_offset + pos
-            rows[r]["rlen"] = len(ln) - (1 if ln.endswith(b"\r") else 0)
-        elif g % 4 == 3:
-            rows[r]["qoff"] = base_offset + pos
+def _lines(data):
+    """[(start, length without '\\n')] incl. an unterminated last line (kseq semantics)"""
+    out, pos = [], 0
+    for ln in data.split(b"\n"):
+        out.append((pos, len(ln)))
         pos += len(ln) + 1
-    return rows, n_lines
+    if out and data.endswith(b"\n"):
+        out.pop()
+    if not data:
+        out = []
+    return out
 
 
-def _worker(rank, world, port, fa, fq, q):
+def py_begin(data, base_offset, mode):
+    """stand-in for fxg_scan_begin: the shard's fxg_shard_info"""
+    from pyfastx_b200._cabi import SHARD_INFO
+    ls = _lines(data)
+    info = np.zeros(1, dtype=SHARD_INFO)[0]
+    info["n_lines"] = len(ls)
+    info["bytes"] = len(data)
+    info["base_offset"] = base_offset
+    info["n_rows"] = sum(1 for s, l in ls if data[s:s + 1] == b">") if mode == 0 else 0
+    info["edge_n"] = min(3, len(ls))
+    for j, (s, l) in enumerate(ls[:3]):
+        info["edge_off"][j] = base_offset + s
+        info["edge_len"][j] = l - (1 if l > 0 and data[s + l - 1:s + l] == b"\r" else 0)
+    return info
+
+
+def py_finish_fastq(data, base_offset, infos, rank):
+    """stand-in for fxg_scan_finish (FASTQ): rows of the reads whose name line lies in this shard"""
+    from pyfastx_b200 import shard
+    from pyfastx_b200._cabi import FASTQ_ROW
+    first, first_read, owned, n_reads = shard.fastq_layout(infos["n_lines"])
+    F, n = int(first[rank]), int(infos["n_lines"][rank])
+    ls = _lines(data)
+
+    def line(g):                       # (global offset, rlen-style length) of global line g
+        if F <= g < F + n:
+            s, l = ls[g - F]
+            return base_offset + s, l - (1 if l > 0 and data[s + l - 1:s + l] == b"\r" else 0)
+        for p in range(rank + 1, len(infos)):
+            Fp, np_ = int(first[p]), int(infos["n_lines"][p])
+            if Fp <= g < Fp + np_:
+                j = g - Fp
+                assert j < int(infos["edge_n"][p])
+                return int(infos["edge_off"][p][j]), int(infos["edge_len"][p][j])
+        raise AssertionError("line %d not found" % g)
+
+    rows = np.zeros(int(owned[rank]), dtype=FASTQ_ROW)
+    size = 0
+    for g in range(F, F + n):
+        if g % 4 == 1:
+            size += line(g)[1]
+    for i in range(len(rows)):
+        R = int(first_read[rank]) + i
+        s, l = ls[4 * R - F]
+        name = data[s + 1:s + l].rstrip(b"\r") if l > 0 else b""
+        if b"\x00" in name.split(b" ")[0]:
+            k = len(name)
+        else:
+            k = name.find(b" ")
+        rows[i]["dlen"] = l
+        rows[i]["nlen"] = len(name) if k < 0 else k
+        rows[i]["soff"], rows[i]["rlen"] = line(4 * R + 1)
+        rows[i]["qoff"] = line(4 * R + 3)[0]
+    return rows, size
+
+
+def _all_gather_infos(info):
+    from pyfastx_b200._cabi import SHARD_INFO
+    t = torch.from_numpy(np.frombuffer(info.tobytes(), dtype=np.uint8).copy())
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.frombuffer(b"".join(o.numpy().tobytes() for o in out), dtype=SHARD_INFO).copy()
+
+
+def _worker(rank, world, port, fa, fq, fq_path, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import fxo
     from pyfastx_b200 import shard
-    # ---- FASTA: header-aligned shards, all-gather of (rows, slen) ----------------------------------
+    # ---- FASTA: shards start at header lines found on the data ------------------------------------------
     pts = shard.fasta_split_points(fa, world)
     a, b = pts[rank], pts[rank + 1]
+    infos = _all_gather_infos(py_begin(fa[a:b], a, 0))
     if b > a:
         rows, total, _ = fxo.fasta_scan(fa[a:b])
         rows["boff"] += a
     else:
         rows, total = np.zeros(0, dtype=fxo.FASTA_ROW), 0
-    counts = shard.all_gather_counts([len(rows), total])
-    base, n_total, slen_total = shard.fasta_global(counts)
-    # ---- FASTQ: line-aligned shards, all-gather of line counts, scan with first_line ------------------
+    assert int(infos["n_rows"][rank]) == len(rows)
+    base, n_total = shard.fasta_layout(infos["n_rows"])
+    fa_parts = shard.gather_objects((rows, total))
+    # ---- FASTQ: shards start at line starts; global line phase from the gathered line counts -----------------
     lp = shard.line_split_points(fq, world)
+    assert lp == shard.split_points_path(fq_path, world, False)          # pread search == in-memory search
     la, lb = lp[rank], lp[rank + 1]
-    part = fq[la:lb]
-    nl = part.count(b"\n") + (1 if part and not part.endswith(b"\n") else 0)
-    first = shard.fastq_first_lines(shard.all_gather_counts([nl])[:, 0])
-    qrows, n_lines = py_fastq_shard(part, la, int(first[rank]))
-    assert n_lines == nl
-    q.put((rank, int(base[rank]), n_total, slen_total, rows, int(first[rank]), n_lines, qrows))
+    qinfos = _all_gather_infos(py_begin(fq[la:lb], la, 1))
+    qrows, qsize = py_finish_fastq(fq[la:lb], la, qinfos, rank)
+    fq_parts = shard.gather_objects((qrows, qsize))
+    if rank == 0:
+        q.put((n_total, [int(x) for x in base], fa_parts, fq_parts, int(qinfos["n_lines"].sum())))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("seed", [0, 1])
-def test_two_rank_gloo_shards_equal_whole_file(seed):
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_host_logic_gloo(world):
     import gen
     from oracle import fxo
-    from pyfastx_b200 import shard
-    fa = gen.random_fasta(40 + seed, n_records=120, crlf_prob=0.0)
-    fq = gen.random_fastq(50 + seed, n_reads=257, partial_tail=seed * 2)
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, fa, fq, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    exp_rows, exp_total, _ = fxo.fasta_scan(fa)
-    assert got[0][2] == len(exp_rows) and got[0][3] == exp_total
-    merged = np.concatenate([g[4] for g in got])
-    assert [g[1] for g in got] == [0, len(got[0][4])]
+    fa = gen.random_fasta(77, n_records=120, crlf_prob=0.0)
+    fq = gen.random_fastq(78, n_reads=301, partial_tail=1)
+    with tempfile.NamedTemporaryFile(suffix=".fq", delete=False) as tf:
+        tf.write(fq)
+        fq_path = tf.name
+    try:
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, fa, fq, fq_path, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        n_total, base, fa_parts, fq_parts, n_lines = q.get(timeout=120)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        os.unlink(fq_path)
+    exp, exp_total, _ = fxo.fasta_scan(fa)
+    got = np.concatenate([p[0] for p in fa_parts])
+    assert n_total == len(exp) and sum(p[1] for p in fa_parts) == exp_total
+    assert base == np.concatenate([[0], np.cumsum([len(p[0]) for p in fa_parts])[:-1]]).tolist()
     for f in ("boff", "blen", "slen", "llen", "dlen", "nlen", "elen", "norm"):
-        assert np.array_equal(merged[f], exp_rows[f]), f
-    qexp, size, nlines = fxo.fastq_scan(fq)
-    qrows, n_reads = shard.fastq_merge([(g[5], g[6], g[7]) for g in got])
-    assert n_reads == len(qexp) == nlines // 4
+        assert np.array_equal(got[f], exp[f]), f
+    qexp, qsize, qlines = fxo.fastq_scan(fq)
+    qgot = np.concatenate([p[0] for p in fq_parts])
+    assert n_lines == qlines and sum(p[1] for p in fq_parts) == qsize and len(qgot) == len(qexp)
     for f in ("soff", "qoff", "rlen", "dlen", "nlen"):
-        assert np.array_equal(qrows[f], qexp[f]), f
+        assert np.array_equal(qgot[f], qexp[f]), f
 
 
-def test_split_points_properties():
-    import gen
+def test_split_points_are_on_the_data():
     from pyfastx_b200 import shard
-    fa = gen.random_fasta(7, n_records=50)
-    for world in (1, 2, 3, 8, 64):
+    fa = b">a\nACGT\nAC\n>b x\nGG\n>c\nTTTT\nTT\n"
+    for world in (1, 2, 3, 5, 9):
         pts = shard.fasta_split_points(fa, world)
         assert pts[0] == 0 and pts[-1] == len(fa) and pts == sorted(pts)
         for p in pts[1:-1]:
             assert p == len(fa) or (fa[p:p + 1] == b">" and fa[p - 1:p] == b"\n")
         lp = shard.line_split_points(fa, world)
-        assert lp[0] == 0 and lp[-1] == len(fa) and lp == sorted(lp)
         for p in lp[1:-1]:
-            assert p in (0, len(fa)) or fa[p - 1:p] == b"\n"
+            assert p == len(fa) or fa[p - 1:p] == b"\n"
+    first, first_read, owned, n_reads = shard.fastq_layout([5, 1, 0, 2, 9])
+    assert first.tolist() == [0, 5, 6, 6, 8] and n_reads == 4
+    assert first_read.tolist() == [0, 2, 2, 2, 2] and owned.tolist() == [2, 0, 0, 0, 2]
