@@ -316,6 +316,21 @@ int fxg_fxi_write_fastq(const char *path, const fxg_fastq_row *rows, int64_t n_r
                         const int64_t *name_off, int64_t n_lines, int64_t total_size, const fxg_gzindex *gz,
                         const fxg_fastq_meta *meta);
 
+/* ---- full-index statistics on the resident file ---------------------------------
+ * fxg_fasta_composition  per-record 128-bin byte composition, the counting loop of pyfastx_fasta_calc_composition
+ *     (src/fasta.c:851-961): every byte of a record's lines except '\n' (a '\r' lands in bin 13; bytes >= 128,
+ *     which index the reference's 128-entry array out of bounds, are dropped).  *out = malloc'ed array of
+ *     (seqid, letter, count) rows, count > 0, in (seqid, letter) order, seqid = row index + 1 (free it with
+ *     fxg_free_host); total[128] = whole-file counts (the reference's 128 rows with seqid 0).
+ * fxg_fastq_stats  A/C/G/T/N totals, min / max read length, min / max quality, phred guess of
+ *     pyfastx_fastq_calc_composition (src/fastq.c:663-795).  trailing_seq != 0: d_rows[n_rows] exists and carries
+ *     the sequence line of a trailing partial record, whose bases the reference counts as well. */
+int  fxg_fasta_composition(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                           int64_t base_offset, fxg_comp_row **out, int64_t *n_out, int64_t *total /* 128 */);
+int  fxg_fastq_stats(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows,
+                     int64_t base_offset, int trailing_seq, fxg_fastq_meta *out);
+void fxg_free_host(void *p);
+
 /* ---- batched name -> row resolution (host side) --------------------------------
  * Replaces one sqlite probe per query (pyfastx_index_get_seq_by_name, src/index.c:527-566;
  * pyfastx_fastq_get_read_by_name, src/fastq.c:487-519) by a hash table over the packed names

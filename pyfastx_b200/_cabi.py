@@ -124,6 +124,9 @@ SIGNATURES = {
     "fxg_file_from_bgzf_host": (i32, [vp, vp, i64, P(vp), P(i64)]),
     "fxg_fxi_write_fasta": (i32, [C.c_char_p, vp, i64, vp, vp, i64, vp, vp, i64]),
     "fxg_fxi_write_fastq": (i32, [C.c_char_p, vp, i64, vp, vp, i64, i64, vp, vp]),
+    "fxg_fasta_composition": (i32, [vp, vp, vp, i64, i64, P(vp), P(i64), vp]),
+    "fxg_fastq_stats": (i32, [vp, vp, vp, i64, i64, i32, P(FastqMeta)]),
+    "fxg_free_host": (None, [vp]),
     "fxg_nametab_build": (i32, [vp, vp, i64, P(vp)]),
     "fxg_nametab_find": (i64, [vp, C.c_char_p, i64]),
     "fxg_nametab_lookup": (i32, [vp, vp, vp, i64, vp]),

@@ -159,7 +159,7 @@ class Fasta:
         if build_index:
             self.build_index()
             if full_index:
-                _ = self.composition
+                self._calc_composition()
 
     # ---- index ---------------------------------------------------------------------------------
     def build_index(self):
@@ -382,54 +382,69 @@ class Fasta:
         k = min(k, len(lens) - 1)
         return int(lens[k]), k + 1
 
-    def _whole_file_hist(self):
-        if self._comp_cache is None:
-            self._need_index()
-            eng = self._st.engine
-            n = len(self._rows)
-            hist = np.zeros(256, dtype=np.int64)
-            step = 65536
-            for a in range(0, n, step):
-                rid = np.arange(a, min(n, a + step), dtype=np.int64)
-                h = np.zeros((rid.size, 256), dtype=np.int64)
-                fl = np.full(rid.size, self._flags(), dtype=np.int32)
-                zs = np.zeros(rid.size, dtype=np.int64)
-                es = np.ascontiguousarray(self._rows["slen"][rid], dtype=np.int64)
-                _cabi.check(_cabi.lib().fxg_composition_host(
-                    eng.ctx, self._st.dfile.handle, self._drows.devptr, n, rid.ctypes.data,
-                    zs.ctypes.data, es.ctypes.data, fl.ctypes.data, rid.size, h.ctypes.data))
-                hist += h.sum(axis=0)
-            self._comp_cache = hist
-        return self._comp_cache
+    def _calc_composition(self):
+        """pyfastx_fasta_calc_composition (src/fasta.c:851-961): per-record byte composition -> `comp` rows, computed
+        once on the GPU (fxg_fasta_composition) and persisted in the .fxi like the reference does on first use."""
+        if self._comp_cache is not None:
+            return self._comp_cache
+        self._need_index()
+        comp = None
+        if self._con is not None:
+            try:
+                comp = fxi.load_comp(self._con)
+            except Exception:
+                comp = None
+        if comp is None or len(comp) == 0:
+            rows, total = self._st.engine.fasta_composition(self._st.dfile, self._drows)
+            tot_rows = np.zeros(128, dtype=_cabi.COMP_ROW)           # the reference's 128 rows with seqid 0
+            tot_rows["abc"] = np.arange(128)
+            tot_rows["num"] = total
+            comp = np.concatenate([rows, tot_rows])
+            if self.index_file != ":memory:":
+                if self._con is not None:
+                    self._con.close()
+                self._con = fxi.write_fasta_index_packed(self.index_file, self._rows, self._names.blob, self._names.off,
+                                                         self._total, gz=self._st.gzindex, comp=comp)
+        self._comp_rows = comp
+        tot = np.zeros(128, dtype=np.int64)
+        z = comp[comp["seqid"] == 0]
+        tot[z["abc"]] = z["num"]
+        self._comp_cache = tot
+        return tot
 
     @property
     def composition(self):
-        h = self._whole_file_hist()
-        return {chr(i): int(h[i]) for i in range(32, 127) if h[i] > 0}
+        h = self._calc_composition()
+        return {chr(i): int(h[i]) for i in range(32, 127) if h[i] > 0}       # src/fasta.c:1092
 
     @property
     def gc_content(self):
-        h = self._whole_file_hist()
+        h = self._calc_composition()
         a, c, g, t = (int(h[ord(x)] + h[ord(x.lower())]) for x in "ACGT")
+        if a + c + g + t <= 0:
+            raise RuntimeError("could not calculate gc content")
         return float(np.float32(g + c) / np.float32(a + c + g + t) * np.float32(100))
 
     @property
     def gc_skew(self):
-        h = self._whole_file_hist()
+        h = self._calc_composition()
         c, g = (int(h[ord(x)] + h[ord(x.lower())]) for x in "CG")
+        if c + g <= 0:
+            raise RuntimeError("could not calculate gc skew")
         return float(np.float32(g - c) / np.float32(g + c))
 
     @property
     def type(self):
-        """DNA / RNA / protein guess from the composition (reference src/fasta.c:1080-1154)."""
-        comp = {k.upper() for k in self.composition}
-        if comp <= set("ACGTN"):
+        """DNA / RNA / protein / unknown from the alphabet in use (reference src/fasta.c:1104-1154)"""
+        h = self._calc_composition()
+        alpha = {chr(i) for i in range(33, 127) if h[i] > 0}
+        if alpha <= set("ACGTNacgtn") or alpha <= set("abcdghkmnrstvwyABCDGHKMNRSTVWY*-"):
             return "DNA"
-        if comp <= set("ACGUN"):
+        if alpha <= set("ACGUNacgun") or alpha <= set("abcdghkmnrsuvwyABCDGHKMNRSUVWY*-"):
             return "RNA"
-        if comp <= set("ACGTUNRYKMSWBDHV"):
-            return "DNA" if "U" not in comp else "RNA"
-        return "protein"
+        if alpha <= set("acdefghiklmnpqrstvwyACDEFGHIKLMNPQRSTVWY*-"):
+            return "protein"
+        return "unknown"
 
 
 class Sequence:
@@ -573,8 +588,12 @@ class Fastq:
         self.index_file = os.fspath(index_file) if index_file else file_name + ".fxi"
         self._phred = phred
         self._rows = None
+        self._meta = None
+        self._full_index = bool(full_index)
         if build_index:
             self.build_index()
+            if full_index:
+                self._calc_composition()
 
     def build_index(self):
         if self._rows is not None:
@@ -582,10 +601,12 @@ class Fastq:
         if os.path.exists(self.index_file):
             self._con, self._rows, self._names, stat = fxi.load_fastq_index(self.index_file)
             self._counts, self.size, self.avglen = int(stat[0]), int(stat[1]), stat[2]
+            self._n_lines = None                     # a loaded index does not say whether a partial record trails
             self._validate_loaded_rows()
         else:
             eng = self._st.engine
-            rows, st = eng.fastq_scan(self._st.dfile)
+            rows, st, self._tail_row = eng.fastq_scan(self._st.dfile, with_tail=True)
+            self._n_lines = int(st["n_lines"])
             blob, off = self._st.ranges_packed(rows["soff"] - rows["dlen"], rows["nlen"].astype(np.int64))
             self._names = fxi.PackedNames(blob, off)
             self._rows = rows
@@ -652,9 +673,98 @@ class Fastq:
         return self._st.engine.reads(self._st.dfile, self._drows, ids, flags=flags, want_qual=want_qual,
                                      rlens=self._rows["rlen"][ids])
 
+    def _calc_composition(self):
+        """pyfastx_fastq_calc_composition (src/fastq.c:663-795): base totals, min / max length and quality, phred
+        guess -- one GPU pass over the sequence and quality lines; persisted in the `base` / `meta` tables."""
+        if self._meta is not None:
+            return self._meta
+        self.build_index()
+        meta = None
+        if self._con is not None:
+            try:
+                m = self._con.execute("SELECT maxlen,minlen,minqs,maxqs,phred FROM meta LIMIT 1").fetchone()
+                b = self._con.execute("SELECT a,c,g,t,n FROM base LIMIT 1").fetchone()
+                if m and b:
+                    meta = dict(zip(("maxlen", "minlen", "minqs", "maxqs", "phred", "a", "c", "g", "t", "n"), [int(x) for x in m + b]))
+            except Exception:
+                meta = None
+        if meta is None:
+            eng = self._st.engine
+            # a trailing partial record's sequence line is counted by the reference too (it walks lines, not reads)
+            trailing = (self._n_lines % 4) >= 2 if self._n_lines is not None else False
+            drows = self._drows
+            if trailing:
+                full = np.zeros(len(self._rows) + 1, dtype=_cabi.FASTQ_ROW)
+                full[:-1] = self._rows
+                full[-1] = self._tail_row
+                drows = eng.upload_rows(full)
+            meta = eng.fastq_stats(self._st.dfile, drows, len(self._rows), trailing_seq=trailing)
+            if self._con is not None and self._n_lines is not None:
+                self._con.close()
+                self._con = fxi.write_fastq_index_packed(self.index_file, self._rows, self._names.blob, self._names.off,
+                                                         self._n_lines, self.size, gz=self._st.gzindex, meta=meta)
+        self._meta = meta
+        return meta
+
     @property
     def phred(self):
-        return self._phred or 33
+        if self._phred:
+            return self._phred
+        return self._calc_composition()["phred"]
+
+    @property
+    def encoding_type(self):
+        """possible quality encodings from the min / max quality (reference src/fastq.c:797-878)"""
+        m = self._calc_composition()
+        lo, hi = m["minqs"], m["maxqs"]
+        if lo < 33 or hi > 126:
+            return ["Unknown"]
+        out = []
+        if hi <= 73:
+            out.append("Sanger Phred+33")
+        if hi <= 74:
+            out.append("Illumina 1.8+ Phred+33")
+        if lo >= 59 and hi <= 104:
+            out.append("Solexa Solexa+64")
+        if lo >= 64 and hi <= 104:
+            out.append("Illumina 1.3+ Phred+64")
+        if lo >= 66 and hi <= 104:
+            out.append("Illumina 1.5+ Phred+64")
+        out.append("PacBio HiFi Phred+33")
+        return out
+
+    @property
+    def gc_content(self):
+        m = self._calc_composition()
+        return float(np.float32(m["g"] + m["c"]) / np.float32(m["a"] + m["c"] + m["g"] + m["t"]) * np.float32(100))
+
+    @property
+    def composition(self):
+        m = self._calc_composition()
+        return {k.upper(): m[k] for k in ("a", "c", "g", "t", "n")}
+
+    @property
+    def maxlen(self):
+        """meta.maxlen if the statistics were computed, else MAX(rlen) of the index (src/fastq.c:947-978)"""
+        self.build_index()
+        if self._meta is not None:
+            return self._meta["maxlen"]
+        return int(self._rows["rlen"].max()) if len(self._rows) else 0
+
+    @property
+    def minlen(self):
+        self.build_index()
+        if self._meta is not None:
+            return self._meta["minlen"]
+        return int(self._rows["rlen"].min()) if len(self._rows) else 0
+
+    @property
+    def maxqual(self):
+        return self._calc_composition()["maxqs"]
+
+    @property
+    def minqual(self):
+        return self._calc_composition()["minqs"]
 
 
 class Read:
@@ -684,7 +794,8 @@ class Read:
 
     @property
     def quali(self):
-        p = self._fq.phred
+        fq = self._fq                    # src/read.c:251-278: the phred offset if one is known, else 33
+        p = fq._phred or (fq._meta["phred"] if fq._meta else 0) or 33
         return [c - p for c in self._fetch(qual=True).encode("latin-1")]
 
     @property

@@ -470,6 +470,74 @@ uint32_t build_small_table(Db &db, const std::vector<std::vector<Val>> &rows) {
     return build_table_interior(db, kids);
 }
 
+// ---- an index b-tree from entries that are already in key order -------------------------------------------
+// payload(i, out) = the record of the i-th entry (indexed columns + rowid).  The range is cut into contiguous
+// runs, one per thread; leaf pages carry no page numbers, so the runs are built independently.  Between two
+// leaves one entry moves up into the parent (an index interior cell IS an entry).
+template <class Payload>
+uint32_t build_index_from_sorted(Db &db, int64_t n, Payload payload) {
+    if (n == 0) {
+        PageRun run; std::vector<Patch> none;
+        uint8_t *pg = run.new_page();
+        pg[0] = 0x0A; put_be16(pg + 3, 0); put_be16(pg + 5, PAGE);
+        if (!db.place(run, none)) return 0;
+        return run.first_page;
+    }
+    unsigned T = worker_count(n);
+    while (T > 1 && n / T < 8) --T;                                // every run needs a few entries
+    struct RunOut { PageRun run; std::vector<Patch> patches; std::vector<uint32_t> leaves; std::vector<std::vector<uint8_t>> seps;
+                    std::vector<uint8_t> tail_sep; };
+    std::vector<RunOut> outs(T);
+    std::vector<std::thread> th;
+    for (unsigned r = 0; r < T; ++r)
+        th.emplace_back([&, r] {
+            RunOut &o = outs[r];
+            const int64_t a = n * r / T;
+            int64_t b = n * (r + 1) / T;
+            if (r + 1 < T) --b;                                    // the run's last entry separates it from the next run
+            LeafWriter w(&o.run, &o.patches, 0x0A);
+            std::vector<uint8_t> pl;
+            for (int64_t i = a; i < b; ++i) {
+                payload(i, pl);
+                uint8_t pre[10];
+                const int pn = put_varint(pre, pl.size());
+                if (w.add(pre, (uint32_t)pn, pl.data(), pl.size())) continue;
+                // leaf full: this entry becomes the separator -- unless it is the run's last one, which would leave no
+                // leaf to its right; then the closed leaf gives up its last entry instead and this one opens a new leaf
+                w.close();
+                if (i + 1 < b) { o.seps.push_back(pl); continue; }
+                uint8_t *pg = o.run.page(w.leaf_pages.back());
+                uint32_t nc = ((uint32_t)pg[3] << 8) | pg[4];
+                std::vector<uint8_t> prev;
+                payload(i - 1, prev);
+                o.seps.push_back(prev);
+                --nc;                                              // drop the last cell (its bytes stay as dead space)
+                put_be16(pg + 3, nc);
+                uint32_t cs = PAGE;
+                for (uint32_t c = 0; c < nc; ++c) { const uint32_t x = ((uint32_t)pg[8 + 2 * c] << 8) | pg[8 + 2 * c + 1]; if (x < cs) cs = x; }
+                put_be16(pg + 5, cs);
+                w.add(pre, (uint32_t)pn, pl.data(), pl.size());
+            }
+            w.close();
+            o.leaves = w.leaf_pages;
+            if (r + 1 < T) payload(b, o.tail_sep);
+        });
+    for (auto &x : th) x.join();
+    std::vector<uint32_t> kids;
+    std::vector<std::vector<uint8_t>> seps;
+    for (unsigned r = 0; r < T; ++r) {
+        RunOut &o = outs[r];
+        if (!db.place(o.run, o.patches)) return 0;
+        for (size_t k = 0; k < o.leaves.size(); ++k) {
+            kids.push_back(o.run.first_page + o.leaves[k]);
+            if (k < o.seps.size()) seps.push_back(o.seps[k]);
+        }
+        if (r + 1 < T) seps.push_back(o.tail_sep);
+        o.run.bytes.clear(); o.run.bytes.shrink_to_fit();
+    }
+    return build_index_interior(db, kids, seps);
+}
+
 // ---- UNIQUE index on the name column --------------------------------------------------------------------------
 struct SortKey { uint64_t k0, k1; uint32_t idx; };
 
@@ -585,14 +653,8 @@ uint32_t build_name_index(Db &db, const uint8_t *names, const int64_t *off, int6
         for (auto &x : th) x.join();
         if (dup) { *created = false; return 0; }
     }
-    // leaf runs: bucket b covers sorted[bstart[b], bstart[b+1]); its LAST entry (all buckets but the final
-    // non-empty one) becomes the separator towards the next run
-    struct RunOut { PageRun run; std::vector<Patch> patches; std::vector<uint32_t> leaves; std::vector<std::vector<uint8_t>> seps;
-                    std::vector<uint8_t> tail_sep; bool has_tail = false; };
-    std::vector<unsigned> live;
-    for (unsigned b = 0; b < T; ++b) if (bstart[b + 1] > bstart[b]) live.push_back(b);
-    std::vector<RunOut> outs(live.size());
-    auto entry_payload = [&](const SortKey &k, std::vector<uint8_t> &out) {
+    auto entry_payload = [&](int64_t i, std::vector<uint8_t> &out) {
+        const SortKey &k = sorted[(size_t)i];
         const int64_t l = off[k.idx + 1] - off[k.idx];
         uint8_t ib[8];
         int il;
@@ -600,83 +662,17 @@ uint32_t build_name_index(Db &db, const uint8_t *names, const int64_t *off, int6
         uint8_t h[24];
         int hl = put_varint(h, (uint64_t)l * 2 + 13);
         hl += put_varint(h + hl, (uint64_t)it);
-        const int hs = hl + 1;                   // header size varint is 1 byte (header < 127)
-        out.resize((size_t)(1 + hl + l + il));
-        out[0] = (uint8_t)hs;
-        memcpy(out.data() + 1, h, (size_t)hl);
-        memcpy(out.data() + 1 + hl, names + off[k.idx], (size_t)l);
-        memcpy(out.data() + 1 + hl + l, ib, (size_t)il);
+        uint8_t hv[4];
+        const int hvn = put_varint(hv, (uint64_t)(hl + 1 <= 127 ? hl + 1 : hl + 2));
+        out.resize((size_t)(hvn + hl + l + il));
+        memcpy(out.data(), hv, (size_t)hvn);
+        memcpy(out.data() + hvn, h, (size_t)hl);
+        memcpy(out.data() + hvn + hl, names + off[k.idx], (size_t)l);
+        memcpy(out.data() + hvn + hl + l, ib, (size_t)il);
     };
-    {
-        std::vector<std::thread> th;
-        for (size_t r = 0; r < live.size(); ++r)
-            th.emplace_back([&, r] {
-                RunOut &o = outs[r];
-                const int64_t a = bstart[live[r]];
-                int64_t b = bstart[live[r] + 1];
-                const bool last_run = r + 1 == live.size();
-                if (!last_run && b - a >= 2) { --b; o.has_tail = true; }       // reserve the separator towards the next run
-                LeafWriter w(&o.run, &o.patches, 0x0A);
-                std::vector<uint8_t> pl;
-                for (int64_t i = a; i < b; ++i) {
-                    entry_payload(sorted[(size_t)i], pl);
-                    uint8_t pre[10];
-                    const int pn = put_varint(pre, pl.size());
-                    if (!w.add(pre, (uint32_t)pn, pl.data(), pl.size())) {
-                        // leaf full: this entry becomes the separator -- unless it is the last one of the run,
-                        // which would leave no leaf to its right; then it opens a new leaf and the previous
-                        // entry is pulled up instead (handled by keeping it simple: new leaf, separator = entry
-                        // only if more entries follow)
-                        w.close();
-                        if (i + 1 < b) { o.seps.push_back(pl); }
-                        else {
-                            // pull the last cell of the closed leaf up as the separator
-                            uint8_t *pg = o.run.page(w.leaf_pages.back());
-                            uint32_t nc = ((uint32_t)pg[3] << 8) | pg[4];
-                            const uint32_t co = ((uint32_t)pg[8 + 2 * (nc - 1)] << 8) | pg[8 + 2 * (nc - 1) + 1];
-                            // decode that cell: varint len + payload (local only; entries with overflow are rare:
-                            // re-encode from the sorted array instead)
-                            std::vector<uint8_t> prev;
-                            entry_payload(sorted[(size_t)i - 1], prev);
-                            o.seps.push_back(prev);
-                            (void)co;
-                            --nc;
-                            put_be16(pg + 3, nc);
-                            uint32_t cs = PAGE;
-                            for (uint32_t c = 0; c < nc; ++c) { const uint32_t x = ((uint32_t)pg[8 + 2 * c] << 8) | pg[8 + 2 * c + 1]; if (x < cs) cs = x; }
-                            put_be16(pg + 5, nc ? cs : PAGE);
-                            w.add(pre, (uint32_t)pn, pl.data(), pl.size());
-                        }
-                    }
-                }
-                w.close();
-                o.leaves = w.leaf_pages;
-                if (o.has_tail) entry_payload(sorted[(size_t)b], o.tail_sep);
-            });
-        for (auto &x : th) x.join();
-    }
+    const uint32_t root = build_index_from_sorted(db, n, entry_payload);
     tm.lap("  index: leaves");
-    std::vector<uint32_t> kids;
-    std::vector<std::vector<uint8_t>> seps;
-    for (size_t r = 0; r < outs.size(); ++r) {
-        RunOut &o = outs[r];
-        if (!db.place(o.run, o.patches)) return 0;
-        for (size_t k = 0; k < o.leaves.size(); ++k) {
-            kids.push_back(o.run.first_page + o.leaves[k]);
-            if (k < o.seps.size()) seps.push_back(o.seps[k]);
-        }
-        if (r + 1 < outs.size()) {
-            if (o.has_tail) seps.push_back(o.tail_sep);
-            else {
-                // a one-entry bucket that is not the last: its single entry sits in its leaf; borrow the first
-                // entry of the next run as separator is not possible any more -- fall back to one thread
-                db.err = "internal: degenerate sample-sort bucket";
-                return 0;
-            }
-        }
-        o.run.bytes.clear(); o.run.bytes.shrink_to_fit();
-    }
-    return build_index_interior(db, kids, seps);
+    return root;
 }
 
 // ---- schema page + header ----------------------------------------------------------------------------------
@@ -782,7 +778,7 @@ extern "C" int fxg_fxi_write_fasta(const char *path, const fxg_fasta_row *rows, 
     const uint32_t seq_root = build_big_table(db, n_rows, enc);
     tm.lap("seq table");
     bool ok = seq_root != 0;
-    uint32_t stat_root = 0, comp_root = 0, gz_root = 0, idx_root = 0;
+    uint32_t stat_root = 0, comp_root = 0, gz_root = 0, idx_root = 0, seqidx_root = 0;
     bool idx_created = false;
     if (ok) {
         std::vector<std::vector<Val>> stat = {{Val::integer(n_rows), Val::integer(total_slen), Val::null(), Val::null(), Val::null(), Val::null()}};
@@ -804,6 +800,28 @@ extern "C" int fxg_fxi_write_fasta(const char *path, const fxg_fasta_row *rows, 
         };
         comp_root = build_big_table(db, n_comp, cenc);
         ok = comp_root != 0;
+        if (ok && n_comp > 0) {
+            // CREATE INDEX seqidx ON comp (seqid)  (src/fasta.c:953).  Entries ordered by (seqid, rowid): rows come in
+            // seqid order except the whole-file rows (seqid 0), which the reference appends LAST -- they sort first.
+            int64_t nz = 0;
+            while (nz < n_comp && comp[n_comp - 1 - nz].seqid == 0) ++nz;
+            bool sorted_ok = true;
+            for (int64_t i = 1; i < n_comp - nz && sorted_ok; ++i) sorted_ok = comp[i - 1].seqid <= comp[i].seqid && comp[i].seqid != 0;
+            if (sorted_ok) {
+                auto pay = [&](int64_t i, std::vector<uint8_t> &out) {
+                    const int64_t row = i < nz ? n_comp - nz + i : i - nz;          // 0-based row of the i-th entry
+                    uint8_t b1[8], b2[8];
+                    int l1, l2;
+                    const int t1 = int_serial(comp[row].seqid, b1, &l1), t2 = int_serial(row + 1, b2, &l2);
+                    out.resize((size_t)(3 + l1 + l2));
+                    out[0] = 3; out[1] = (uint8_t)t1; out[2] = (uint8_t)t2;
+                    memcpy(out.data() + 3, b1, (size_t)l1);
+                    memcpy(out.data() + 3 + l1, b2, (size_t)l2);
+                };
+                seqidx_root = build_index_from_sorted(db, n_comp, pay);
+                ok = seqidx_root != 0;
+            }
+        }
     }
     if (ok) {
         std::vector<std::vector<Val>> grows;
@@ -828,6 +846,7 @@ extern "C" int fxg_fxi_write_fasta(const char *path, const fxg_fasta_row *rows, 
             {"table", "gzindex", "gzindex", gz_root, "CREATE TABLE gzindex ( \n\t\t\tID INTEGER PRIMARY KEY, \n \t\t\tcontent BLOB \n \t\t)"},
         };
         if (idx_created) schema.push_back({"index", "chromidx", "seq", idx_root, "CREATE UNIQUE INDEX chromidx ON seq (chrom)"});
+        if (seqidx_root) schema.push_back({"index", "seqidx", "comp", seqidx_root, "CREATE INDEX seqidx ON comp (seqid)"});
         ok = write_page1(db, schema);
     }
     ::close(db.fd);

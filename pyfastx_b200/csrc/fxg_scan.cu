@@ -799,19 +799,39 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
         // ---- flatten the window ----
         uint16_t *flat = s_flat[warp];
         uint8_t *cutf = s_cut[warp];
+        // Entries of all window regions are requested BEFORE any of them is used: two entries per lane and load
+        // (64 per region cover every region of a typical short-read file in one load), RWIN loads in flight together
+        // instead of RWIN dependent round trips.  Entries past a region's count are stale and never used.
+        uint32_t E2[RWIN];
+#pragma unroll
+        for (int i = 0; i < RWIN; ++i) {
+            E2[i] = 0u;
+            if (r0 + i < P.nreg) E2[i] = reinterpret_cast<const uint32_t *>(P.seg + (r0 + i) * SEGCAP)[lane];
+        }
         int W = 0, Ls = 0;                                           // entries in the window / in the span
-#pragma unroll 1
+        bool closed = false;                                         // a dense look-ahead region ends the window
+#pragma unroll
         for (int i = 0; i < RWIN; ++i) {
             const int nl = (int)__shfl_sync(0xffffffffu, nll, i + 1);
-            if (nl > SEGCAP) break;                                  // dense look-ahead region: the window ends here
-            const uint16_t *sg = P.seg + (r0 + i) * SEGCAP;
-            const uint8_t *cg = P.cut + (r0 + i) * SEGCAP;
-            for (int k = lane; k < nl; k += 32) {
-                const uint32_t e = sg[k];
-                flat[W + k] = (uint16_t)((i * REGION + (int)(e & E_POS)) | ((e & E_CR) ? 0x8000u : 0u));
-                if (FXG_MARK_CUT) cutf[W + k] = cg[k];
+            if (nl > SEGCAP) closed = true;
+            if (!closed) {
+                const int k = 2 * lane;
+                const uint32_t e0 = E2[i] & 0xffffu, e1 = E2[i] >> 16;
+                if (k < nl) flat[W + k] = (uint16_t)((i * REGION + (int)(e0 & E_POS)) | ((e0 & E_CR) ? 0x8000u : 0u));
+                if (k + 1 < nl) flat[W + k + 1] = (uint16_t)((i * REGION + (int)(e1 & E_POS)) | ((e1 & E_CR) ? 0x8000u : 0u));
+                if (nl > 64) {                                       // lines shorter than 32 bytes on average
+                    const uint16_t *sg = P.seg + (r0 + i) * SEGCAP;
+                    for (int kk = 64 + lane; kk < nl; kk += 32) {
+                        const uint32_t e = sg[kk];
+                        flat[W + kk] = (uint16_t)((i * REGION + (int)(e & E_POS)) | ((e & E_CR) ? 0x8000u : 0u));
+                    }
+                }
+                if (FXG_MARK_CUT) {
+                    const uint8_t *cg = P.cut + (r0 + i) * SEGCAP;
+                    for (int kk = lane; kk < nl; kk += 32) cutf[W + kk] = cg[kk];
+                }
+                W += nl;
             }
-            W += nl;
             if (i == RG - 1) Ls = W;
         }
         __syncwarp();
@@ -852,16 +872,18 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
         // ---- (b) reads that start inside the span: one lane each ----
         for (int fb = lead; fb < Ls; fb += 128) {
             const int f = fb + 4 * lane;
-            if (f < Ls) {
-                const int64_t row = ((g0 + f) >> 2) - row0;
-                const bool have1 = f + 1 < W, have3 = f + 3 < W;
+            int64_t row = 0, soff = 0, rlen = 0, qoff = 0, len = 0, k = 0;
+            bool have1 = false, have3 = false;
+            const bool mine = f < Ls;
+            if (mine) {
+                row = ((g0 + f) >> 2) - row0;
+                have1 = f + 1 < W; have3 = f + 3 < W;
                 const int64_t pm1 = POS(f - 1), p0 = POS(f);
-                const int64_t len = p0 - pm1 - 1;                    // name line incl. '@' and '\r'
+                len = p0 - pm1 - 1;                                  // name line incl. '@' and '\r'
                 int64_t l = len - 1;
                 if (l > 0 && CR(f)) --l;
                 if (l < 0) l = 0;
                 const int64_t s = pm1 + 1;
-                int64_t k = 0;
                 const uint32_t cv = !FXG_MARK_CUT ? 255u : (f >= 1 ? (uint32_t)cutf[f - 1] : carry_cut);   // found by mark while the bytes were on chip
                 if (cv < 254u) k = (int64_t)cv < l ? (int64_t)cv : l;
                 else if (cv == 254u) k = l;
@@ -876,7 +898,6 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
                         if (ch == ' ') break;
                     }
                 }
-                int64_t soff = 0, rlen = 0, qoff = 0;
                 if (have1) {
                     const int64_t p1 = POS(f + 1);
                     const int64_t len1 = p1 - p0 - 1;
@@ -885,18 +906,32 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
                     if (f + 1 < Ls) my_size += (unsigned long long)rlen;
                 }
                 if (have3) qoff = P.base_offset + POS(f + 2) + 1;
-                if (row < P.qrows_cap) {
-                    fxg_fastq_row *q = &P.qrows[row];
-                    if (have3) {
-                        longlong2 a, b;
-                        a.x = soff; a.y = qoff;
-                        b.x = rlen; b.y = (long long)(((unsigned long long)(uint32_t)(int)k << 32) | (uint32_t)(int)len);
-                        reinterpret_cast<longlong2 *>(q)[0] = a;
-                        reinterpret_cast<longlong2 *>(q)[1] = b;
-                    } else {
-                        *reinterpret_cast<int2 *>(&q->dlen) = make_int2((int)len, (int)k);
-                        if (have1) { q->soff = soff; q->rlen = rlen; }
-                    }
+            }
+            // ---- row stores.  A lane holds one 32-byte row = one DRAM sector; written as two 16-byte halves by ONE
+            //      lane, every store instruction leaves half-filled sectors.  Neighbouring lanes swap halves instead, so
+            //      that each instruction writes whole sectors: lanes (2j, 2j+1) write row 2j, then row 2j+1. ----
+            const bool full = mine && have3 && row < P.qrows_cap;
+            const bool pair_full = full && __shfl_xor_sync(0xffffffffu, full ? 1 : 0, 1) != 0;
+            longlong2 a, b;
+            a.x = soff; a.y = qoff;
+            b.x = rlen; b.y = (long long)(((unsigned long long)(uint32_t)(int)k << 32) | (uint32_t)(int)len);
+            const bool odd = (lane & 1) != 0;
+            const longlong2 send = odd ? a : b;
+            longlong2 recv;
+            recv.x = shfl_i64(send.x, lane ^ 1);
+            recv.y = shfl_i64(send.y, lane ^ 1);
+            if (pair_full) {
+                fxg_fastq_row *q0 = &P.qrows[odd ? row - 1 : row];                 // row of the even lane
+                reinterpret_cast<longlong2 *>(q0)[odd ? 1 : 0] = odd ? recv : a;   // row 2j:   even lane's a, even lane's b
+                reinterpret_cast<longlong2 *>(q0 + 1)[odd ? 1 : 0] = odd ? b : recv;   // row 2j+1: odd lane's a, odd lane's b
+            } else if (mine && row < P.qrows_cap) {
+                fxg_fastq_row *q = &P.qrows[row];
+                if (have3) {
+                    reinterpret_cast<longlong2 *>(q)[0] = a;
+                    reinterpret_cast<longlong2 *>(q)[1] = b;
+                } else {
+                    *reinterpret_cast<int2 *>(&q->dlen) = make_int2((int)len, (int)k);
+                    if (have1) { q->soff = soff; q->rlen = rlen; }
                 }
             }
         }

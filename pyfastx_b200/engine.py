@@ -194,14 +194,20 @@ class Engine:
         check(lib().fxg_fastq_scan(self.ctx, dfile.handle, base_offset, C.byref(d_rows), C.byref(st)))
         return d_rows.value, _stats_dict(st)
 
-    def fastq_scan(self, dfile, base_offset=0, keep_device_rows=False):
+    def fastq_scan(self, dfile, base_offset=0, keep_device_rows=False, with_tail=False):
+        """rows of the complete reads; with_tail also returns the (partial) row of a trailing incomplete record"""
         d_rows, st = self.fastq_scan_dev(dfile, base_offset)
         n = st["n_rows"]
-        rows = np.zeros(n, dtype=FASTQ_ROW)
-        if n:
-            check(lib().fxg_rows_download(self.ctx, d_rows, n, FASTQ_ROW.itemsize, rows.ctypes.data))
+        has_tail = with_tail and st["n_lines"] % 4 != 0
+        rows = np.zeros(n + (1 if has_tail else 0), dtype=FASTQ_ROW)
+        if rows.size:
+            check(lib().fxg_rows_download(self.ctx, d_rows, rows.size, FASTQ_ROW.itemsize, rows.ctypes.data))
+        tail = rows[n].copy() if has_tail else np.zeros(1, dtype=FASTQ_ROW)[0]
+        rows = rows[:n]
         if keep_device_rows:
             return rows, st, self.upload_rows(rows)
+        if with_tail:
+            return rows, st, tail
         return rows, st
 
     # ---- multi-GPU index build: split-phase scan + the one small exchange (SURVEY 8e) --------
@@ -256,6 +262,27 @@ class Engine:
         h = C.c_void_p()
         check(lib().fxg_file_from_path_range(self.ctx, os.fsencode(path), int(begin), int(end), C.byref(h)))
         return DeviceFile(self, h)
+
+    # ---- full-index statistics (K7) ----------------------------------------------------------------
+    def fasta_composition(self, dfile, drows, base_offset=0):
+        """per-record composition of the resident file -> (COMP_ROW array in (seqid, letter) order, total[128])"""
+        out = C.c_void_p()
+        n = C.c_int64(0)
+        total = np.zeros(128, dtype=np.int64)
+        check(lib().fxg_fasta_composition(self.ctx, dfile.handle, drows.devptr, drows.n_rows, base_offset,
+                                          C.byref(out), C.byref(n), total.ctypes.data))
+        rows = np.zeros(n.value, dtype=_cabi.COMP_ROW)
+        if n.value:
+            C.memmove(rows.ctypes.data, out.value, n.value * _cabi.COMP_ROW.itemsize)
+        lib().fxg_free_host(out)
+        return rows, total
+
+    def fastq_stats(self, dfile, drows, n_rows, base_offset=0, trailing_seq=False):
+        """A/C/G/T/N totals, min/max read length and quality, phred guess (reference src/fastq.c:663-795)"""
+        m = _cabi.FastqMeta()
+        check(lib().fxg_fastq_stats(self.ctx, dfile.handle, drows.devptr, n_rows, base_offset, 1 if trailing_seq else 0,
+                                    C.byref(m)))
+        return {k: getattr(m, k) for k, _ in _cabi.FastqMeta._fields_}
 
     def dev_alloc(self, nbytes):
         """small device scratch (gathered shard infos in tests / single-process emulation)"""
