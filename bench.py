@@ -818,7 +818,8 @@ def all_cores_extract(spath, names, rid, qs, qe, minus, n_rec):
     chunks = np.array_split(sel, cores)
     tasks = [(spath, names, rid[ch], qs[ch], qe[ch], minus[ch]) for ch in chunks if ch.size]
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(len(tasks)) as pool:
+    # spawn, not fork: this process holds a CUDA context and pinned memory, which a forked child must not touch
+    with mp.get_context("spawn").Pool(len(tasks)) as pool:
         res = pool.map(_ref_worker, tasks, chunksize=1)
     wall = time.perf_counter() - t0
     bases = sum(r[0] for r in res)

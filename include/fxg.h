@@ -253,6 +253,13 @@ int fxg_extract_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_row
                      int64_t nq, int64_t *out_off_host, uint8_t *out_host, int64_t out_cap,
                      int64_t *acgt_host /* nq*4 or NULL */);
 
+/* ONE query through one kernel launch and one stream synchronisation -- what a per-object getter of the reference
+ * costs here (Sequence.seq / .reverse / .complement / .antisense, src/sequence.c:337-398): no plan kernels, no H2D
+ * copies (the query travels as kernel arguments), output written straight to mapped pinned memory.  Same bytes as
+ * fxg_extract_host with nq = 1. */
+int fxg_extract_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                         int64_t row_id, int64_t s, int64_t e, int32_t flags, uint8_t *out_host, int64_t out_cap);
+
 /* K4 (full form): per-query byte histogram of the extracted bytes -- the counting loop of
  * pyfastx_sequence_composition (src/sequence.c:727-747) and, summed over records, of the
  * full-index composition scan (src/fasta.c:901-927).  hist_host receives nq x 256 int64. */

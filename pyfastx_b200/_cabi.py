@@ -116,6 +116,7 @@ SIGNATURES = {
     "fxg_extract_plan_dev": (i32, [vp, vp, vp, i64, vp, P(i64)]),
     "fxg_extract_dev": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp]),
     "fxg_extract_host": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, i64, vp]),
+    "fxg_extract_one_host": (i32, [vp, vp, vp, i64, i64, i64, i64, i32, vp, i64]),
     "fxg_composition_host": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
     "fxg_reads_dev": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64, P(i64)]),
     "fxg_reads_host": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64]),

@@ -299,8 +299,7 @@ class Fasta:
         return [buf[off[i]:off[i + 1]].decode("latin-1") for i in range(rid.size)]
 
     def _one(self, i, s, e, extra=0):
-        out, _, _ = self._st.engine.extract(self._st.dfile, self._drows, [i], [s], [e], [self._flags(extra)])
-        return out.tobytes().decode("latin-1")
+        return self._st.engine.extract_one(self._st.dfile, self._drows, i, s, e, self._flags(extra)).decode("latin-1")
 
     # ---- reference methods -------------------------------------------------------------------------
     def fetch(self, chrom, intervals, strand="+"):

@@ -88,6 +88,7 @@ extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_one) cudaFreeHost(c->h_one);
     for (int i = 0; i < 2; ++i) {
         if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
         if (c->pinned_ev[i]) cudaEventDestroy(c->pinned_ev[i]);

@@ -66,6 +66,7 @@ struct fxg_ctx {
     // scan scratch
     FxgScratch   tile_desc, seg, cut, row_tmp, rows, counters, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small
+    void        *h_one = nullptr;        // pinned + mapped: output of single-query launches (fxg_extract_one_host)
     // measurement hooks
     bool         profiling = false;
     cudaEvent_t  prof_ev[FXG_PROF_SLOTS][2] = {};

@@ -429,6 +429,50 @@ constexpr int QPW = 32 / QG;          // queries per warp and step
 #endif
 constexpr int XU = FXG_XU;            // output words per lane and step
 
+// Complement of four bytes at once for the letters that make up almost all nucleotide data: A C G T N in either
+// case.  (b >> 1) & 7 is a perfect hash of these five letters (A 0, C 1, T 2, G 3, N 7), so ONE byte-permute
+// looks up all four complements in an 8-entry register table; a second permute with the table of the letters
+// themselves verifies that every byte really was one of the five -- any other byte (IUPAC codes, '*', '-', ...)
+// makes `ok` false and the caller uses the 256-entry shared-memory LUT for that word.  Case is preserved.
+__device__ __forceinline__ uint32_t comp4_acgtn(uint32_t w, bool &ok) {
+    const uint32_t h = (w >> 1) & 0x07070707u;
+    const uint32_t t = h | (h >> 4);
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);                    // nibbles h0 h1 h2 h3
+    const uint32_t up = __byte_perm(0x47544341u, 0x4E000000u, sel);      // the letter each hash stands for (upper case)
+    const uint32_t cm = __byte_perm(0x43414754u, 0x4E000000u, sel);      // its complement
+    ok = (w & 0xDFDFDFDFu) == up;
+    return cm | (w & 0x20202020u);
+}
+
+// upper-case / complement of 16 kept bytes (all in 0x40..0x7f, checked by the caller)
+__device__ __forceinline__ void xform16(uint32_t V[4], bool upper, bool comp, const uint8_t (*__restrict__ s_lut)[256]) {
+    if (comp) {
+        bool f0, f1, f2, f3;
+        uint32_t c0 = comp4_acgtn(V[0], f0), c1 = comp4_acgtn(V[1], f1), c2 = comp4_acgtn(V[2], f2), c3 = comp4_acgtn(V[3], f3);
+        if (f0 && f1 && f2 && f3) {
+            if (upper) { c0 &= 0xDFDFDFDFu; c1 &= 0xDFDFDFDFu; c2 &= 0xDFDFDFDFu; c3 &= 0xDFDFDFDFu; }
+            V[0] = c0; V[1] = c1; V[2] = c2; V[3] = c3;
+        } else {
+            const uint8_t *tbl = upper ? s_lut[2] : s_lut[0];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t x = V[i];
+                V[i] = (uint32_t)tbl[x & 0xff] | ((uint32_t)tbl[(x >> 8) & 0xff] << 8) |
+                       ((uint32_t)tbl[(x >> 16) & 0xff] << 16) | ((uint32_t)tbl[x >> 24] << 24);
+            }
+        }
+    } else if (upper) {
+        // bytes are in 0x40..0x7f here: 'a'..'z' = 0x61..0x7a lose bit 5
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = V[i];
+            const uint32_t ge = (x + 0x1f1f1f1fu) & 0x80808080u;            // byte >= 0x61
+            const uint32_t le = ~(x + 0x05050505u) & 0x80808080u;           // byte <= 0x7a
+            V[i] = x & ~((ge & le) >> 2);
+        }
+    }
+}
+
 // The 16 output bytes [j0, j0+16) of a query (0 <= j0 <= out_len-16) as four little-endian words, in two
 // steps so that the loads of several words can be in flight together.
 // fq = file + boff + s + elen*(s/bpl): source address of kept rank 0;  rem_s = s % bpl;  inv = 2^32 / bpl.
@@ -453,8 +497,8 @@ __device__ __forceinline__ void ow_load(const WordReq &q, uint32_t W[6]) {
     for (int i = 0; i < 6; ++i) W[i] = __ldg(q.wp + i);
 }
 // Returns false if the bytes contradict the uniform-line layout (the query is then redone by the general path).
-__device__ __forceinline__ bool ow_finish(const uint32_t W[6], const WordReq &q, int elen, bool rev, bool xform,
-                                          const uint8_t *__restrict__ tbl, uint32_t o[4]) {
+__device__ __forceinline__ bool ow_finish(const uint32_t W[6], const WordReq &q, int elen, bool rev, bool upper, bool comp,
+                                          const uint8_t (*__restrict__ s_lut)[256], uint32_t o[4]) {
     const int o1 = q.o1;
     const uint32_t c = q.c;
     uint32_t V[4];
@@ -476,17 +520,29 @@ __device__ __forceinline__ bool ow_finish(const uint32_t W[6], const WordReq &q,
             V[i] = (V[i] & ~m) | (e2 & m);
         }
     }
-    // conservative layout check: every kept byte must be >= 0x40 (letters); see pull_one
-    const uint32_t all = (V[0] | (V[0] >> 1)) & (V[1] | (V[1] >> 1)) & (V[2] | (V[2] >> 1)) & (V[3] | (V[3] >> 1));
-    ok = ok && (all & 0x40404040u) == 0x40404040u;
-    if (xform) {
+    // conservative layout check: every kept byte must lie in 0x40..0x7f (letters); see ow_finish_line
+    const uint32_t all = V[0] & V[1] & V[2] & V[3], hi = V[0] | V[1] | V[2] | V[3];
+    ok = ok && (all & 0x40404040u) == 0x40404040u && (hi & 0x80808080u) == 0u;
+    xform16(V, upper, comp, s_lut);
+    if (rev) {
+        o[0] = __byte_perm(V[3], 0, 0x0123); o[1] = __byte_perm(V[2], 0, 0x0123);
+        o[2] = __byte_perm(V[1], 0, 0x0123); o[3] = __byte_perm(V[0], 0, 0x0123);
+    } else { o[0] = V[0]; o[1] = V[1]; o[2] = V[2]; o[3] = V[3]; }
+    return ok;
+}
+
+// 16 output bytes that lie on ONE source line (no line break inside): five aligned words cover them.
+__device__ __forceinline__ bool ow_finish_line(const uint32_t W[5], int o1, bool rev, bool upper, bool comp,
+                                               const uint8_t (*__restrict__ s_lut)[256], uint32_t o[4]) {
+    uint32_t V[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t x = V[i];
-            V[i] = (uint32_t)tbl[x & 0xff] | ((uint32_t)tbl[(x >> 8) & 0xff] << 8) |
-                   ((uint32_t)tbl[(x >> 16) & 0xff] << 16) | ((uint32_t)tbl[x >> 24] << 24);
-        }
-    }
+    for (int i = 0; i < 4; ++i) V[i] = __funnelshift_r(W[i], W[i + 1], o1 * 8);
+    // conservative layout check: every kept byte must be a letter-range byte (>= 0x40, < 0x80); anything else --
+    // which includes the strippable 10 / 13 / 32 -- sends the query to the general strip path
+    const uint32_t hi = V[0] | V[1] | V[2] | V[3];
+    const uint32_t all = V[0] & V[1] & V[2] & V[3];
+    bool ok = (all & 0x40404040u) == 0x40404040u && (hi & 0x80808080u) == 0u;
+    xform16(V, upper, comp, s_lut);
     if (rev) {
         o[0] = __byte_perm(V[3], 0, 0x0123); o[1] = __byte_perm(V[2], 0, 0x0123);
         o[2] = __byte_perm(V[1], 0, 0x0123); o[3] = __byte_perm(V[0], 0, 0x0123);
@@ -524,7 +580,7 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
         const int64_t bpl64 = r.llen - (int64_t)r.elen;
         const bool fast = row_ok && out_len64 >= 16 && out_len64 < (1ll << 30) && r.norm && (r.pad[0] & 1) != 0 &&
                           bpl64 >= 16 && bpl64 < (1ll << 30) && s >= 0 && s < (1ll << 32) && e <= r.slen &&
-                          r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW);
+                          r.boff >= 0 && r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW);
         bool bad = false;
         if (fast) {
             const uint32_t bpl = (uint32_t)bpl64, out_len = (uint32_t)out_len64;
@@ -534,32 +590,49 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
             const uint8_t *fq = file + r.boff + s + (int64_t)elen * (int64_t)q_s32;
             const bool rev = (flags & FXG_X_REVERSE) != 0;
             const bool upper = (flags & FXG_X_UPPER) != 0, comp = (flags & FXG_X_COMPLEMENT) != 0;
-            const uint8_t *tbl = comp ? (upper ? s_lut[2] : s_lut[0]) : s_lut[1];
-            const bool xform = upper || comp;
             uint8_t *dst = out + off;
             const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15);
             const uint32_t total = a + out_len;
             const uint32_t nwords = (total + 15u) >> 4, hi_last = total & 15u;
             const uint32_t w_begin = a ? 1u : 0u, w_end = nwords - (hi_last ? 1u : 0u);
             uint8_t *dst0 = dst - a;                                     // 16-byte aligned
-            // interior words: all 16 slots belong to the query
-            // (XU words per lane and step: 6 * XU loads in flight)
+            // ---- pass 1: interior words that lie on one source line (4 of 5 for 80-column lines): no merge code ----
             for (uint32_t w = w_begin + (uint32_t)li; w < w_end; w += XU * QG) {
                 WordReq rq[XU];
-                uint32_t WW[XU][6], o[4];
+                uint32_t WW[XU][5], o[4];
+                bool take[XU];
 #pragma unroll
                 for (int u = 0; u < XU; ++u) {
                     const uint32_t wu = w + u * QG;
                     rq[u] = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, 16u * (wu < w_end ? wu : w) - a);
+                    take[u] = wu < w_end && rq[u].c >= 16u;
                 }
 #pragma unroll
-                for (int u = 0; u < XU; ++u) ow_load(rq[u], WW[u]);
+                for (int u = 0; u < XU; ++u)
+                    if (take[u]) {
 #pragma unroll
-                for (int u = 0; u < XU; ++u) {
-                    const uint32_t wu = w + u * QG;
-                    if (u == 0 || wu < w_end) {
-                        if (!ow_finish(WW[u], rq[u], elen, rev, xform, tbl, o)) bad = true;
-                        *reinterpret_cast<uint4 *>(dst0 + 16u * wu) = make_uint4(o[0], o[1], o[2], o[3]);
+                        for (int i = 0; i < 5; ++i) WW[u][i] = __ldg(rq[u].wp + i);
+                    }
+#pragma unroll
+                for (int u = 0; u < XU; ++u)
+                    if (take[u]) {
+                        if (!ow_finish_line(WW[u], rq[u].o1, rev, upper, comp, s_lut, o)) bad = true;
+                        *reinterpret_cast<uint4 *>(dst0 + 16u * (w + u * QG)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+            }
+            // ---- pass 2: the interior words that contain a line break, found by walking the breaks of the query:
+            //      break j sits in front of kept rank R_j = (bpl - rem_s) + j * bpl ----
+            {
+                const uint32_t first_r = bpl - rem_s;
+                for (uint32_t rj = first_r + (uint32_t)li * bpl; rj < out_len; rj += QG * bpl) {
+                    const uint32_t bpos = a + (rev ? out_len - rj : rj);     // output position where the next segment starts
+                    const uint32_t w = bpos >> 4;
+                    if ((bpos & 15u) != 0u && w >= w_begin && w < w_end) {
+                        uint32_t WE[6], o[4];
+                        const WordReq re = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, 16u * w - a);
+                        ow_load(re, WE);
+                        if (!ow_finish(WE, re, elen, rev, upper, comp, s_lut, o)) bad = true;
+                        *reinterpret_cast<uint4 *>(dst0 + 16u * w) = make_uint4(o[0], o[1], o[2], o[3]);
                     }
                 }
             }
@@ -569,7 +642,7 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
                 uint32_t o[4], WE[6];
                 const WordReq re = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, first ? 0u : out_len - 16u);
                 ow_load(re, WE);
-                if (!ow_finish(WE, re, elen, rev, xform, tbl, o)) bad = true;
+                if (!ow_finish(WE, re, elen, rev, upper, comp, s_lut, o)) bad = true;
                 uint64_t lo = (uint64_t)o[0] | ((uint64_t)o[1] << 32), hi = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
                 uint32_t b_lo, b_hi;                                     // slots [b_lo, b_hi) of the word are ours
                 uint8_t *gw;
@@ -615,6 +688,32 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
                                     lane, nullptr);
         }
     }
+}
+
+// ---- one query, ONE launch, ONE synchronisation: what a per-object getter (Sequence.seq, .antisense, ...) costs ----
+// The query's output range is cut into `chunk`-byte pieces, one per warp; a piece of a query is itself a query, exact
+// for records with uniform lines (the slice formula) -- any other record is served whole by warp 0.  The output goes
+// straight to mapped pinned host memory (or to device scratch for long sequences).
+__global__ void __launch_bounds__(XTHREADS) extract_one_kernel(
+    const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fasta_row *__restrict__ rows,
+    int64_t n_rows, int64_t rid, int64_t s, int64_t e, int flags, int64_t chunk, uint8_t *__restrict__ out) {
+    __shared__ uint8_t s_lut[3][256];
+    __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
+    init_luts(s_lut);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool row_ok = rid >= 0 && rid < n_rows;
+    fxg_fasta_row r;
+    memset(&r, 0, sizeof(r));
+    if (row_ok) r = rows[rid];
+    const int64_t gw = (int64_t)blockIdx.x * XWARPS + warp;
+    const bool splittable = row_ok && r.norm && (r.pad[0] & 1) != 0 && !(flags & FXG_X_RAW);
+    int64_t ss = s, ee = e;
+    if (splittable) { ss = s + gw * chunk; ee = ss + chunk < e ? ss + chunk : e; }
+    else if (gw != 0) return;
+    if (ss >= ee) return;
+    const int64_t ooff = (flags & FXG_X_REVERSE) ? e - ee : ss - s;      // reversed strands fill the output back to front
+    serve_query_warp<false>(file, fsize, capacity, r, row_ok, ss, ee, flags, out + ooff, s_lut, s_stage[warp], lane, nullptr);
 }
 
 // K5: FASTQ reads: raw copies of rlen bytes at soff (sequence) and qoff (quality)
@@ -943,5 +1042,46 @@ extern "C" int fxg_composition_host(fxg_ctx *ctx, const fxg_file *f, const fxg_f
     FXG_CUDA(cudaGetLastError());
     FXG_CUDA(cudaMemcpyAsync(hist_host, d_hist, (size_t)nq * 2048, cudaMemcpyDeviceToHost, ctx->stream));
     FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FXG_OK;
+}
+
+// One query through one kernel launch and one stream synchronisation (no plan kernels, no H2D copies: the query
+// travels as kernel arguments).  Same result as fxg_extract_host with nq = 1.
+extern "C" int fxg_extract_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
+                                    int64_t row_id, int64_t s, int64_t e, int32_t flags, uint8_t *out_host, int64_t out_cap) {
+    FXG_CHECK_ARG(ctx && f && d_rows && (out_host || e <= s), "bad arguments");
+    FXG_LOCK(ctx);
+    const int64_t len = e > s ? e - s : 0;
+    if (len == 0) return FXG_OK;
+    if (len > out_cap) { fxg_set_error("output needs %lld bytes, capacity %lld", (long long)len, (long long)out_cap); return FXG_ECAP; }
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    const int64_t ONE_PINNED = 1 << 20;
+    if (!ctx->h_one) FXG_CUDA(cudaHostAlloc(&ctx->h_one, (size_t)ONE_PINNED + 64, cudaHostAllocMapped));
+    uint8_t *d_out;
+    const bool direct = len <= ONE_PINNED;
+    if (direct) {
+        void *dp = nullptr;
+        FXG_CUDA(cudaHostGetDevicePointer(&dp, ctx->h_one, 0));
+        d_out = (uint8_t *)dp;
+    } else {
+        int rc = ctx->row_tmp.reserve((size_t)len + 64);
+        if (rc) return rc;
+        d_out = (uint8_t *)ctx->row_tmp.ptr;
+    }
+    // pieces of >= 2 KiB, multiples of 16 bytes, at most 8 warps x 4 CTAs per SM worth of them
+    int64_t warps = (len + 2047) / 2048;
+    const int64_t maxw = (int64_t)ctx->sm_count * 4 * XWARPS;
+    if (warps > maxw) warps = maxw;
+    int64_t chunk = ((len + warps - 1) / warps + 15) & ~(int64_t)15;
+    warps = (len + chunk - 1) / chunk;
+    const unsigned grid = (unsigned)((warps + XWARPS - 1) / XWARPS);
+    {
+        FxgProfScope prof(ctx, FXG_PROF_GATHER);
+        extract_one_kernel<<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, row_id, s, e, flags, chunk, d_out);
+    }
+    FXG_CUDA(cudaGetLastError());
+    if (!direct) FXG_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (direct) memcpy(out_host, ctx->h_one, (size_t)len);
     return FXG_OK;
 }

@@ -911,7 +911,8 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
             //      lane, every store instruction leaves half-filled sectors.  Neighbouring lanes swap halves instead, so
             //      that each instruction writes whole sectors: lanes (2j, 2j+1) write row 2j, then row 2j+1. ----
             const bool full = mine && have3 && row < P.qrows_cap;
-            const bool pair_full = full && __shfl_xor_sync(0xffffffffu, full ? 1 : 0, 1) != 0;
+            const int other_full = __shfl_xor_sync(0xffffffffu, full ? 1 : 0, 1);   // every lane must reach the shuffle
+            const bool pair_full = full && other_full != 0;
             longlong2 a, b;
             a.x = soff; a.y = qoff;
             b.x = rlen; b.y = (long long)(((unsigned long long)(uint32_t)(int)k << 32) | (uint32_t)(int)len);

@@ -341,6 +341,15 @@ class Engine:
                                      ptr(fl), nq, ptr(off), ptr(out), out.size, ptr(acgt)))
         return out[:total], off, acgt
 
+    def extract_one(self, dfile, drows, row_id, s, e, flags=0):
+        """one query, one kernel launch, one synchronisation -> bytes (the per-object getters)"""
+        n = e - s
+        if n <= 0:
+            return b""
+        buf = C.create_string_buffer(n)
+        check(lib().fxg_extract_one_host(self.ctx, dfile.handle, drows.devptr, drows.n_rows, row_id, s, e, flags, buf, n))
+        return buf.raw
+
     def reads(self, dfile, drows, ids, flags=0, want_seq=True, want_qual=True, rlens=None):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         nq = ids.size
