@@ -313,6 +313,9 @@ typedef struct fxg_gzindex {
     int64_t  npoints;
     const int64_t *cmp_offset;           /* per point: offset of the deflate data in the compressed file  */
     const int64_t *uncmp_offset;         /* per point: offset in the uncompressed stream                  */
+    const uint8_t *bits;                 /* per point: bit offset (0..7) of the block start; NULL = all 0 */
+    const uint8_t *has_data;             /* per point: 1 = a window follows in `windows`; NULL = none     */
+    const uint8_t *windows;              /* window_size bytes per point with has_data, in point order     */
 } fxg_gzindex;
 typedef struct fxg_comp_row { int64_t seqid, abc, num; } fxg_comp_row;      /* seqid 0 = whole file        */
 typedef struct fxg_fastq_meta { int64_t a, c, g, t, n, maxlen, minlen, minqs, maxqs, phred; } fxg_fastq_meta;
@@ -322,6 +325,17 @@ int fxg_fxi_write_fasta(const char *path, const fxg_fasta_row *rows, int64_t n_r
 int fxg_fxi_write_fastq(const char *path, const fxg_fastq_row *rows, int64_t n_rows, const uint8_t *names,
                         const int64_t *name_off, int64_t n_lines, int64_t total_size, const fxg_gzindex *gz,
                         const fxg_fastq_meta *meta);
+
+/* ---- generic (non-BGZF) gzip: one sequential zlib pass on the host that inflates the stream AND collects the zran
+ * checkpoints the `.fxi` must carry (replaces gzread during the scan, src/kseq.c:70, and the second inflate pass of
+ * zran_build_index, src/index.c:381-387).  One access point per >= `spacing` bytes of output at a deflate block
+ * boundary, with the 32 KiB of output in front of it (the published zran.c method); a reader resumes at any point
+ * with inflatePrime + inflateSetDictionary.  The inflated bytes are then staged into HBM like a plain file. */
+typedef struct fxg_gzip_result fxg_gzip_result;
+int            fxg_gzip_inflate_host(const void *comp, int64_t nbytes, uint32_t spacing /* 0 = 1 MiB */, fxg_gzip_result **out);
+const uint8_t *fxg_gzip_data(const fxg_gzip_result *r, int64_t *size);
+int            fxg_gzip_index(const fxg_gzip_result *r, fxg_gzindex *gz);   /* pointers into r, valid until freed */
+void           fxg_gzip_free(fxg_gzip_result *r);
 
 /* ---- full-index statistics on the resident file ---------------------------------
  * fxg_fasta_composition  per-record 128-bin byte composition, the counting loop of pyfastx_fasta_calc_composition

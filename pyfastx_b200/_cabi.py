@@ -46,7 +46,7 @@ COMM_ID_BYTES = 128
 class GzIndex(C.Structure):
     _fields_ = [("compressed_size", C.c_int64), ("uncompressed_size", C.c_int64), ("spacing", C.c_uint32),
                 ("window_size", C.c_uint32), ("npoints", C.c_int64), ("cmp_offset", C.c_void_p),
-                ("uncmp_offset", C.c_void_p)]
+                ("uncmp_offset", C.c_void_p), ("bits", C.c_void_p), ("has_data", C.c_void_p), ("windows", C.c_void_p)]
 
 
 class FastqMeta(C.Structure):
@@ -125,6 +125,10 @@ SIGNATURES = {
     "fxg_file_from_bgzf_host": (i32, [vp, vp, i64, P(vp), P(i64)]),
     "fxg_fxi_write_fasta": (i32, [C.c_char_p, vp, i64, vp, vp, i64, vp, vp, i64]),
     "fxg_fxi_write_fastq": (i32, [C.c_char_p, vp, i64, vp, vp, i64, i64, vp, vp]),
+    "fxg_gzip_inflate_host": (i32, [vp, i64, C.c_uint32, P(vp)]),
+    "fxg_gzip_data": (vp, [vp, P(i64)]),
+    "fxg_gzip_index": (i32, [vp, P(GzIndex)]),
+    "fxg_gzip_free": (None, [vp]),
     "fxg_fasta_composition": (i32, [vp, vp, vp, i64, i64, P(vp), P(i64), vp]),
     "fxg_fastq_stats": (i32, [vp, vp, vp, i64, i64, i32, P(FastqMeta)]),
     "fxg_free_host": (None, [vp]),

@@ -94,11 +94,10 @@ class _Staged:
             except _cabi.FxgError as ex:
                 if ex.code != _cabi.FXG_EFORMAT:
                     raise
-                self.dfile = self.engine.stage_bytes(np.frombuffer(_gzip.decompress(comp.tobytes()), dtype=np.uint8))
-                # a single deflate stream: one checkpoint at its start (no window needed there)
-                hdr = _gzip_header_len(comp)
-                self.gzindex = {"compressed_size": int(comp.size), "uncompressed_size": int(self.dfile.size),
-                                "cmp_offset": np.array([hdr], dtype=np.int64), "uncmp_offset": np.zeros(1, dtype=np.int64)}
+                # a single serial deflate stream: one zlib pass on the host (what the reference's gzread does too),
+                # collecting the zran checkpoints in the same pass; everything after runs on the GPU copy
+                view, self.gzindex, self._gz_handle = self.engine.gzip_inflate(comp)
+                self.dfile = self.engine.stage_bytes(view)
         else:
             self.dfile = self.engine.stage_path(path)
 
@@ -124,6 +123,15 @@ class _Staged:
     def close(self):
         try:
             self.dfile.free()
+        except Exception:
+            pass
+
+    def __del__(self):
+        try:
+            h = getattr(self, "_gz_handle", None)
+            if h:
+                self.engine.gzip_free(h)
+                self._gz_handle = None
         except Exception:
             pass
 

@@ -732,8 +732,14 @@ void gzindex_rows(const fxg_gzindex *gz, std::vector<std::vector<Val>> &rows, st
     add("GZIDX", 5); add(&version, 1); add(&flags, 1); add(&csz, 8); add(&usz, 8); add(&spacing, 4); add(&wsz, 4); add(&np, 4);
     for (int64_t i = 0; i < gz->npoints; ++i) {
         const uint64_t c = (uint64_t)gz->cmp_offset[i], u = (uint64_t)gz->uncmp_offset[i];
-        const uint8_t bits = 0, has_data = 0;
+        const uint8_t bits = gz->bits ? gz->bits[i] : 0, has_data = gz->has_data ? gz->has_data[i] : 0;
         add(&c, 8); add(&u, 8); add(&bits, 1); add(&has_data, 1);
+    }
+    // window data of the points that have one, in point order (src/util.c:514-527)
+    if (gz->has_data && gz->windows) {
+        int64_t k = 0;
+        for (int64_t i = 0; i < gz->npoints; ++i)
+            if (gz->has_data[i]) { add(gz->windows + (size_t)k * gz->window_size, gz->window_size); ++k; }
     }
     for (size_t i = 0; i < rows.size(); ++i) rows[i][1] = Val::blob(store[i].data(), store[i].size());
 }
@@ -826,7 +832,7 @@ extern "C" int fxg_fxi_write_fasta(const char *path, const fxg_fasta_row *rows, 
     if (ok) {
         std::vector<std::vector<Val>> grows;
         std::vector<std::vector<uint8_t>> store;
-        store.reserve(gz && gz->npoints > 0 ? (size_t)gz->npoints * 4 + 8 : 0);
+        store.reserve(gz && gz->npoints > 0 ? (size_t)gz->npoints * 5 + 8 : 0);
         gzindex_rows(gz, grows, store);
         gz_root = build_small_table(db, grows);
         ok = gz_root != 0;
@@ -890,7 +896,7 @@ extern "C" int fxg_fxi_write_fastq(const char *path, const fxg_fastq_row *rows, 
     if (ok) {
         std::vector<std::vector<Val>> grows;
         std::vector<std::vector<uint8_t>> store;
-        store.reserve(gz && gz->npoints > 0 ? (size_t)gz->npoints * 4 + 8 : 0);
+        store.reserve(gz && gz->npoints > 0 ? (size_t)gz->npoints * 5 + 8 : 0);
         gzindex_rows(gz, grows, store);
         gz_root = build_small_table(db, grows);
         ok = gz_root != 0;

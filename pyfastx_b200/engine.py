@@ -140,6 +140,22 @@ class Engine:
                                           C.byref(nm), C.byref(tot)))
         return co, uo
 
+    def gzip_inflate(self, data):
+        """generic gzip (one serial deflate stream): ONE zlib pass on the host -> (inflated uint8 view, GzIndex with
+        the zran checkpoints, handle).  The handle owns both; keep it until the .fxi is written, then gzip_free."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        h = C.c_void_p()
+        check(lib().fxg_gzip_inflate_host(a.ctypes.data, a.size, 0, C.byref(h)))
+        n = C.c_int64(0)
+        p = lib().fxg_gzip_data(h, C.byref(n))
+        view = np.frombuffer((C.c_uint8 * n.value).from_address(p), dtype=np.uint8) if n.value else np.zeros(0, np.uint8)
+        gz = _cabi.GzIndex()
+        check(lib().fxg_gzip_index(h, C.byref(gz)))
+        return view, gz, h
+
+    def gzip_free(self, handle):
+        lib().fxg_gzip_free(handle)
+
     def gather_ranges(self, dfile, offsets, lengths):
         """raw byte ranges of the resident file (e.g. record names) -> (packed uint8, offsets[n+1])"""
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)

@@ -136,11 +136,14 @@ def bgzf_gzindex(comp, cmp_off, ucmp_off):
 
 
 def _gz_struct(gz):
+    """dict (BGZF member table, see bgzf_gzindex) or a ready _cabi.GzIndex (generic gzip, engine.gzip_inflate)"""
     if not gz:
         return None, None
+    if isinstance(gz, _cabi.GzIndex):
+        return gz, None
     keep = (np.ascontiguousarray(gz["cmp_offset"], dtype=np.int64), np.ascontiguousarray(gz["uncmp_offset"], dtype=np.int64))
     g = _cabi.GzIndex(int(gz["compressed_size"]), int(gz["uncompressed_size"]), ZRAN_SPACING, ZRAN_WINDOW,
-                      len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data)
+                      len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, None, None, None)
     return g, keep
 
 
