@@ -723,7 +723,13 @@ def run_e2e_and_cpu(c, args, info, rows, st, host_file, result):
                 per_obj = time.perf_counter() - t1
                 out_host, off_host = c.x_keep[5], c.x_keep[6]
                 for j in range(sel.size):
-                    assert got[j].encode() == out_host[off_host[j]:off_host[j + 1]].tobytes()
+                    want = out_host[off_host[j]:off_host[j + 1]].tobytes()
+                    if got[j].encode() != want:
+                        g = got[j].encode()
+                        k = next((x for x in range(min(len(g), len(want))) if g[x] != want[x]), -1)
+                        raise AssertionError("per-object getter differs from the batch: query %d (%s, %d:%d, minus=%s) lengths %d/%d, "
+                                             "first difference at %d: %r vs %r" % (j, names[j], qs[j], qe[j], minus[j], len(g), len(want), k,
+                                                                                 g[max(0, k - 8):k + 24], want[max(0, k - 8):k + 24]))
                 result["extract"]["per_object_idiom"] = {
                     "api": "fa[name][s:e].seq / .antisense through pyfastx_b200 (one GPU launch + one sync per query)",
                     "queries_per_s": sel.size / per_obj, "Mbases_per_s": float((qe - qs).sum()) / per_obj / 1e6,

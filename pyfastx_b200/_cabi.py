@@ -10,7 +10,7 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfxg.so")
+LIB_PATH = os.environ.get("FXG_LIB_PATH") or os.path.join(_HERE, "libfxg.so")     # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fxg.h")
 
 FASTA_ROW = np.dtype([("boff", "<i8"), ("blen", "<i8"), ("slen", "<i8"), ("llen", "<i8"),

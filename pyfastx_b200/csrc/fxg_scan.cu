@@ -769,6 +769,12 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams
 // of a read that began earlier are written field by field) and completes the reads that START in its span
 // as far as its window reaches; lines past the window are (also) covered by the warp that owns their
 // region, which writes identical values.  Spans containing a dense region use the general path.
+#ifndef FXG_FQ_PRELOAD
+#define FXG_FQ_PRELOAD 1
+#endif
+#ifndef FXG_FQ_PAIRSTORE
+#define FXG_FQ_PAIRSTORE 1
+#endif
 constexpr int RG = 8;                          // regions per warp
 constexpr int RWIN = RG + 2;                   // + look-ahead
 static_assert(RWIN * REGION <= 32768, "window positions must fit 15 bits");
@@ -806,7 +812,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
 #pragma unroll
         for (int i = 0; i < RWIN; ++i) {
             E2[i] = 0u;
-            if (r0 + i < P.nreg) E2[i] = reinterpret_cast<const uint32_t *>(P.seg + (r0 + i) * SEGCAP)[lane];
+            if (FXG_FQ_PRELOAD && r0 + i < P.nreg) E2[i] = reinterpret_cast<const uint32_t *>(P.seg + (r0 + i) * SEGCAP)[lane];
         }
         int W = 0, Ls = 0;                                           // entries in the window / in the span
         bool closed = false;                                         // a dense look-ahead region ends the window
@@ -816,6 +822,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
             if (nl > SEGCAP) closed = true;
             if (!closed) {
                 const int k = 2 * lane;
+                if (!FXG_FQ_PRELOAD && k < nl) E2[i] = reinterpret_cast<const uint32_t *>(P.seg + (r0 + i) * SEGCAP)[lane];
                 const uint32_t e0 = E2[i] & 0xffffu, e1 = E2[i] >> 16;
                 if (k < nl) flat[W + k] = (uint16_t)((i * REGION + (int)(e0 & E_POS)) | ((e0 & E_CR) ? 0x8000u : 0u));
                 if (k + 1 < nl) flat[W + k + 1] = (uint16_t)((i * REGION + (int)(e1 & E_POS)) | ((e1 & E_CR) ? 0x8000u : 0u));
@@ -912,7 +919,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
             //      that each instruction writes whole sectors: lanes (2j, 2j+1) write row 2j, then row 2j+1. ----
             const bool full = mine && have3 && row < P.qrows_cap;
             const int other_full = __shfl_xor_sync(0xffffffffu, full ? 1 : 0, 1);   // every lane must reach the shuffle
-            const bool pair_full = full && other_full != 0;
+            const bool pair_full = FXG_FQ_PAIRSTORE && full && other_full != 0;
             longlong2 a, b;
             a.x = soff; a.y = qoff;
             b.x = rlen; b.y = (long long)(((unsigned long long)(uint32_t)(int)k << 32) | (uint32_t)(int)len);

@@ -28,13 +28,14 @@ def main():
     for case in G.cases():
         data = G.case_data(case)
         name = case["name"]
+        key = case["kind"] + ":" + name          # FASTA and FASTQ edge cases share some names
         if any(b >= 128 for b in data):
             continue                                   # the reference indexes a 128-entry array with such bytes (UB)
         if case["kind"] == "fasta":
             path = os.path.join(tmp, name + ".fa")
             open(path, "wb").write(data)
             try:
-                fa = pyfastx.Fasta(path, full_index=True)
+                fa = pyfastx.Fasta(path, full_index=True, uppercase=case["uppercase"], full_name=case["full_name"])
                 rec = {"kind": "fasta"}
                 try:
                     rec["composition"] = fa.composition
@@ -47,7 +48,7 @@ def main():
                 con = sqlite3.connect(path + ".fxi")
                 rec["comp"] = [list(r) for r in con.execute("SELECT seqid,abc,num FROM comp ORDER BY ID")]
                 con.close()
-                out[name] = rec
+                out[key] = rec
             except Exception as ex:
                 print("skip", name, repr(ex))
         else:
@@ -63,7 +64,7 @@ def main():
                 rec["base"] = [list(r) for r in con.execute("SELECT * FROM base")]
                 rec["meta"] = [list(r) for r in con.execute("SELECT * FROM meta")]
                 con.close()
-                out[name] = rec
+                out[key] = rec
             except Exception as ex:
                 print("skip", name, repr(ex))
     dst = os.path.join(HERE, "golden_stats.json")

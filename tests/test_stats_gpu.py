@@ -20,15 +20,16 @@ with open(os.path.join(G.GOLD, "golden_stats.json")) as _f:
 
 
 def _cases(kind):
-    return [c for c in G.cases(kind) if c["name"] in STATS]
+    return [c for c in G.cases(kind) if kind + ":" + c["name"] in STATS]
 
 
 @pytest.mark.parametrize("case", _cases("fasta"), ids=lambda c: c["name"])
 def test_fasta_full_index_golden(tmp_path, case):
-    exp = STATS[case["name"]]
+    exp = STATS["fasta:" + case["name"]]
     p = tmp_path / "x.fa"
     p.write_bytes(G.case_data(case))
-    fa = pyfastx.Fasta(str(p), full_index=True)
+    kw = dict(uppercase=case["uppercase"], full_name=case["full_name"])
+    fa = pyfastx.Fasta(str(p), full_index=True, **kw)
     con = sqlite3.connect(str(p) + ".fxi")
     comp = [list(r) for r in con.execute("SELECT seqid,abc,num FROM comp ORDER BY ID")]
     idx = {r[0] for r in con.execute("SELECT name FROM sqlite_master WHERE type='index'")}
@@ -45,14 +46,14 @@ def test_fasta_full_index_golden(tmp_path, case):
         assert fa.gc_content == exp["gc_content"] and fa.gc_skew == exp["gc_skew"]
     assert fa.type == exp["type"]
     # a second object loads the persisted comp rows instead of recomputing
-    fb = pyfastx.Fasta(str(p))
+    fb = pyfastx.Fasta(str(p), **kw)
     if "error" not in exp:
         assert fb.composition == exp["composition"]
 
 
 @pytest.mark.parametrize("case", _cases("fastq"), ids=lambda c: c["name"])
 def test_fastq_stats_golden(tmp_path, case):
-    exp = STATS[case["name"]]
+    exp = STATS["fastq:" + case["name"]]
     p = tmp_path / "x.fq"
     p.write_bytes(G.case_data(case))
     fq = pyfastx.Fastq(str(p), full_index=True)
