@@ -676,10 +676,10 @@ def run_extract(c, args, dfile, info, rows, result, host_file):
             n_cmp = oracle_extract_compare(host_file, local_rows, rid, qs, qe, flags, out_host, off_host, n_threads())
             out["parity"] = {"queries_compared_with_oracle": int(n_cmp), "of": nq, "bytes": bases,
                              "seconds": time.perf_counter() - t0}
-        c.x_keep = (rid, qs, qe, minus, flags, out_host, off_host)
-        for p in (hp3, hp4) + tuple(p for _, p in q_pinned):
+        c.x_keep = (rid, qs, qe, minus, flags, out_host, off_host)      # out_host / off_host stay alive (pinned: hp2, hp4)
+        for p in (hp3,) + tuple(p for _, p in q_pinned):
             L.fxg_host_free(p)
-        c.x_pinned = hp2
+        c.x_pinned = (hp2, hp4)
         del d_rid, d_s, d_e, d_fl, d_ooff, d_out
     result["extract"] = out
     return drows, local_rows
@@ -1061,7 +1061,8 @@ def run_b200(args):
         c.L.fxg_host_free(hp1)
     if getattr(c, "x_pinned", None) is not None:
         c.x_keep = None
-        c.L.fxg_host_free(c.x_pinned)
+        for p in c.x_pinned:
+            c.L.fxg_host_free(p)
     if not args.skip_fastq:
         run_fastq(c, args, result)
     result["comm"] = {"nranks": c.world, "collective": "ncclAllGather via fxg_shard_exchange (libfxg.so, dlopen libnccl.so.2)"

@@ -279,6 +279,10 @@ int fxg_reads_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows,
                    const int64_t *ids, int64_t nq, int32_t flags,
                    int64_t *out_off_host, uint8_t *seq_host, uint8_t *qual_host, int64_t out_cap);
 
+/* one read, one kernel launch, one synchronisation: the Read.seq / .qual getters (which: 0 = sequence, 1 = quality) */
+int fxg_read_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows, int64_t read_id,
+                      int which, int32_t flags, int64_t rlen, uint8_t *out_host, int64_t out_cap);
+
 /* ---- K6: BGZF (block-gzip) inputs: member table on the host, member-parallel inflate on the GPU ----
  * Replaces zlib's gzread during the scan (src/kseq.c:70), the second full inflate pass that builds
  * the zran checkpoints (zran_build_index, src/index.c:381-387) and zran_seek + zran_read per random

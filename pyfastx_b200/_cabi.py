@@ -120,6 +120,7 @@ SIGNATURES = {
     "fxg_composition_host": (i32, [vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
     "fxg_reads_dev": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64, P(i64)]),
     "fxg_reads_host": (i32, [vp, vp, vp, i64, vp, i64, i32, vp, vp, vp, i64]),
+    "fxg_read_one_host": (i32, [vp, vp, vp, i64, i64, i32, i32, i64, vp, i64]),
     "fxg_bgzf_members_host": (i32, [vp, i64, vp, vp, i64, P(i64), P(i64)]),
     "fxg_inflate_members_dev": (i32, [vp, vp, vp, vp, i64, vp, i64, vp]),
     "fxg_file_from_bgzf_host": (i32, [vp, vp, i64, P(vp), P(i64)]),

@@ -18,7 +18,8 @@ import numpy as np
 from . import _cabi, fxi
 from .engine import get_engine
 
-__all__ = ["Fasta", "Fastq", "Sequence", "Read", "version", "gzip_check", "reverse_complement"]
+__all__ = ["Fasta", "Fastq", "Fastx", "Sequence", "Read", "FastaKeys", "FastqKeys", "version", "gzip_check",
+           "reverse_complement"]
 
 VERSION = "2.3.1+b200.1"     # tracks the reference version whose behaviour is reproduced
 
@@ -136,6 +137,104 @@ class _Staged:
             pass
 
 
+class _Keys:
+    """names of an index in file order (reference FastaKeys / FastqKeys, src/fakeys.c, src/fqkeys.c: len, iteration,
+    indexing, `in`); backed by the packed name buffer + the native hash table instead of SQL."""
+
+    def __init__(self, names, what):
+        self._names, self._what = names, what
+
+    def __len__(self):
+        return len(self._names)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._names.get(k) for k in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if i < 0 or i >= n:
+            raise IndexError("index out of range")
+        return self._names.get(i)
+
+    def __iter__(self):
+        return (self._names.get(i) for i in range(len(self)))
+
+    def __contains__(self, name):
+        return isinstance(name, str) and self._names.find(name) >= 0
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return "<%s> contains %d keys" % (self._what, len(self))
+
+
+class FastaKeys(_Keys):
+    pass
+
+
+class FastqKeys(_Keys):
+    pass
+
+
+class Fastx:
+    """Fastx(file_name, format="auto", uppercase=False, comment=False): iterate (name, seq[, comment]) of a FASTA
+    or (name, seq, qual[, comment]) of a FASTQ file without keeping an index file (reference src/fastx.c:42-43).
+    Records come from the GPU scan + batched gather, a few thousand per round trip."""
+
+    def __init__(self, file_name, format="auto", uppercase=False, comment=False):
+        file_name = os.fspath(file_name)
+        if not os.path.exists(file_name):
+            raise FileExistsError("the input file %s does not exists" % file_name)
+        self.file_name, self.uppercase, self.comment = file_name, bool(uppercase), bool(comment)
+        self._st = _Staged(file_name)
+        first = self._st.first_non_space()
+        if format == "auto":
+            format = "fasta" if first == ord(">") else ("fastq" if first == ord("@") else None)
+        if format not in ("fasta", "fastq"):
+            raise RuntimeError("%s is not fasta or fastq sequence file" % file_name)
+        self.format = format
+
+    def __iter__(self):
+        st, eng = self._st, self._st.engine
+        step = 4096
+        if self.format == "fasta":
+            rows, _ = eng.fasta_scan(st.dfile)
+            drows = eng.upload_rows(rows)
+            hoff = rows["boff"] - rows["elen"].astype(np.int64) - rows["dlen"]
+            flags = _cabi.X_UPPER if self.uppercase else 0
+            for a in range(0, len(rows), step):
+                b = min(len(rows), a + step)
+                rid = np.arange(a, b, dtype=np.int64)
+                out, off, _ = eng.extract(st.dfile, drows, rid, np.zeros(b - a, np.int64), rows["slen"][a:b],
+                                          np.full(b - a, flags, np.int32))
+                hdr = st.ranges(hoff[a:b], rows["dlen"][a:b].astype(np.int64))
+                buf = out.tobytes()
+                for k in range(b - a):
+                    h = hdr[k].decode("latin-1")
+                    name = h[:int(rows["nlen"][a + k])]
+                    seq = buf[off[k]:off[k + 1]].decode("latin-1")
+                    yield (name, seq, h[len(name) + 1:]) if self.comment else (name, seq)
+        else:
+            rows, _ = eng.fastq_scan(st.dfile)
+            drows = eng.upload_rows(rows)
+            for a in range(0, len(rows), step):
+                b = min(len(rows), a + step)
+                ids = np.arange(a, b, dtype=np.int64)
+                seq, qual, off = eng.reads(st.dfile, drows, ids, rlens=rows["rlen"][a:b])
+                hdr = st.ranges(rows["soff"][a:b] - rows["dlen"][a:b], rows["dlen"][a:b].astype(np.int64) - 1)
+                sb, qb = seq.tobytes(), qual.tobytes()
+                for k in range(b - a):
+                    h = hdr[k].rstrip(b"\r").decode("latin-1")
+                    name = h[:int(rows["nlen"][a + k])]
+                    s = sb[off[k]:off[k + 1]].decode("latin-1")
+                    if self.uppercase:
+                        s = s.upper()
+                    rec = (name, s, qb[off[k]:off[k + 1]].decode("latin-1"))
+                    yield rec + (h[len(name) + 1:],) if self.comment else rec
+
+
 # =================================================================================================
 # FASTA
 # =================================================================================================
@@ -235,7 +334,7 @@ class Fasta:
 
     def keys(self):
         self._need_index()
-        return self._names.tolist()
+        return FastaKeys(self._names, "FastaKeys")
 
     def _row_id(self, key):
         self._need_index()
@@ -643,7 +742,7 @@ class Fastq:
 
     def keys(self):
         self.build_index()
-        return self._names.tolist()
+        return FastqKeys(self._names, "FastqKeys")
 
     def _row_id(self, key):
         self.build_index()
@@ -787,9 +886,7 @@ class Read:
 
     def _fetch(self, flags=0, qual=False):
         fq = self._fq
-        seq, ql, _ = fq._st.engine.reads(fq._st.dfile, fq._drows, [self._i], flags=flags, want_seq=not qual,
-                                         want_qual=qual, rlens=[len(self)])
-        return (ql if qual else seq).tobytes().decode("latin-1")
+        return fq._st.engine.read_one(fq._st.dfile, fq._drows, self._i, len(self), 1 if qual else 0, flags).decode("latin-1")
 
     @property
     def seq(self):

@@ -74,6 +74,10 @@ extern "C" int fxg_ctx_create(int device, fxg_ctx **out) {
         fxg_set_error("device %d is sm_%d%d; libfxg is built for sm_100a only", device, prop.major, prop.minor);
         return FXG_ENODEV;
     }
+    if (const char *g = getenv("FXG_L2_FETCH")) {            // A/B: L2 fetch granularity (32 / 64 / 128 bytes)
+        const int v = atoi(g);
+        if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+    }
     fxg_ctx *c = new fxg_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;

@@ -750,6 +750,28 @@ __global__ void __launch_bounds__(XTHREADS) reads_kernel(
     }
 }
 
+// one FASTQ read, one launch: sequence (which = 0) or quality (which = 1) bytes of read `id` (src/read.c:37-45,152-249)
+__global__ void __launch_bounds__(32) read_one_kernel(const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity,
+                                                      const fxg_fastq_row *__restrict__ rows, int64_t n_rows, int64_t id,
+                                                      int which, int flags, uint8_t *__restrict__ out) {
+    __shared__ uint8_t s_lut[3][256];
+    __shared__ __align__(16) uint8_t s_stage[1][XSTAGE];
+    init_luts(s_lut);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    if (id < 0 || id >= n_rows) return;
+    const fxg_fastq_row r = rows[id];
+    if (r.rlen <= 0) return;
+    GatherJob job;
+    job.skip = 0; job.src_len = r.rlen; job.out_len = r.rlen;
+    job.src = which ? r.qoff : r.soff;
+    job.dst = out;
+    job.flags = (which ? (flags & FXG_X_REVERSE) : flags) | FXG_X_RAW;      // qualities are never complemented
+    const bool fast = r.rlen < (1ll << 30) && job.src >= 0 && job.src + r.rlen + 32 <= capacity;
+    if (!fast || !pull_one<false>(file, job.src, 0, r.rlen, 1u << 30, 1, job.flags, job.dst, s_lut, lane, nullptr))
+        gather_one<false>(file, fsize, job, s_lut[0], s_stage[0], lane, nullptr);
+}
+
 // ---- exclusive prefix sum of lengths (3 small kernels; < 2 % of the gather traffic) -----------
 constexpr int PS_ITEMS = 2048;   // per block
 __global__ void ps_block_sums(const int64_t *s, const int64_t *e, const fxg_fastq_row *rows, const int64_t *ids,
@@ -1083,5 +1105,35 @@ extern "C" int fxg_extract_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_f
     if (!direct) FXG_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t)len, cudaMemcpyDeviceToHost, ctx->stream));
     FXG_CUDA(cudaStreamSynchronize(ctx->stream));
     if (direct) memcpy(out_host, ctx->h_one, (size_t)len);
+    return FXG_OK;
+}
+
+// One read through one kernel launch and one stream synchronisation (the Read.seq / .qual getters).
+extern "C" int fxg_read_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fastq_row *d_rows, int64_t n_rows, int64_t read_id,
+                                 int which, int32_t flags, int64_t rlen, uint8_t *out_host, int64_t out_cap) {
+    FXG_CHECK_ARG(ctx && f && d_rows && (out_host || rlen <= 0), "bad arguments");
+    FXG_LOCK(ctx);
+    if (rlen <= 0) return FXG_OK;
+    if (rlen > out_cap) { fxg_set_error("output needs %lld bytes, capacity %lld", (long long)rlen, (long long)out_cap); return FXG_ECAP; }
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    const int64_t ONE_PINNED = 1 << 20;
+    if (!ctx->h_one) FXG_CUDA(cudaHostAlloc(&ctx->h_one, (size_t)ONE_PINNED + 64, cudaHostAllocMapped));
+    const bool direct = rlen <= ONE_PINNED;
+    uint8_t *d_out;
+    if (direct) {
+        void *dp = nullptr;
+        FXG_CUDA(cudaHostGetDevicePointer(&dp, ctx->h_one, 0));
+        d_out = (uint8_t *)dp;
+    } else {
+        int rc = ctx->row_tmp.reserve((size_t)rlen + 64);
+        if (rc) return rc;
+        d_out = (uint8_t *)ctx->row_tmp.ptr;
+    }
+    ctx->launches += 1;
+    read_one_kernel<<<1, 32, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, read_id, which, flags, d_out);
+    FXG_CUDA(cudaGetLastError());
+    if (!direct) FXG_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t)rlen, cudaMemcpyDeviceToHost, ctx->stream));
+    FXG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (direct) memcpy(out_host, ctx->h_one, (size_t)rlen);
     return FXG_OK;
 }

@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams
 // as far as its window reaches; lines past the window are (also) covered by the warp that owns their
 // region, which writes identical values.  Spans containing a dense region use the general path.
 #ifndef FXG_FQ_PRELOAD
-#define FXG_FQ_PRELOAD 1
+#define FXG_FQ_PRELOAD 0
 #endif
 #ifndef FXG_FQ_PAIRSTORE
 #define FXG_FQ_PAIRSTORE 1

@@ -11,6 +11,11 @@ import numpy as np
 from . import _cabi
 from ._cabi import FASTA_ROW, FASTQ_ROW, ScanStats, check, lib, ptr
 
+try:
+    from . import _fast                     # compiled bridge: per-object getters call the C-ABI without ctypes
+except ImportError:                         # pragma: no cover
+    _fast = None
+
 _engines = {}
 _lock = threading.Lock()
 
@@ -362,8 +367,20 @@ class Engine:
         n = e - s
         if n <= 0:
             return b""
+        if _fast is not None:
+            return _fast.extract_one(self.ctx.value, dfile.handle.value, drows.devptr, drows.n_rows, row_id, s, e, flags)
         buf = C.create_string_buffer(n)
         check(lib().fxg_extract_one_host(self.ctx, dfile.handle, drows.devptr, drows.n_rows, row_id, s, e, flags, buf, n))
+        return buf.raw
+
+    def read_one(self, dfile, drows, read_id, rlen, which=0, flags=0):
+        """sequence (which = 0) or quality (1) bytes of one read: one kernel launch, one synchronisation"""
+        if rlen <= 0:
+            return b""
+        if _fast is not None:
+            return _fast.read_one(self.ctx.value, dfile.handle.value, drows.devptr, drows.n_rows, read_id, which, flags, rlen)
+        buf = C.create_string_buffer(rlen)
+        check(lib().fxg_read_one_host(self.ctx, dfile.handle, drows.devptr, drows.n_rows, read_id, which, flags, rlen, buf, rlen))
         return buf.raw
 
     def reads(self, dfile, drows, ids, flags=0, want_seq=True, want_qual=True, rlens=None):

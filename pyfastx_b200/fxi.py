@@ -25,6 +25,11 @@ import numpy as np
 from . import _cabi
 from ._cabi import FASTA_ROW, FASTQ_ROW
 
+try:
+    from . import _fast
+except ImportError:                          # pragma: no cover
+    _fast = None
+
 
 def _text(b):
     # names are stored as raw bytes; bytes that are not UTF-8 are shown one-to-one (latin-1)
@@ -79,18 +84,19 @@ class PackedNames:
     def find(self, name):
         """0-based row of `name` (str or bytes) or -1"""
         L = _cabi.lib()
+        tab = self._table()
+        probe = (lambda b: _fast.name_find(tab.value, b)) if _fast is not None else (lambda b: L.fxg_nametab_find(tab, b, len(b)))
         if isinstance(name, str):
             for enc in ("utf-8", "latin-1"):
                 try:
                     b = name.encode(enc)
                 except UnicodeEncodeError:
                     continue
-                i = L.fxg_nametab_find(self._table(), b, len(b))
+                i = probe(b)
                 if i >= 0:
                     return i
             return -1
-        b = bytes(name)
-        return L.fxg_nametab_find(self._table(), b, len(b))
+        return probe(bytes(name))
 
     def lookup(self, names):
         """rows of many names at once (list of str/bytes, or a PackedNames) -> int64 array, -1 = absent"""

@@ -208,3 +208,27 @@ def test_fxi_interoperates_with_reference(tmp_path):
     fq = pyfastx.Fastq(oq)
     rq = ref.Fastq(oq)
     assert len(rq) == len(fq) == 800 and rq[5].seq == fq[5].seq and rq[799].qual == fq[799].qual
+
+
+def test_compiled_object_layer_keys_and_fastx(tmp_path):
+    """the object layer in use is the compiled CPython extension (PyInit_pyfastx); key views and the Fastx iterator"""
+    assert pyfastx.COMPILED and pyfastx.Fasta.__module__.endswith("pyfastx")
+    data = gzip.open(os.path.join(G.GOLD, "data", "test.fa.gz")).read()
+    case = [c for c in G.cases("fasta") if c["name"] == "test_fa"][0]
+    path = write(tmp_path, "t.fa", data)
+    fa = pyfastx.Fasta(path)
+    keys = fa.keys()
+    names = [r[1] for r in case["rows"]]
+    assert isinstance(keys, pyfastx.FastaKeys) and len(keys) == 211 and list(keys) == names
+    assert keys[0] == names[0] and keys[-1] == names[-1] and names[5] in keys and "nope" not in keys
+    recs = list(pyfastx.Fastx(path))
+    assert [r[0] for r in recs] == names and all(recs[i][1] == fa[i].seq for i in (0, 100, 210))
+    with_comment = list(pyfastx.Fastx(path, comment=True))
+    assert with_comment[0][2] == fa[0].description[len(names[0]) + 1:]
+    fq_case = [c for c in G.cases("fastq") if c["name"] == "test_fq"][0]
+    qpath = write(tmp_path, "t.fq", G.case_data(fq_case))
+    fq = pyfastx.Fastq(qpath)
+    recs = list(pyfastx.Fastx(qpath))
+    assert len(recs) == 800 and isinstance(fq.keys(), pyfastx.FastqKeys)
+    for q in fq_case["reads"][:10]:
+        assert recs[q["id"]][1] == q["seq"] and recs[q["id"]][2] == q["qual"] and recs[q["id"]][0] == fq[q["id"]].name

@@ -81,3 +81,20 @@ def test_synth_is_deterministic_and_well_formed():
     assert min(lines[3]) >= 35 and max(lines[3]) <= 70
     rid, s, e, minus = synth.random_queries(lens, 1000, seed=123)
     assert ((e - s) == 1000).all() and (s >= 0).all() and (e <= lens[rid]).all()
+
+
+def test_compiled_object_layer_is_a_cpython_extension():
+    """the object layer is a compiled extension module exporting PyInit_pyfastx with the reference's type names
+    (src/module.c:61-138); it must import without a GPU (compute calls then fail with NoDeviceError)"""
+    import ctypes
+    import importlib
+    import pyfastx_b200
+    mod = importlib.import_module("pyfastx_b200.pyfastx")
+    assert mod.__file__.endswith(".so") and pyfastx_b200.COMPILED
+    lib = ctypes.CDLL(mod.__file__)
+    assert hasattr(lib, "PyInit_pyfastx")
+    for name in ("Fasta", "Fastq", "Fastx", "Sequence", "Read", "FastaKeys", "FastqKeys", "version", "gzip_check",
+                 "reverse_complement"):
+        assert hasattr(mod, name) and getattr(pyfastx_b200, name) is getattr(mod, name)
+    fast = importlib.import_module("pyfastx_b200._fast")
+    assert fast.__file__.endswith(".so") and all(hasattr(fast, n) for n in ("extract_one", "read_one", "name_find"))
