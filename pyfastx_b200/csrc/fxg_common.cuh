@@ -64,7 +64,7 @@ struct fxg_ctx {
     size_t       pinned_bytes = 0;
     cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
     // scan scratch
-    FxgScratch   tile_desc, seg, cut, row_tmp, rows, counters, plan, misc, stage_file;
+    FxgScratch   tile_desc, seg, cut, row_tmp, rows, counters, params, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small
     void        *h_one = nullptr;        // pinned + mapped: output of single-query launches (fxg_extract_one_host)
     // measurement hooks

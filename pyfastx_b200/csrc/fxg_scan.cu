@@ -75,6 +75,7 @@ struct ScanTotals {     // device, 128 bytes; every phase-B kernel reads its siz
 static_assert(sizeof(ScanTotals) == 128, "ScanTotals layout");
 static_assert(sizeof(fxg_shard_info) == 128, "fxg_shard_info layout");
 
+struct ScanParams;
 struct ScanParams {
     const uint8_t *file;
     int64_t   n;            // bytes
@@ -96,6 +97,9 @@ struct ScanParams {
     int64_t   tmp_cap;      // slots
     fxg_fastq_row *qrows;   // FASTQ
     int64_t   qrows_cap;
+    const ScanParams *self; // the same struct in GLOBAL memory: the rare noinline paths take this pointer -- passing the
+                            // kernel parameter by reference made every thread copy all 200 bytes to its local memory
+                            // (r02 ncu: 1 GB of DRAM writes per 5 GB FASTQ came from that copy alone)
 };
 
 __device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
@@ -548,7 +552,9 @@ __device__ __forceinline__ void do_line(const ScanParams &P, int64_t first_line,
 // ---- the two newlines before region r (warp-uniform): walk back over the region records, 32 at a time.
 //      General path: long lines (more than ~60 KiB without a newline) and neighbours of dense regions. ----
 template <int MODE>
-__device__ __noinline__ void carry_walk(const ScanParams &P, int64_t r, Prev2 &cy) {
+__device__ __noinline__ Prev2 carry_walk(const ScanParams *Pg, int64_t r) {
+    const ScanParams &P = *Pg;
+    Prev2 cy;
     const int lane = threadIdx.x & 31;
     cy.pos1 = cy.pos0 = NOPOS; cy.h1 = cy.h0 = 0;
     int need = 2;
@@ -578,12 +584,15 @@ __device__ __noinline__ void carry_walk(const ScanParams &P, int64_t r, Prev2 &c
         q -= 1;
     }
     if (need > 0) push(-1, is_hdr_at<MODE>(P, 0));            // the virtual newline before byte 0
+    return cy;
 }
 
 // ---- dense region (more than SEGCAP newlines in 2 KiB): re-read the bytes; every lane owns 64 of them ----
 template <int MODE>
-__device__ __noinline__ void dense_region(const ScanParams &P, int64_t first_line, int64_t r, const Prev2 &cy, ulonglong2 exv,
-                                          unsigned long long &my_size) {
+__device__ __noinline__ unsigned long long dense_region(const ScanParams *Pg, int64_t first_line, int64_t r, Prev2 cy,
+                                                        ulonglong2 exv) {
+    const ScanParams &P = *Pg;
+    unsigned long long my_size = 0;
     const int lane = threadIdx.x & 31;
     const uint8_t *file = P.file;
     const int64_t b0 = r * REGION + lane * 64;
@@ -632,6 +641,7 @@ __device__ __noinline__ void dense_region(const ScanParams &P, int64_t first_lin
         hcount += hh; ++idx;
         pv.pos0 = pv.pos1; pv.h0 = pv.h1; pv.pos1 = x; pv.h1 = hh;
     }
+    return my_size;
 }
 
 // ---- the lines of one region with at most SEGCAP newlines, warp-cooperative: batches of 32 entries.
@@ -671,16 +681,18 @@ __device__ __forceinline__ void region_batches(const ScanParams &P, int64_t firs
 
 // ---- general path for one region: everything looked up from scratch ----
 template <int MODE>
-__device__ __noinline__ void full_region(const ScanParams &P, int64_t first_line, int64_t r, unsigned long long &my_size) {
+__device__ __noinline__ unsigned long long full_region(const ScanParams *Pg, int64_t first_line, int64_t r) {
+    const ScanParams &P = *Pg;
+    unsigned long long my_size = 0;
     const int lane = threadIdx.x & 31;
     const int nl = (int)(P.rc[r].x & 0xffffu);
-    if (nl == 0) return;
+    if (nl == 0) return 0;
     const ulonglong2 X = P.ex[r];
-    Prev2 cy;
-    carry_walk<MODE>(P, r, cy);
+    Prev2 cy = carry_walk<MODE>(Pg, r);
     if (MODE != 0) cy.h1 = cy.h0 = 0;
     if (nl <= SEGCAP) region_batches<MODE>(P, first_line, r, nl, cy, X, P.seg[r * SEGCAP + lane], P.seg[r * SEGCAP + 32 + lane], my_size);
-    else dense_region<MODE>(P, first_line, r, cy, X, my_size);
+    else my_size += dense_region<MODE>(Pg, first_line, r, cy, X);
+    return my_size;
 }
 
 constexpr int LG = 4;     // consecutive regions per warp of the lines kernel (all their loads in flight together)
@@ -748,11 +760,11 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) lines_kernel(const ScanParams
                 }
             } else if (window_hits_start) { cy.pos1 = -1; cy.h1 = is_hdr_at<MODE>(P, 0); }
             else slow = true;
-            if (slow) carry_walk<MODE>(P, r, cy);
+            if (slow) cy = carry_walk<MODE>(P.self, r);
             if (MODE != 0) cy.h1 = cy.h0 = 0;
         }
         if (nl <= SEGCAP) region_batches<MODE>(P, first_line, r, nl, cy, X[i], E[i][0], E[i][1], my_size);
-        else dense_region<MODE>(P, first_line, r, cy, X[i], my_size);
+        else my_size += dense_region<MODE>(P.self, first_line, r, cy, X[i]);
     }
 
     if (MODE == 1) {
@@ -799,7 +811,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
     const uint32_t densem = __ballot_sync(0xffffffffu, nll > (uint32_t)SEGCAP);
     if (densem & (((1u << RG) - 1u) << 1)) {                       // a dense region inside the span
         for (int i = 0; i < RG; ++i)
-            if (r0 + i < P.nreg) full_region<1>(P, first_line, r0 + i, my_size);
+            if (r0 + i < P.nreg) my_size += full_region<1>(P.self, first_line, r0 + i);
     } else {
         const uint64_t ex0 = (uint64_t)shfl_i64((int64_t)exl, 1);    // lines before the span
         // ---- flatten the window ----
@@ -851,7 +863,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fastq_records_kernel(const Sc
             else if (pn >= 1 && pn <= (uint32_t)SEGCAP) {
                 carry = (r0 - 1) * REGION + (int64_t)(py & E_POS);
                 if (FXG_MARK_CUT) carry_cut = P.cut[(r0 - 1) * SEGCAP + (pn - 1)];
-            } else { Prev2 cy; carry_walk<1>(P, r0, cy); carry = cy.pos1; }
+            } else carry = carry_walk<1>(P.self, r0).pos1;
         }
         const int64_t span_base = r0 * REGION;
         auto POS = [&](int f) -> int64_t { return f < 0 ? carry : span_base + (int64_t)(flat[f] & 0x7fffu); };
@@ -999,7 +1011,7 @@ __global__ void __launch_bounds__(MARK_WARPS * 32) fasta_lines_kernel(const Scan
     while (fm) {
         const int f = __ffs(fm) - 1;
         fm &= fm - 1;
-        full_region<0>(P, 0, R0 + f, dummy);
+        full_region<0>(P.self, 0, R0 + f);
     }
 }
 
@@ -1296,8 +1308,17 @@ extern "C" int fxg_scan_begin(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t
     return FXG_OK;
 }
 
-static int launch_phase_b(fxg_ctx *ctx, const ScanParams &P, int mode, int64_t tmp_slots, const fxg_shard_info *d_all,
+static int launch_phase_b(fxg_ctx *ctx, const ScanParams &P0, int mode, int64_t tmp_slots, const fxg_shard_info *d_all,
                           int nranks, int rank) {
+    // the parameter block also goes to global memory (P.self) for the rare noinline paths of the rows kernels
+    int rc0 = ctx->params.reserve(512);
+    if (rc0) return rc0;
+    if (!ctx->h_counters) FXG_CUDA(cudaHostAlloc(&ctx->h_counters, 8192, cudaHostAllocDefault));
+    ScanParams P = P0;
+    P.self = (const ScanParams *)ctx->params.ptr;
+    static_assert(sizeof(ScanParams) <= 512, "ScanParams staging");
+    memcpy((uint8_t *)ctx->h_counters + 4096, &P, sizeof(P));
+    FXG_CUDA(cudaMemcpyAsync(ctx->params.ptr, (uint8_t *)ctx->h_counters + 4096, sizeof(P), cudaMemcpyHostToDevice, ctx->stream));
     const int64_t nreg = P.nreg;
     {
         FxgProfScope prof(ctx, FXG_PROF_LINES, 3);
@@ -1341,7 +1362,7 @@ extern "C" int fxg_scan_finish(fxg_ctx *ctx, const fxg_shard_info *d_all, int nr
     if (!d_all) { FXG_CHECK_ARG(nranks == 1, "d_all == NULL with more than one rank"); d_all = own_info(ctx); }
     memset(stats, 0, sizeof(*stats));
     if (d_rows_out) *d_rows_out = nullptr;
-    if (!ctx->h_counters) FXG_CUDA(cudaHostAlloc(&ctx->h_counters, 4096, cudaHostAllocDefault));
+    if (!ctx->h_counters) FXG_CUDA(cudaHostAlloc(&ctx->h_counters, 8192, cudaHostAllocDefault));
     FXG_CHECK_ARG((size_t)nranks * sizeof(fxg_shard_info) + 256 <= 4096 || !all_host, "too many ranks for all_host");
     ScanTotals *ht = (ScanTotals *)ctx->h_counters;
     fxg_shard_info *hall = (fxg_shard_info *)((uint8_t *)ctx->h_counters + 256);
