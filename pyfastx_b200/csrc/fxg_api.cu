@@ -53,7 +53,7 @@ extern "C" int fxg_device_count(void) {
     return n;
 }
 
-static const size_t PINNED_CHUNK = (size_t)64 << 20;
+static const size_t PINNED_CHUNK = (size_t)128 << 20;
 
 extern "C" int fxg_ctx_create(int device, fxg_ctx **out) {
     FXG_CHECK_ARG(out, "out == NULL");
@@ -256,7 +256,7 @@ extern "C" int fxg_file_from_host(fxg_ctx *c, const void *host, int64_t nbytes, 
 }
 
 // bytes [begin, end) of `path` (end < 0: to the end of the file) -> a device buffer of their own:
-// 8 pread threads fill two 64 MiB pinned buffers in turn while the copy engine drains the other
+// up to 32 pread threads fill two 128 MiB pinned buffers in turn while the copy engine drains the other
 static int stage_path_range(fxg_ctx *c, const char *path, int64_t begin, int64_t end, fxg_file **out) {
     FXG_CHECK_ARG(c && path && out && begin >= 0, "bad arguments");
     *out = nullptr;
