@@ -939,25 +939,14 @@ BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b00030000000000000000
 
 
 def bgzf_compress(host, level, workers):
-    import struct
-    import zlib
-    n = host.size
-    nblk = (n + BGZF_BLOCK - 1) // BGZF_BLOCK
-    out = [None] * nblk
-    mv = memoryview(host)
-
-    def work(k):
-        for b in range(k, nblk, workers):
-            chunk = mv[b * BGZF_BLOCK:min(n, (b + 1) * BGZF_BLOCK)]
-            co = zlib.compressobj(level, zlib.DEFLATED, -15)
-            comp = co.compress(chunk) + co.flush()
-            out[b] = (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25)
-                      + comp + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
-
-    with ThreadPoolExecutor(workers) as ex:
-        list(ex.map(work, range(workers)))
-    out.append(BGZF_EOF)
-    return np.frombuffer(b"".join(out), dtype=np.uint8)
+    """the C2 bytes as BGZF, by all host threads (fxg_bgzf_compress_host: zlib deflate per 0xff00-byte block)"""
+    from pyfastx_b200 import _cabi
+    L = _cabi.lib()
+    out, n = C.c_void_p(), C.c_int64(0)
+    _cabi.check(L.fxg_bgzf_compress_host(host.ctypes.data, host.size, level, C.byref(out), C.byref(n)))
+    z = np.frombuffer((C.c_uint8 * n.value).from_address(out.value), dtype=np.uint8).copy()
+    L.fxg_free_host(out)
+    return z
 
 
 def run_bgzf(c, args, dfile_plain, rows_plain, drows, host_file, result):

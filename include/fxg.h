@@ -368,6 +368,10 @@ int64_t fxg_nametab_find(const fxg_nametab *t, const uint8_t *name, int64_t len)
 int     fxg_nametab_lookup(const fxg_nametab *t, const uint8_t *q, const int64_t *q_off, int64_t nq, int64_t *ids_out);
 void    fxg_nametab_free(fxg_nametab *t);
 
+/* BGZF writer (bench / test tooling only: the image has no bgzip): 0xff00-byte blocks, raw deflate at `level`, all host
+ * threads; *out is malloc'ed (fxg_free_host). */
+int fxg_bgzf_compress_host(const void *data, int64_t nbytes, int level, uint8_t **out, int64_t *out_len);
+
 /* ---- synthetic inputs generated directly in HBM (bench / test tooling) -------------------
  * Byte-identical to pyfastx_b200/synth.py.  rec_off has n_records+1 entries (device). */
 int fxg_synth_fasta_dev(fxg_ctx *ctx, uint64_t seed, const int64_t *d_lengths, const int64_t *d_rec_off,

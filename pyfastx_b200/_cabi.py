@@ -137,6 +137,7 @@ SIGNATURES = {
     "fxg_nametab_find": (i64, [vp, C.c_char_p, i64]),
     "fxg_nametab_lookup": (i32, [vp, vp, vp, i64, vp]),
     "fxg_nametab_free": (None, [vp]),
+    "fxg_bgzf_compress_host": (i32, [vp, i64, i32, P(vp), P(i64)]),
     "fxg_synth_fasta_dev": (i32, [vp, u64, vp, vp, i64, i64, i32, vp]),
     "fxg_synth_fastq_dev": (i32, [vp, u64, i64, i64, i32, vp, vp]),
 }

@@ -125,3 +125,66 @@ extern "C" void fxg_gzip_free(fxg_gzip_result *r) {
     free(r->data);
     delete r;
 }
+
+// ---- BGZF writer (bench / test tooling: the image has no bgzip) ------------------------------------------
+// `data` is cut into 0xff00-byte blocks, each deflated on its own (raw deflate, `level`) into a gzip member with the
+// 'BC' extra field, by all host threads; an empty EOF member ends the file.  *out is malloc'ed (fxg_free_host).
+#include <thread>
+#include <atomic>
+extern "C" int fxg_bgzf_compress_host(const void *data, int64_t nbytes, int level, uint8_t **out, int64_t *out_len) {
+    if ((!data && nbytes) || nbytes < 0 || !out || !out_len) { fxg_set_error("invalid argument: fxg_bgzf_compress_host"); return FXG_EINVAL; }
+    const int64_t BLOCK = 0xff00;
+    const int64_t nblk = (nbytes + BLOCK - 1) / BLOCK;
+    const size_t bound = 18 + compressBound((uLong)BLOCK) + 8 + 64;
+    std::vector<uint32_t> sizes((size_t)nblk, 0);
+    uint8_t *scratch = (uint8_t *)malloc((size_t)nblk * bound + 64);
+    if (!scratch) { fxg_set_error("out of memory (bgzf scratch)"); return FXG_ENOMEM; }
+    unsigned T = std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 128) T = 128;
+    if ((int64_t)T > nblk) T = (unsigned)(nblk > 0 ? nblk : 1);
+    std::atomic<int64_t> next(0);
+    std::atomic<int> bad(0);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&] {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+            for (;;) {
+                const int64_t b = next.fetch_add(1);
+                if (b >= nblk) break;
+                const uint8_t *src = (const uint8_t *)data + b * BLOCK;
+                const int64_t len = nbytes - b * BLOCK < BLOCK ? nbytes - b * BLOCK : BLOCK;
+                uint8_t *dst = scratch + (size_t)b * bound;
+                static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+                memcpy(dst, hdr, 16);
+                deflateReset(&zs);
+                zs.next_in = const_cast<Bytef *>(src); zs.avail_in = (uInt)len;
+                zs.next_out = dst + 18; zs.avail_out = (uInt)(bound - 18 - 8);
+                if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { bad = 1; break; }
+                const uint32_t clen = (uint32_t)zs.total_out;
+                const uint32_t total = 18 + clen + 8;
+                if (total > 65536) { bad = 1; break; }
+                dst[16] = (uint8_t)((total - 1) & 0xff); dst[17] = (uint8_t)((total - 1) >> 8);
+                const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)len);
+                uint8_t *tl = dst + 18 + clen;
+                for (int i = 0; i < 4; ++i) { tl[i] = (uint8_t)(crc >> (8 * i)); tl[4 + i] = (uint8_t)((uint32_t)len >> (8 * i)); }
+                sizes[(size_t)b] = total;
+            }
+            deflateEnd(&zs);
+        });
+    for (auto &x : th) x.join();
+    if (bad) { free(scratch); fxg_set_error("deflate failed"); return FXG_EFORMAT; }
+    int64_t total = 28;
+    for (int64_t b = 0; b < nblk; ++b) total += sizes[(size_t)b];
+    uint8_t *o = (uint8_t *)malloc((size_t)total);
+    if (!o) { free(scratch); fxg_set_error("out of memory (bgzf output)"); return FXG_ENOMEM; }
+    int64_t p = 0;
+    for (int64_t b = 0; b < nblk; ++b) { memcpy(o + p, scratch + (size_t)b * bound, sizes[(size_t)b]); p += sizes[(size_t)b]; }
+    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    memcpy(o + p, eof, 28);
+    free(scratch);
+    *out = o; *out_len = total;
+    return FXG_OK;
+}
