@@ -354,7 +354,7 @@ class Fasta:
 
     def __getitem__(self, key):
         i = self._row_id(key)
-        return Sequence(self, i, 0, int(self._rows["slen"][i]), True)
+        return Sequence(self, i, 0, int(self._rows["slen"][i]), True, report_end=False)
 
     def __iter__(self):
         self._need_index()
@@ -556,12 +556,14 @@ class Fasta:
 class Sequence:
     """A record or a slice of one (reference src/sequence.c).  start/end are 1-based inclusive."""
 
-    def __init__(self, fasta, row_id, s, e, complete):
+    def __init__(self, fasta, row_id, s, e, complete, report_end=True):
         self._fa, self.id = fasta, row_id + 1
         self._i, self._s, self._e = row_id, s, e
         self._complete = complete
         self.name = fasta._names.get(row_id)
-        self.start, self.end = s + 1, e
+        # reference quirk Q10 (SURVEY 8a), reproduced: a whole record obtained by index or name reports end = 0
+        # (src/index.c:482-483); only the iterator sets end = seq_len (src/index.c:522); slices report s + 1 .. e
+        self.start, self.end = s + 1, (e if report_end else 0)
 
     def __len__(self):
         return self._e - self._s
