@@ -927,6 +927,24 @@ def run_fastq(c, args, result):
                         if os.path.exists(p):
                             os.unlink(p)
             del host
+            # the step after the scan: names gathered on the GPU + the native .fxi writer on all rows of the file
+            if c.world == 1 and not args.skip_e2e:
+                from pyfastx_b200 import fxi
+                t0 = time.perf_counter()
+                blob, noff = eng.gather_ranges(dfile, rows["soff"] - rows["dlen"] - q0, rows["nlen"].astype(np.int64))
+                t1 = time.perf_counter()
+                wp = os.path.join(shm_dir(), "fxg_bench_%d.fq.fxi" % os.getpid())
+                con = fxi.write_fastq_index_packed(wp, rows, blob, noff, 4 * R, int(st["total_len"]))
+                t2 = time.perf_counter()
+                nchk = con.execute("SELECT COUNT(1) FROM read").fetchone()[0]
+                probe = con.execute("SELECT ID FROM read WHERE name=?", ("read%d" % (R // 2 + 1),)).fetchall()
+                con.close()
+                assert nchk == n_rows and probe == [(R // 2 + 1,)]
+                rec["fxi_write"] = {"rows": int(n_rows), "names_gather_seconds": t1 - t0, "write_seconds": t2 - t1,
+                                    "rows_per_s": n_rows / (t2 - t1), "file_bytes": os.path.getsize(wp),
+                                    "api": "fxg_fxi_write_fastq (read table + UNIQUE readidx, SQLite pages written directly)"}
+                os.unlink(wp)
+                del blob, noff
         else:
             rec["parity"] = {"skipped": "host memory: %.0f GB available" % (avail / 1e9)}
     result["fastq"] = rec
