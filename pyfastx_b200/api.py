@@ -100,7 +100,12 @@ class _Staged:
                 view, self.gzindex, self._gz_handle = self.engine.gzip_inflate(comp)
                 self.dfile = self.engine.stage_bytes(view)
         else:
+            import time as _t
+            t0 = _t.perf_counter()
             self.dfile = self.engine.stage_path(path)
+            if os.environ.get("FXG_TIMING"):
+                import sys as _s
+                print("[fxg timing] stage_path %.3f s (%.2f GB)" % (_t.perf_counter() - t0, self.dfile.size / 1e9), file=_s.stderr)
 
     def first_non_space(self):
         head = self.dfile.download(0, min(self.dfile.size, 1 << 16))
@@ -293,12 +298,19 @@ class Fasta:
         return fxi.PackedNames.from_list([str(self.key_func(h.decode("latin-1"))).encode("utf-8") for h in hdrs])
 
     def _scan_and_write(self, index_file):
+        import time as _t
         eng = self._st.engine
+        t0 = _t.perf_counter()
         rows, st = eng.fasta_scan(self._st.dfile, full_name=self.full_name)
+        t1 = _t.perf_counter()
         self._names = self._scan_names(rows)
+        t2 = _t.perf_counter()
         self._rows, self._total = rows, int(st["total_len"])
         self._con = fxi.write_fasta_index_packed(index_file, rows, self._names.blob, self._names.off, self._total,
                                                  gz=self._st.gzindex)
+        if os.environ.get("FXG_TIMING"):
+            import sys as _s
+            print("[fxg timing] scan %.3f s, names %.3f s, fxi %.3f s" % (t1 - t0, t2 - t1, _t.perf_counter() - t2), file=_s.stderr)
 
     def _verify_loaded_index(self):
         """A loaded .fxi carries no line-uniformity bits; one GPU scan (milliseconds) recovers them and doubles
