@@ -53,7 +53,7 @@ extern "C" int fxg_device_count(void) {
     return n;
 }
 
-static const size_t PINNED_CHUNK = (size_t)128 << 20;
+static const size_t PINNED_CHUNK = (size_t)256 << 20;
 
 extern "C" int fxg_ctx_create(int device, fxg_ctx **out) {
     FXG_CHECK_ARG(out, "out == NULL");
@@ -277,7 +277,7 @@ static int stage_path_range(fxg_ctx *c, const char *path, int64_t begin, int64_t
         cudaEventSynchronize(c->pinned_ev[which]);
         // parallel pread into the pinned chunk
         unsigned nt = std::thread::hardware_concurrency();
-        if (nt > 32) nt = 32;                                  // page-cache copies: ~1.5 GB/s per thread; PCIe wants ~50 GB/s
+        if (nt > 48) nt = 48;                                  // page-cache copies: ~1.5 GB/s per thread; PCIe wants ~50 GB/s
         if (nt < 1 || len < ((int64_t)8 << 20)) nt = 1;
         std::atomic<int> bad(0);
         std::vector<std::thread> th;

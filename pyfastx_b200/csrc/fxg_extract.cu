@@ -345,6 +345,8 @@ __device__ void serve_query_warp(const uint8_t *__restrict__ file, int64_t fsize
     job.src = 0; job.src_len = 0;
     job.out_len = e > s ? e - s : 0;
     bool done = false;
+    // rows come from a scan or from a loaded .fxi: offsets that point outside the buffer never reach a load
+    row_ok = row_ok && r.boff >= 0 && r.blen >= 0 && r.boff <= fsize && s >= 0;
     if (row_ok && job.out_len > 0) {
         const int64_t bpl = r.llen - (int64_t)r.elen;
         const bool whole = (s == 0 && e == r.slen);
@@ -596,59 +598,24 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
             const uint32_t nwords = (total + 15u) >> 4, hi_last = total & 15u;
             const uint32_t w_begin = a ? 1u : 0u, w_end = nwords - (hi_last ? 1u : 0u);
             uint8_t *dst0 = dst - a;                                     // 16-byte aligned
-            // ---- pass 1: interior words that lie on one source line (4 of 5 for 80-column lines): no merge code.
-            //      Loads are issued for all XU words of the step before any is used (break words load too: the
-            //      addresses are valid, and an unconditional load keeps all of them in flight together) ----
+            // interior words: all 16 slots belong to the query
+            // (XU words per lane and step: 6 * XU loads in flight)
             for (uint32_t w = w_begin + (uint32_t)li; w < w_end; w += XU * QG) {
                 WordReq rq[XU];
-                uint32_t WW[XU][5], o[4];
+                uint32_t WW[XU][6], o[4];
 #pragma unroll
                 for (int u = 0; u < XU; ++u) {
                     const uint32_t wu = w + u * QG;
                     rq[u] = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, 16u * (wu < w_end ? wu : w) - a);
                 }
 #pragma unroll
-                for (int u = 0; u < XU; ++u) {
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) WW[u][i] = __ldg(rq[u].wp + i);
-                }
+                for (int u = 0; u < XU; ++u) ow_load(rq[u], WW[u]);
 #pragma unroll
                 for (int u = 0; u < XU; ++u) {
                     const uint32_t wu = w + u * QG;
-                    if (wu < w_end && rq[u].c >= 16u) {
-                        if (!ow_finish_line(WW[u], rq[u].o1, rev, upper, comp, s_lut, o)) bad = true;
+                    if (u == 0 || wu < w_end) {
+                        if (!ow_finish(WW[u], rq[u], elen, rev, upper, comp, s_lut, o)) bad = true;
                         *reinterpret_cast<uint4 *>(dst0 + 16u * wu) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-            }
-            // ---- pass 2: the interior words that contain a line break, found by walking the breaks of the query:
-            //      break j sits in front of kept rank R_j = (bpl - rem_s) + j * bpl; XB of them per lane and step,
-            //      all loads first ----
-            {
-                constexpr int XB = 4;
-                const uint32_t first_r = bpl - rem_s;
-                for (uint32_t rj0 = first_r + (uint32_t)li * bpl; rj0 < out_len; rj0 += XB * QG * bpl) {
-                    WordReq re[XB];
-                    uint32_t WE[XB][6], o[4], wv[XB];
-                    bool takeb[XB];
-#pragma unroll
-                    for (int u = 0; u < XB; ++u) {
-                        const uint32_t rj = rj0 + (uint32_t)u * QG * bpl;
-                        const bool in = rj < out_len;
-                        const uint32_t bpos = a + (rev ? out_len - (in ? rj : rj0) : (in ? rj : rj0));   // where the next segment starts
-                        wv[u] = bpos >> 4;
-                        takeb[u] = in && (bpos & 15u) != 0u && wv[u] >= w_begin && wv[u] < w_end;
-                        re[u] = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, 16u * (takeb[u] ? wv[u] : w_begin) - a);
-                    }
-                    if (w_begin < w_end) {
-#pragma unroll
-                        for (int u = 0; u < XB; ++u) ow_load(re[u], WE[u]);
-#pragma unroll
-                        for (int u = 0; u < XB; ++u)
-                            if (takeb[u]) {
-                                if (!ow_finish(WE[u], re[u], elen, rev, upper, comp, s_lut, o)) bad = true;
-                                *reinterpret_cast<uint4 *>(dst0 + 16u * wv[u]) = make_uint4(o[0], o[1], o[2], o[3]);
-                            }
                     }
                 }
             }
@@ -747,7 +714,7 @@ __global__ void __launch_bounds__(XTHREADS) reads_kernel(
         const int64_t id = ids[q];
         if (id < 0 || id >= n_rows) continue;
         const fxg_fastq_row r = rows[id];
-        if (r.rlen <= 0) continue;
+        if (r.rlen <= 0 || r.soff < 0 || r.qoff < 0 || r.soff > fsize || r.qoff > fsize) continue;   // untrusted rows (loaded .fxi)
         const bool fast = r.rlen < (1ll << 30) && r.soff + r.rlen + 32 <= capacity && r.qoff + r.rlen + 32 <= capacity &&
                           r.soff >= 0 && r.qoff >= 0;
         GatherJob job;
