@@ -158,6 +158,9 @@ int      fxg_file_download(fxg_ctx *ctx, const fxg_file *f, int64_t src_off, voi
 void    *fxg_file_devptr(const fxg_file *f);
 int64_t  fxg_file_size(const fxg_file *f);
 void     fxg_file_free(fxg_file *f);
+/* fxg_file_free keeps ONE spare device buffer per device for the next fxg_file_alloc that fits (cudaMalloc / cudaFree of
+ * a 10 GB buffer cost ~0.1 s each); fxg_pool_trim returns the spares to the driver.  FXG_FILE_POOL=0 disables the pool. */
+void     fxg_pool_trim(void);
 
 /* ---- K1: FASTA index scan -----------------------------------------------------------------
  * Replaces the scan loop of pyfastx_create_index (src/index.c:226-361) over

@@ -93,6 +93,7 @@ SIGNATURES = {
     "fxg_file_devptr": (vp, [vp]),
     "fxg_file_size": (i64, [vp]),
     "fxg_file_free": (None, [vp]),
+    "fxg_pool_trim": (None, []),
     "fxg_fasta_scan": (i32, [vp, vp, i64, i32, P(vp), P(ScanStats)]),
     "fxg_fastq_scan": (i32, [vp, vp, i64, P(vp), P(ScanStats)]),
     "fxg_scan_begin": (i32, [vp, vp, i32, i64, i32, vp]),

@@ -39,7 +39,8 @@ struct FxgScratch {
 struct fxg_file {
     uint8_t *d = nullptr;   // device bytes; buffer capacity >= size rounded up to FXG_FILE_PAD
     int64_t  size = 0;
-    int64_t  capacity = 0;
+    int64_t  capacity = 0;   // logical capacity (zero padded up to here)
+    int64_t  alloc_cap = 0;  // bytes really allocated (a pooled buffer may be larger than `capacity`)
     bool     owned = false;
     int      device = 0;
 };
@@ -63,6 +64,8 @@ struct fxg_ctx {
     void        *pinned[2] = {nullptr, nullptr};
     size_t       pinned_bytes = 0;
     cudaEvent_t  pinned_ev[2] = {nullptr, nullptr};
+    void        *ring = nullptr;         // pinned ring of the path stager (32 x 16 MiB), one event per slot
+    cudaEvent_t  ring_ev[32] = {};
     // scan scratch
     FxgScratch   tile_desc, seg, cut, row_tmp, rows, counters, params, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small

@@ -16,6 +16,7 @@
 // 16-byte stores; only the ragged first/last words of a round use byte stores.
 #include "fxg_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace fxg {
 
@@ -673,6 +674,277 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
     }
 }
 
+// ---- bulk-copy pull path: the covering source range of every 1 KiB output piece travels global -> shared memory
+//      as ONE 1-D TMA bulk copy (cp.async.bulk, completion counted on an mbarrier), several pieces in flight per warp ----
+// ncu on the 4-lanes-per-query kernel (profiles/r02_extract_group_ncu.txt): the L1 data pipe was the limiter
+// (l1tex__data_pipe_lsu_wavefronts 78 % of peak: six 4-byte loads per 16 output bytes, each touching eight different
+// cache lines for the eight queries of a warp), not DRAM (45 %).  Here the file bytes never pass through the load/store
+// unit as global loads: the TMA engine writes them to shared memory, every lane assembles its aligned 16-byte output
+// words from two conflict-free 16-byte shared-memory loads, and a warp's stores are 512 contiguous bytes.
+//   * a warp owns a batch of `bq` queries (one per lane: descriptor + index row in registers);
+//   * a query is cut into items of BK_WORDS aligned output words; items of the batch are enumerated in order and run
+//     through a ring of BK_NS slots per warp: the lane that owns the query computes the covering, 16-byte aligned source
+//     range (slice formula, sequence.c:498-510) and issues the bulk copy; all lanes consume;
+//   * the layout assumption is verified on every word exactly as in the group kernel; failures and queries that do not
+//     qualify (norm = 0, odd lines, < 16 bytes, RAW ...) are redone by the general strip path.
+#ifndef FXG_BK_NS
+#define FXG_BK_NS 4
+#endif
+#ifndef FXG_BK_FENCE
+#define FXG_BK_FENCE 0                         // the slot's readers are ordered before the refill by __syncwarp (their
+#endif                                         // loads feed the stores issued before it); no proxy fence needed for a WAR
+constexpr int BK_NS = FXG_BK_NS;               // slots (items in flight) per warp
+constexpr int BK_WORDS = 64;                   // aligned 16-byte output words per item
+constexpr int BK_OUT = BK_WORDS * 16;          // output bytes per item
+constexpr int BK_SLOT = 1280;                  // >= BK_OUT + 16 (ragged-word reach) + 2 * ((BK_OUT + 16) / 16 + 2) + 30 + 16
+constexpr size_t BK_SMEM = (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 16 + 3 * 256 + (size_t)XWARPS * XSTAGE;
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <bool WANT_ACGT>
+__global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
+    const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fasta_row *__restrict__ rows,
+    int64_t n_rows, const int64_t *__restrict__ q_row, const int64_t *__restrict__ q_s,
+    const int64_t *__restrict__ q_e, const int32_t *__restrict__ q_flags, int64_t nq,
+    const int64_t *__restrict__ out_off, uint8_t *__restrict__ out, int64_t *__restrict__ acgt, int bq) {
+    extern __shared__ __align__(128) uint8_t bk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *slots = bk_smem + (size_t)warp * BK_NS * BK_SLOT;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT) + warp * BK_NS;
+    int2 *infos = reinterpret_cast<int2 *>(bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 8) + warp * BK_NS;
+    uint8_t (*s_lut)[256] = reinterpret_cast<uint8_t (*)[256]>(bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 16);
+    uint8_t *stage = bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 16 + 3 * 256 + (size_t)warp * XSTAGE;
+    init_luts(s_lut);
+    if (lane < BK_NS) mbar_init(&bars[lane], 1);
+    mbar_fence_init();
+    __syncthreads();
+    uint32_t it_issue = 0, it_cons = 0;                     // items issued / consumed by this warp since the launch
+    const int64_t step = (int64_t)gridDim.x * XWARPS * bq;
+    for (int64_t qb = ((int64_t)blockIdx.x * XWARPS + warp) * bq; qb < nq; qb += step) {
+        const int64_t q = qb + lane;
+        const bool valid = lane < bq && q < nq;
+        int64_t rid = -1, s = 0, e = 0, off = 0;
+        int flags = 0;
+        if (valid) { rid = q_row[q]; s = q_s[q]; e = q_e[q]; off = out_off[q]; flags = q_flags ? q_flags[q] : 0; }
+        const bool row_ok = rid >= 0 && rid < n_rows;
+        union RowU { fxg_fasta_row r; uint4 v[3]; } ru;
+        ru.v[0] = ru.v[1] = ru.v[2] = make_uint4(0, 0, 0, 0);
+        if (row_ok) {
+            const uint4 *p4 = reinterpret_cast<const uint4 *>(rows + rid);
+            ru.v[0] = p4[0]; ru.v[1] = p4[1]; ru.v[2] = p4[2];
+        }
+        const fxg_fasta_row &r = ru.r;
+        const int64_t out_len64 = e > s ? e - s : 0;
+        const int64_t bpl64 = r.llen - (int64_t)r.elen;
+        const bool fast = row_ok && out_len64 >= 16 && out_len64 < (1ll << 30) && r.norm && (r.pad[0] & 1) != 0 &&
+                          bpl64 >= 16 && bpl64 < (1ll << 30) && s >= 0 && s < (1ll << 32) && e <= r.slen &&
+                          r.boff >= 0 && r.boff + r.blen + 32 <= capacity && !(flags & FXG_X_RAW);
+        // per-lane constants of the lane's own query
+        uint32_t bpl = 16, out_len = 0, rem_s = 0, inv = 0, pk = 0;
+        const uint8_t *fq = file;
+        uint8_t *dst0 = out;
+        int np = 0;
+        if (fast) {
+            bpl = (uint32_t)bpl64; out_len = (uint32_t)out_len64;
+            const uint32_t q_s32 = (uint32_t)s / bpl;
+            rem_s = (uint32_t)s - q_s32 * bpl;
+            inv = (uint32_t)(0x100000000ull / bpl);
+            fq = file + r.boff + s + (int64_t)r.elen * (int64_t)q_s32;
+            uint8_t *dst = out + off;
+            const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15);
+            dst0 = dst - a;
+            pk = a | ((uint32_t)r.elen << 4) | ((flags & FXG_X_REVERSE) ? 0x100u : 0u) | ((flags & FXG_X_UPPER) ? 0x200u : 0u) |
+                 ((flags & FXG_X_COMPLEMENT) ? 0x400u : 0u);
+            np = (int)((((a + out_len + 15u) >> 4) + BK_WORDS - 1) / BK_WORDS);
+        }
+        int incl = np;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o2 = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o2;
+        }
+        const int base = incl - np;
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t badmask = 0;
+
+        auto issue = [&](int t) {
+            const uint32_t m = __ballot_sync(0xffffffffu, np > 0 && base <= t);
+            const int j = 31 - __clz(m);
+            const int slot = (int)(it_issue % BK_NS);
+            if (lane == j) {
+                const int p = t - base;
+                const int a = (int)(pk & 15u), elen = (int)((pk >> 4) & 15u);
+                int olo = p * BK_OUT - a - 16, ohi = p * BK_OUT + BK_OUT - a;
+                if (olo < 0) olo = 0;
+                if (ohi > (int)out_len) ohi = (int)out_len;
+                const bool rev = (pk & 0x100u) != 0;
+                const uint32_t ra = rev ? out_len - (uint32_t)ohi : (uint32_t)olo;
+                const uint32_t rb1 = (rev ? out_len - (uint32_t)olo : (uint32_t)ohi) - 1u;      // last kept rank of the item
+                uint32_t t1 = rem_s + ra, d1 = __umulhi(t1, inv);
+                if (t1 - d1 * bpl >= bpl) ++d1;
+                uint32_t t2 = rem_s + rb1, d2 = __umulhi(t2, inv);
+                if (t2 - d2 * bpl >= bpl) ++d2;
+                const int rel1 = (int)(ra + (uint32_t)elen * d1), rel2 = (int)(rb1 + (uint32_t)elen * d2) + 1;
+                const int fqa = (int)(reinterpret_cast<uintptr_t>(fq) & 15);
+                const int g0 = rel1 - ((fqa + rel1) & 15);
+                const int g1 = rel2 + ((16 - ((fqa + rel2) & 15)) & 15);
+                uint32_t bytes = (uint32_t)(g1 - g0);
+                if (bytes > (uint32_t)(BK_SLOT - 16)) bytes = (uint32_t)(BK_SLOT - 16);       // cannot happen (BK_SLOT bound)
+                infos[slot] = make_int2(g0, j);
+#if FXG_BK_FENCE
+                fence_proxy_async();
+#endif
+                mbar_expect_tx(&bars[slot], bytes);
+                tma_load_1d(slots + (size_t)slot * BK_SLOT, fq + g0, bytes, &bars[slot]);
+            }
+            ++it_issue;
+        };
+
+        for (int t = 0; t < T && t < BK_NS; ++t) issue(t);
+        __syncwarp();
+        int cntA = 0, cntC = 0, cntG = 0, cntT = 0;
+        for (int t = 0; t < T; ++t) {
+            const int slot = (int)(it_cons % BK_NS);
+            const uint32_t parity = (it_cons / BK_NS) & 1u;
+            ++it_cons;
+            {
+                uint32_t spins = 0;
+                while (!mbar_try_wait(&bars[slot], parity))
+                    if (++spins > (1u << 22)) __trap();      // a lost completion must not hang the device
+            }
+            const int2 inf = infos[slot];
+            const int j = inf.y, base_rel = inf.x;
+            const uint32_t j_bpl = __shfl_sync(0xffffffffu, bpl, j), j_inv = __shfl_sync(0xffffffffu, inv, j);
+            const uint32_t j_rem = __shfl_sync(0xffffffffu, rem_s, j), j_len = __shfl_sync(0xffffffffu, out_len, j);
+            const uint32_t j_pk = __shfl_sync(0xffffffffu, pk, j);
+            const int p = t - __shfl_sync(0xffffffffu, base, j);
+            const int j_np = __shfl_sync(0xffffffffu, np, j);
+            uint8_t *j_dst0 = reinterpret_cast<uint8_t *>(shfl_i64((int64_t)reinterpret_cast<uintptr_t>(dst0), j));
+            const uint32_t a = j_pk & 15u;
+            const int elen = (int)((j_pk >> 4) & 15u);
+            const bool rev = (j_pk & 0x100u) != 0, upper = (j_pk & 0x200u) != 0, comp = (j_pk & 0x400u) != 0;
+            const uint32_t total = a + j_len, nwords = (total + 15u) >> 4, hi_last = total & 15u;
+            const uint8_t *sl = slots + (size_t)slot * BK_SLOT;
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < BK_WORDS / 32; ++k) {
+                const uint32_t w = (uint32_t)p * BK_WORDS + (uint32_t)lane + 32u * k;
+                if (w < nwords) {
+                    const bool first_rag = w == 0u && a != 0u, last_rag = w == nwords - 1u && hi_last != 0u;
+                    const uint32_t j0 = first_rag ? 0u : (last_rag ? j_len - 16u : 16u * w - a);
+                    const uint32_t rk = rev ? j_len - 16u - j0 : j0;
+                    const uint32_t tt = j_rem + rk;
+                    uint32_t dq = __umulhi(tt, j_inv);
+                    uint32_t rr = tt - dq * j_bpl;
+                    if (rr >= j_bpl) { ++dq; rr -= j_bpl; }
+                    WordReq rq;
+                    rq.wp = nullptr;
+                    rq.c = j_bpl - rr;
+                    const int soff = (int)(rk + (uint32_t)elen * dq) - base_rel;
+                    rq.o1 = soff & 3;
+                    const int wi = (soff >> 2) & 3;
+                    const uint8_t *cp = sl + (soff & ~15);
+                    const uint4 x0 = *reinterpret_cast<const uint4 *>(cp), x1 = *reinterpret_cast<const uint4 *>(cp + 16);
+                    uint32_t x8 = 0;
+                    if (elen == 2 && wi == 3 && rq.o1 == 3 && rq.c < 16u) x8 = *reinterpret_cast<const uint32_t *>(cp + 32);
+                    // 24 bytes from the 4-byte aligned address: words [wi, wi + 6) of x0 x1 x8
+                    const bool s2 = (wi & 2) != 0, s1 = (wi & 1) != 0;
+                    const uint32_t z0 = s2 ? x0.z : x0.x, z1 = s2 ? x0.w : x0.y, z2 = s2 ? x1.x : x0.z, z3 = s2 ? x1.y : x0.w,
+                                   z4 = s2 ? x1.z : x1.x, z5 = s2 ? x1.w : x1.y, z6 = s2 ? x8 : x1.z;
+                    uint32_t W[6] = {s1 ? z1 : z0, s1 ? z2 : z1, s1 ? z3 : z2, s1 ? z4 : z3, s1 ? z5 : z4, s1 ? z6 : z5};
+                    uint32_t o[4];
+                    if (!ow_finish(W, rq, elen, rev, upper, comp, s_lut, o)) bad = true;
+                    uint8_t *gw = j_dst0 + 16u * w;
+                    if (!first_rag && !last_rag) {
+                        *reinterpret_cast<uint4 *>(gw) = make_uint4(o[0], o[1], o[2], o[3]);
+                        if (WANT_ACGT) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                cntA += count_letter(o[i], 0x61616161u, 0x80808080u);
+                                cntC += count_letter(o[i], 0x63636363u, 0x80808080u);
+                                cntG += count_letter(o[i], 0x67676767u, 0x80808080u);
+                                cntT += count_letter(o[i], 0x74747474u, 0x80808080u);
+                            }
+                        }
+                    } else {
+                        // ragged first / last word: the nearest complete 16 output bytes, shifted into place
+                        uint64_t lo = (uint64_t)o[0] | ((uint64_t)o[1] << 32), hi = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
+                        uint32_t b_lo, b_hi;                                     // slots [b_lo, b_hi) of the word are ours
+                        if (first_rag) {
+                            const uint32_t sh = 8u * a;
+                            if (sh < 64u) { hi = (hi << sh) | (lo >> (64u - sh)); lo <<= sh; } else { hi = lo << (sh - 64u); lo = 0; }
+                            b_lo = a; b_hi = 16u;
+                            if (nwords == 1u) b_hi = total;                      // cannot happen (out_len >= 16, a > 0)
+                        } else {
+                            const uint32_t sh = 8u * (16u - hi_last);
+                            if (sh < 64u) { lo = (lo >> sh) | (hi << (64u - sh)); hi >>= sh; } else { lo = hi >> (sh - 64u); hi = 0; }
+                            b_lo = 0u; b_hi = hi_last;
+                        }
+                        const uint32_t x[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
+#pragma unroll
+                        for (uint32_t i = 0; i < 4; ++i) {
+                            const uint32_t b0 = 4u * i;
+                            uint32_t vm = 0;
+                            if (b_lo <= b0 && b0 + 4u <= b_hi) { *reinterpret_cast<uint32_t *>(gw + b0) = x[i]; vm = 0x80808080u; }
+                            else {
+#pragma unroll
+                                for (uint32_t b = 0; b < 4; ++b)
+                                    if (b0 + b >= b_lo && b0 + b < b_hi) { gw[b0 + b] = (uint8_t)(x[i] >> (8u * b)); vm |= 0x80u << (8u * b); }
+                            }
+                            if (WANT_ACGT) {
+                                cntA += count_letter(x[i], 0x61616161u, vm);
+                                cntC += count_letter(x[i], 0x63636363u, vm);
+                                cntG += count_letter(x[i], 0x67676767u, vm);
+                                cntT += count_letter(x[i], 0x74747474u, vm);
+                            }
+                        }
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, bad)) badmask |= 1u << j;
+            if (WANT_ACGT && p == j_np - 1) {                 // last item of query j: its counts
+#pragma unroll
+                for (int dd = 16; dd > 0; dd >>= 1) {
+                    cntA += __shfl_down_sync(0xffffffffu, cntA, dd);
+                    cntC += __shfl_down_sync(0xffffffffu, cntC, dd);
+                    cntG += __shfl_down_sync(0xffffffffu, cntG, dd);
+                    cntT += __shfl_down_sync(0xffffffffu, cntT, dd);
+                }
+                if (lane == 0) {
+                    int64_t *aq = acgt + 4 * (qb + j);
+                    aq[0] = cntA; aq[1] = cntC; aq[2] = cntG; aq[3] = cntT;
+                }
+                cntA = cntC = cntG = cntT = 0;
+            }
+            __syncwarp();                                      // every lane is done with the slot
+            if (t + BK_NS < T) issue(t + BK_NS);
+        }
+        // queries the bulk path could not serve (or that failed its layout check): whole warp, one at a time
+        uint32_t fb = __ballot_sync(0xffffffffu, valid && (!fast || ((badmask >> lane) & 1u)) && (out_len64 > 0 || WANT_ACGT));
+        while (fb) {
+            const int src = __ffs(fb) - 1;
+            fb &= fb - 1;
+            const int64_t b_rid = shfl_i64(rid, src), b_s = shfl_i64(s, src), b_e = shfl_i64(e, src), b_off = shfl_i64(off, src);
+            const int b_flags = __shfl_sync(0xffffffffu, flags, src);
+            const bool b_ok = b_rid >= 0 && b_rid < n_rows;
+            RowU bu;
+            bu.v[0] = bu.v[1] = bu.v[2] = make_uint4(0, 0, 0, 0);
+            if (b_ok) {
+                const uint4 *p4 = reinterpret_cast<const uint4 *>(rows + b_rid);
+                bu.v[0] = p4[0]; bu.v[1] = p4[1]; bu.v[2] = p4[2];
+            }
+            serve_query_warp<WANT_ACGT>(file, fsize, capacity, bu.r, b_ok, b_s, b_e, b_flags, out + b_off, s_lut, stage, lane,
+                                        WANT_ACGT ? acgt + 4 * (qb + src) : nullptr);
+            __syncwarp();
+        }
+    }
+}
+
 // ---- one query, ONE launch, ONE synchronisation: what a per-object getter (Sequence.seq, .antisense, ...) costs ----
 // The query's output range is cut into `chunk`-byte pieces, one per warp; a piece of a query is itself a query, exact
 // for records with uniform lines (the slice formula) -- any other record is served whole by warp 0.  The output goes
@@ -914,11 +1186,42 @@ extern "C" int fxg_extract_dev(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_
     FXG_CHECK_ARG(d_rows && d_row_id && d_s && d_e && d_out_off && d_out, "null device pointer");
     FXG_CUDA(cudaSetDevice(ctx->device));
     const int grid = gather_grid(ctx, nq);
+    // A/B switches: FXG_EXTRACT_PATH = bulk (default) | group | warp
+    const char *path_env = getenv("FXG_EXTRACT_PATH");
+    const bool want_group = path_env && !strcmp(path_env, "group");
+    const bool want_warp = (path_env && !strcmp(path_env, "warp")) || getenv("FXG_EXTRACT_WARP_PER_QUERY");
     FxgProfScope prof(ctx, FXG_PROF_GATHER);
-    if (d_acgt)
+    if (!want_warp && !(want_group && !d_acgt)) {
+        static int ctas_per_sm[2] = {0, 0};                 // [with counts]
+        const int v = d_acgt ? 1 : 0;
+        if (!ctas_per_sm[v]) {
+            int nb = 0;
+            if (v) {
+                FXG_CUDA(cudaFuncSetAttribute(extract_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
+                FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extract_bulk_kernel<true>, XTHREADS, BK_SMEM));
+            } else {
+                FXG_CUDA(cudaFuncSetAttribute(extract_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BK_SMEM));
+                FXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, extract_bulk_kernel<false>, XTHREADS, BK_SMEM));
+            }
+            ctas_per_sm[v] = nb > 0 ? nb : 1;
+        }
+        const int64_t resident_warps = (int64_t)ctx->sm_count * ctas_per_sm[v] * XWARPS;
+        // queries per warp batch: a lane per query when there is enough work to fill the machine that way
+        int bq = nq >= resident_warps * 32 ? 32 : (nq >= resident_warps * 16 ? 16 : 8);
+        if (const char *b = getenv("FXG_BK_BQ")) { const int v = atoi(b); if (v >= 1 && v <= 32) bq = v; }   // tests: force a batch width
+        int64_t blocks = (nq + (int64_t)XWARPS * bq - 1) / ((int64_t)XWARPS * bq);
+        const int64_t maxb = (int64_t)ctx->sm_count * ctas_per_sm[v];
+        if (blocks > maxb) blocks = maxb;
+        if (v)
+            extract_bulk_kernel<true><<<(unsigned)blocks, XTHREADS, BK_SMEM, ctx->stream>>>(
+                f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e, d_flags, nq, d_out_off, d_out, d_acgt, bq);
+        else
+            extract_bulk_kernel<false><<<(unsigned)blocks, XTHREADS, BK_SMEM, ctx->stream>>>(
+                f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e, d_flags, nq, d_out_off, d_out, nullptr, bq);
+    } else if (d_acgt)
         extract_kernel<true><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e,
                                                                 d_flags, nq, d_out_off, d_out, d_acgt);
-    else if (getenv("FXG_EXTRACT_WARP_PER_QUERY"))          // A/B and debugging
+    else if (want_warp)          // A/B and debugging
         extract_kernel<false><<<grid, XTHREADS, 0, ctx->stream>>>(f->d, f->size, f->capacity, d_rows, n_rows, d_row_id, d_s, d_e,
                                                                  d_flags, nq, d_out_off, d_out, nullptr);
     else {
