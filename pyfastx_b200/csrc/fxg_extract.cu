@@ -680,24 +680,28 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_group_kernel(
 // (l1tex__data_pipe_lsu_wavefronts 78 % of peak: six 4-byte loads per 16 output bytes, each touching eight different
 // cache lines for the eight queries of a warp), not DRAM (45 %).  Here the file bytes never pass through the load/store
 // unit as global loads: the TMA engine writes them to shared memory, every lane assembles its aligned 16-byte output
-// words from two conflict-free 16-byte shared-memory loads, and a warp's stores are 512 contiguous bytes.
-//   * a warp owns a batch of `bq` queries (one per lane: descriptor + index row in registers);
-//   * a query is cut into items of BK_WORDS aligned output words; items of the batch are enumerated in order and run
-//     through a ring of BK_NS slots per warp: the lane that owns the query computes the covering, 16-byte aligned source
-//     range (slice formula, sequence.c:498-510) and issues the bulk copy; all lanes consume;
+// words from three 8-byte shared-memory loads, and a warp's stores are 512 contiguous bytes.
+//   * a warp owns a batch of `bq` queries (one per lane: descriptor + index row in registers, the constants the
+//     consumers need in shared memory);
+//   * a query is cut into items of BK_WORDS aligned output words; the items of the batch are enumerated in order by
+//     two warp-uniform cursors (issue / consume) and run through a ring of BK_NS slots per warp: the lane that owns the
+//     query computes the covering, 16-byte aligned source range (slice formula, sequence.c:498-510) and issues the
+//     bulk copy; all lanes consume;
 //   * the layout assumption is verified on every word exactly as in the group kernel; failures and queries that do not
 //     qualify (norm = 0, odd lines, < 16 bytes, RAW ...) are redone by the general strip path.
 #ifndef FXG_BK_NS
 #define FXG_BK_NS 4
 #endif
-#ifndef FXG_BK_FENCE
-#define FXG_BK_FENCE 0                         // the slot's readers are ordered before the refill by __syncwarp (their
-#endif                                         // loads feed the stores issued before it); no proxy fence needed for a WAR
 constexpr int BK_NS = FXG_BK_NS;               // slots (items in flight) per warp
 constexpr int BK_WORDS = 64;                   // aligned 16-byte output words per item
 constexpr int BK_OUT = BK_WORDS * 16;          // output bytes per item
-constexpr int BK_SLOT = 1280;                  // >= BK_OUT + 16 (ragged-word reach) + 2 * ((BK_OUT + 16) / 16 + 2) + 30 + 16
-constexpr size_t BK_SMEM = (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 16 + 3 * 256 + (size_t)XWARPS * XSTAGE;
+constexpr int BK_SLOT = 1280;                  // >= BK_OUT + 16 (ragged-word reach) + 2 * ((BK_OUT + 16) / 16 + 2) + 30 + 32
+constexpr size_t BK_OFF_BAR = (size_t)XWARPS * BK_NS * BK_SLOT;
+constexpr size_t BK_OFF_G0 = BK_OFF_BAR + (size_t)XWARPS * BK_NS * 8;
+constexpr size_t BK_OFF_QC = (BK_OFF_G0 + (size_t)XWARPS * BK_NS * 4 + 15) & ~(size_t)15;
+constexpr size_t BK_OFF_LUT = BK_OFF_QC + (size_t)XWARPS * 32 * 32;
+constexpr size_t BK_OFF_STAGE = BK_OFF_LUT + 3 * 256;
+constexpr size_t BK_SMEM = BK_OFF_STAGE + (size_t)XWARPS * XSTAGE;
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -715,10 +719,11 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
     extern __shared__ __align__(128) uint8_t bk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *slots = bk_smem + (size_t)warp * BK_NS * BK_SLOT;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT) + warp * BK_NS;
-    int2 *infos = reinterpret_cast<int2 *>(bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 8) + warp * BK_NS;
-    uint8_t (*s_lut)[256] = reinterpret_cast<uint8_t (*)[256]>(bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 16);
-    uint8_t *stage = bk_smem + (size_t)XWARPS * BK_NS * BK_SLOT + (size_t)XWARPS * BK_NS * 16 + 3 * 256 + (size_t)warp * XSTAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bk_smem + BK_OFF_BAR) + warp * BK_NS;
+    int *g0s = reinterpret_cast<int *>(bk_smem + BK_OFF_G0) + warp * BK_NS;
+    uint4 *qc = reinterpret_cast<uint4 *>(bk_smem + BK_OFF_QC) + warp * 64;          // two uint4 per lane
+    uint8_t (*s_lut)[256] = reinterpret_cast<uint8_t (*)[256]>(bk_smem + BK_OFF_LUT);
+    uint8_t *stage = bk_smem + BK_OFF_STAGE + (size_t)warp * XSTAGE;
     init_luts(s_lut);
     if (lane < BK_NS) mbar_init(&bars[lane], 1);
     mbar_fence_init();
@@ -760,42 +765,54 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
             dst0 = dst - a;
             pk = a | ((uint32_t)r.elen << 4) | ((flags & FXG_X_REVERSE) ? 0x100u : 0u) | ((flags & FXG_X_UPPER) ? 0x200u : 0u) |
                  ((flags & FXG_X_COMPLEMENT) ? 0x400u : 0u);
-            np = (int)((((a + out_len + 15u) >> 4) + BK_WORDS - 1) / BK_WORDS);
+            // items cover the FULL aligned output words only; a ragged first / last word is written by the batch epilogue
+            const uint32_t tot = a + out_len;
+            const uint32_t nfull = ((tot + 15u) >> 4) - (a ? 1u : 0u) - ((tot & 15u) ? 1u : 0u);
+            np = (int)((nfull + BK_WORDS - 1) / BK_WORDS);
         }
-        int incl = np;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o2 = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o2;
-        }
-        const int base = incl - np;
-        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        // source range of one item of the lane's own query: (offset of the 16-byte aligned start relative to fq, bytes)
+        auto item_range = [&](int p, int &g0, uint32_t &bytes) {
+            const int a = (int)(pk & 15u), elen = (int)((pk >> 4) & 15u);
+            const int tot = a + (int)out_len;
+            const int olo = (p * BK_WORDS + (a ? 1 : 0)) * 16 - a;                // output bytes of the item's full words
+            int ohi = olo + BK_OUT;
+            const int oend = (tot & ~15) - a;
+            if (ohi > oend) ohi = oend;
+            const bool rev = (pk & 0x100u) != 0;
+            const uint32_t ra = rev ? out_len - (uint32_t)ohi : (uint32_t)olo;
+            const uint32_t rb1 = (rev ? out_len - (uint32_t)olo : (uint32_t)ohi) - 1u;          // last kept rank of the item
+            uint32_t t1 = rem_s + ra, d1 = __umulhi(t1, inv);
+            if (t1 - d1 * bpl >= bpl) ++d1;
+            uint32_t t2 = rem_s + rb1, d2 = __umulhi(t2, inv);
+            if (t2 - d2 * bpl >= bpl) ++d2;
+            const int rel1 = (int)(ra + (uint32_t)elen * d1), rel2 = (int)(rb1 + (uint32_t)elen * d2) + 1;
+            const int fqa = (int)(reinterpret_cast<uintptr_t>(fq) & 15);
+            g0 = rel1 - ((fqa + rel1) & 15);
+            const int g1 = rel2 + ((16 - ((fqa + rel2) & 15)) & 15);
+            bytes = (uint32_t)(g1 - g0);
+            if (bytes > (uint32_t)(BK_SLOT - 32)) bytes = (uint32_t)(BK_SLOT - 32);             // cannot happen (BK_SLOT bound)
+        };
+        int g0_first = 0;
+        uint32_t bytes_first = 16;
+        if (np > 0) item_range(0, g0_first, bytes_first);        // all lanes at once: most queries are a single item
+        __syncwarp();                                        // the previous batch's consumers are done with qc
+        qc[2 * lane] = make_uint4(bpl, inv, rem_s, out_len);
+        qc[2 * lane + 1] = make_uint4(pk, (uint32_t)np, (uint32_t)reinterpret_cast<uintptr_t>(dst0),
+                                      (uint32_t)(reinterpret_cast<uintptr_t>(dst0) >> 32));
+        const uint32_t nz = __ballot_sync(0xffffffffu, np > 0);        // lanes whose query runs through the ring
+        __syncwarp();
         uint32_t badmask = 0;
+        // cursors over the batch's items (warp-uniform): lane (= query) and item index within the query
+        int ji = nz ? __ffs(nz) - 1 : 32, pi = 0;              // next item to issue
+        int jc = ji, pc = 0;                                    // next item to consume
 
-        auto issue = [&](int t) {
-            const uint32_t m = __ballot_sync(0xffffffffu, np > 0 && base <= t);
-            const int j = 31 - __clz(m);
+        auto issue = [&]() {                                    // issues item (ji, pi) and advances the cursor
             const int slot = (int)(it_issue % BK_NS);
-            if (lane == j) {
-                const int p = t - base;
-                const int a = (int)(pk & 15u), elen = (int)((pk >> 4) & 15u);
-                int olo = p * BK_OUT - a - 16, ohi = p * BK_OUT + BK_OUT - a;
-                if (olo < 0) olo = 0;
-                if (ohi > (int)out_len) ohi = (int)out_len;
-                const bool rev = (pk & 0x100u) != 0;
-                const uint32_t ra = rev ? out_len - (uint32_t)ohi : (uint32_t)olo;
-                const uint32_t rb1 = (rev ? out_len - (uint32_t)olo : (uint32_t)ohi) - 1u;      // last kept rank of the item
-                uint32_t t1 = rem_s + ra, d1 = __umulhi(t1, inv);
-                if (t1 - d1 * bpl >= bpl) ++d1;
-                uint32_t t2 = rem_s + rb1, d2 = __umulhi(t2, inv);
-                if (t2 - d2 * bpl >= bpl) ++d2;
-                const int rel1 = (int)(ra + (uint32_t)elen * d1), rel2 = (int)(rb1 + (uint32_t)elen * d2) + 1;
-                const int fqa = (int)(reinterpret_cast<uintptr_t>(fq) & 15);
-                const int g0 = rel1 - ((fqa + rel1) & 15);
-                const int g1 = rel2 + ((16 - ((fqa + rel2) & 15)) & 15);
-                uint32_t bytes = (uint32_t)(g1 - g0);
-                if (bytes > (uint32_t)(BK_SLOT - 16)) bytes = (uint32_t)(BK_SLOT - 16);       // cannot happen (BK_SLOT bound)
-                infos[slot] = make_int2(g0, j);
+            if (lane == ji) {
+                int g0 = g0_first;
+                uint32_t bytes = bytes_first;
+                if (pi > 0) item_range(pi, g0, bytes);
+                g0s[slot] = g0;
 #if FXG_BK_FENCE
                 fence_proxy_async();
 #endif
@@ -803,12 +820,19 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                 tma_load_1d(slots + (size_t)slot * BK_SLOT, fq + g0, bytes, &bars[slot]);
             }
             ++it_issue;
+            const int np_i = __shfl_sync(0xffffffffu, np, ji & 31);
+            if (pi + 1 < np_i) ++pi;
+            else {
+                const uint32_t rest = ji < 31 ? nz & (0xffffffffu << (ji + 1)) : 0u;
+                ji = rest ? __ffs(rest) - 1 : 32;
+                pi = 0;
+            }
         };
 
-        for (int t = 0; t < T && t < BK_NS; ++t) issue(t);
+        for (int k = 0; k < BK_NS && ji < 32; ++k) issue();
         __syncwarp();
         int cntA = 0, cntC = 0, cntG = 0, cntT = 0;
-        for (int t = 0; t < T; ++t) {
+        while (jc < 32) {
             const int slot = (int)(it_cons % BK_NS);
             const uint32_t parity = (it_cons / BK_NS) & 1u;
             ++it_cons;
@@ -817,97 +841,84 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                 while (!mbar_try_wait(&bars[slot], parity))
                     if (++spins > (1u << 22)) __trap();      // a lost completion must not hang the device
             }
-            const int2 inf = infos[slot];
-            const int j = inf.y, base_rel = inf.x;
-            const uint32_t j_bpl = __shfl_sync(0xffffffffu, bpl, j), j_inv = __shfl_sync(0xffffffffu, inv, j);
-            const uint32_t j_rem = __shfl_sync(0xffffffffu, rem_s, j), j_len = __shfl_sync(0xffffffffu, out_len, j);
-            const uint32_t j_pk = __shfl_sync(0xffffffffu, pk, j);
-            const int p = t - __shfl_sync(0xffffffffu, base, j);
-            const int j_np = __shfl_sync(0xffffffffu, np, j);
-            uint8_t *j_dst0 = reinterpret_cast<uint8_t *>(shfl_i64((int64_t)reinterpret_cast<uintptr_t>(dst0), j));
+            const int base_rel = g0s[slot];
+            const uint4 qa = qc[2 * jc], qd = qc[2 * jc + 1];
+            const uint32_t j_bpl = qa.x, j_inv = qa.y, j_rem = qa.z, j_len = qa.w, j_pk = qd.x;
+            const int j_np = (int)qd.y;
+            uint8_t *j_dst0 = reinterpret_cast<uint8_t *>((uintptr_t)qd.z | ((uintptr_t)qd.w << 32));
             const uint32_t a = j_pk & 15u;
             const int elen = (int)((j_pk >> 4) & 15u);
             const bool rev = (j_pk & 0x100u) != 0, upper = (j_pk & 0x200u) != 0, comp = (j_pk & 0x400u) != 0;
-            const uint32_t total = a + j_len, nwords = (total + 15u) >> 4, hi_last = total & 15u;
+            const uint32_t w_beg = a ? 1u : 0u, w_end = (a + j_len) >> 4;          // the query's full words [w_beg, w_end)
+            const int lenm16 = (int)j_len - 16;
             const uint8_t *sl = slots + (size_t)slot * BK_SLOT;
             bool bad = false;
 #pragma unroll
             for (int k = 0; k < BK_WORDS / 32; ++k) {
-                const uint32_t w = (uint32_t)p * BK_WORDS + (uint32_t)lane + 32u * k;
-                if (w < nwords) {
-                    const bool first_rag = w == 0u && a != 0u, last_rag = w == nwords - 1u && hi_last != 0u;
-                    const uint32_t j0 = first_rag ? 0u : (last_rag ? j_len - 16u : 16u * w - a);
-                    const uint32_t rk = rev ? j_len - 16u - j0 : j0;
+                const uint32_t w = w_beg + (uint32_t)pc * BK_WORDS + (uint32_t)lane + 32u * k;
+                if (w < w_end) {
+                    const int j0 = (int)(16u * w) - (int)a;                             // first output byte of the word
+                    const uint32_t rk = (uint32_t)(rev ? lenm16 - j0 : j0);          // first kept rank (source order)
                     const uint32_t tt = j_rem + rk;
                     uint32_t dq = __umulhi(tt, j_inv);
                     uint32_t rr = tt - dq * j_bpl;
                     if (rr >= j_bpl) { ++dq; rr -= j_bpl; }
-                    WordReq rq;
-                    rq.wp = nullptr;
-                    rq.c = j_bpl - rr;
-                    const int soff = (int)(rk + (uint32_t)elen * dq) - base_rel;
-                    rq.o1 = soff & 3;
-                    const int wi = (soff >> 2) & 3;
-                    const uint8_t *cp = sl + (soff & ~15);
-                    const uint4 x0 = *reinterpret_cast<const uint4 *>(cp), x1 = *reinterpret_cast<const uint4 *>(cp + 16);
-                    uint32_t x8 = 0;
-                    if (elen == 2 && wi == 3 && rq.o1 == 3 && rq.c < 16u) x8 = *reinterpret_cast<const uint32_t *>(cp + 32);
-                    // 24 bytes from the 4-byte aligned address: words [wi, wi + 6) of x0 x1 x8
-                    const bool s2 = (wi & 2) != 0, s1 = (wi & 1) != 0;
-                    const uint32_t z0 = s2 ? x0.z : x0.x, z1 = s2 ? x0.w : x0.y, z2 = s2 ? x1.x : x0.z, z3 = s2 ? x1.y : x0.w,
-                                   z4 = s2 ? x1.z : x1.x, z5 = s2 ? x1.w : x1.y, z6 = s2 ? x8 : x1.z;
-                    uint32_t W[6] = {s1 ? z1 : z0, s1 ? z2 : z1, s1 ? z3 : z2, s1 ? z4 : z3, s1 ? z5 : z4, s1 ? z6 : z5};
+                    const uint32_t c = j_bpl - rr;                                    // bytes left on this source line
+                    const int soff = (int)(rk + (uint32_t)elen * dq) - base_rel;    // position in the slot
+                    const uint8_t *cp = sl + (soff & ~7);
+                    const uint2 xa = *reinterpret_cast<const uint2 *>(cp), xb = *reinterpret_cast<const uint2 *>(cp + 8),
+                                xc = *reinterpret_cast<const uint2 *>(cp + 16);
+                    const bool hiw = (soff & 4) != 0;
+                    const int sh = (soff & 3) * 8;
+                    const uint32_t y0 = hiw ? xa.y : xa.x, y1 = hiw ? xb.x : xa.y, y2 = hiw ? xb.y : xb.x,
+                                   y3 = hiw ? xc.x : xb.y, y4 = hiw ? xc.y : xc.x;
+                    uint32_t V[4] = {__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh), __funnelshift_r(y2, y3, sh),
+                                     __funnelshift_r(y3, y4, sh)};
+                    bool ok = true;
+                    if (c < 16u) {                                                    // one line break inside the word
+                        uint32_t y5 = hiw ? 0u : xc.y;
+                        if (elen == 2) {
+                            if (hiw && sh == 24) y5 = *reinterpret_cast<const uint32_t *>(cp + 24);
+                            const uint32_t vw = c < 8u ? (c < 4u ? V[0] : V[1]) : (c < 12u ? V[2] : V[3]);
+                            ok = ((vw >> (8 * (c & 3u))) & 0xffu) == 0x0du;           // the first skipped byte must be '\r'
+                        }
+                        const uint32_t v4 = __funnelshift_r(y4, y5, sh);
+                        const int es = 8 * elen;
+                        const uint32_t E[4] = {__funnelshift_r(V[0], V[1], es), __funnelshift_r(V[1], V[2], es),
+                                               __funnelshift_r(V[2], V[3], es), __funnelshift_r(V[3], v4, es)};
+                        const int c8 = 8 * (int)c;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            // bytes of word i at or after the break come from E: mask = ~0 << 8 * clamp(c - 4 i, 0, 4)
+                            const uint32_t m = __funnelshift_lc(0u, 0xffffffffu, max(c8 - 32 * i, 0));
+                            V[i] = (V[i] & ~m) | (E[i] & m);
+                        }
+                    }
+                    // conservative layout check: every kept byte must lie in 0x40..0x7f (letters)
+                    const uint32_t all = V[0] & V[1] & V[2] & V[3], hi = V[0] | V[1] | V[2] | V[3];
+                    ok = ok && (all & 0x40404040u) == 0x40404040u && (hi & 0x80808080u) == 0u;
+                    if (!ok) bad = true;
+                    xform16(V, upper, comp, s_lut);
                     uint32_t o[4];
-                    if (!ow_finish(W, rq, elen, rev, upper, comp, s_lut, o)) bad = true;
-                    uint8_t *gw = j_dst0 + 16u * w;
-                    if (!first_rag && !last_rag) {
-                        *reinterpret_cast<uint4 *>(gw) = make_uint4(o[0], o[1], o[2], o[3]);
-                        if (WANT_ACGT) {
+                    if (rev) {
+                        o[0] = __byte_perm(V[3], 0, 0x0123); o[1] = __byte_perm(V[2], 0, 0x0123);
+                        o[2] = __byte_perm(V[1], 0, 0x0123); o[3] = __byte_perm(V[0], 0, 0x0123);
+                    } else { o[0] = V[0]; o[1] = V[1]; o[2] = V[2]; o[3] = V[3]; }
+                    *reinterpret_cast<uint4 *>(j_dst0 + 16u * w) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (WANT_ACGT) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                cntA += count_letter(o[i], 0x61616161u, 0x80808080u);
-                                cntC += count_letter(o[i], 0x63636363u, 0x80808080u);
-                                cntG += count_letter(o[i], 0x67676767u, 0x80808080u);
-                                cntT += count_letter(o[i], 0x74747474u, 0x80808080u);
-                            }
-                        }
-                    } else {
-                        // ragged first / last word: the nearest complete 16 output bytes, shifted into place
-                        uint64_t lo = (uint64_t)o[0] | ((uint64_t)o[1] << 32), hi = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
-                        uint32_t b_lo, b_hi;                                     // slots [b_lo, b_hi) of the word are ours
-                        if (first_rag) {
-                            const uint32_t sh = 8u * a;
-                            if (sh < 64u) { hi = (hi << sh) | (lo >> (64u - sh)); lo <<= sh; } else { hi = lo << (sh - 64u); lo = 0; }
-                            b_lo = a; b_hi = 16u;
-                            if (nwords == 1u) b_hi = total;                      // cannot happen (out_len >= 16, a > 0)
-                        } else {
-                            const uint32_t sh = 8u * (16u - hi_last);
-                            if (sh < 64u) { lo = (lo >> sh) | (hi << (64u - sh)); hi >>= sh; } else { lo = hi >> (sh - 64u); hi = 0; }
-                            b_lo = 0u; b_hi = hi_last;
-                        }
-                        const uint32_t x[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
-#pragma unroll
-                        for (uint32_t i = 0; i < 4; ++i) {
-                            const uint32_t b0 = 4u * i;
-                            uint32_t vm = 0;
-                            if (b_lo <= b0 && b0 + 4u <= b_hi) { *reinterpret_cast<uint32_t *>(gw + b0) = x[i]; vm = 0x80808080u; }
-                            else {
-#pragma unroll
-                                for (uint32_t b = 0; b < 4; ++b)
-                                    if (b0 + b >= b_lo && b0 + b < b_hi) { gw[b0 + b] = (uint8_t)(x[i] >> (8u * b)); vm |= 0x80u << (8u * b); }
-                            }
-                            if (WANT_ACGT) {
-                                cntA += count_letter(x[i], 0x61616161u, vm);
-                                cntC += count_letter(x[i], 0x63636363u, vm);
-                                cntG += count_letter(x[i], 0x67676767u, vm);
-                                cntT += count_letter(x[i], 0x74747474u, vm);
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            cntA += count_letter(o[i], 0x61616161u, 0x80808080u);
+                            cntC += count_letter(o[i], 0x63636363u, 0x80808080u);
+                            cntG += count_letter(o[i], 0x67676767u, 0x80808080u);
+                            cntT += count_letter(o[i], 0x74747474u, 0x80808080u);
                         }
                     }
                 }
             }
-            if (__any_sync(0xffffffffu, bad)) badmask |= 1u << j;
-            if (WANT_ACGT && p == j_np - 1) {                 // last item of query j: its counts
+            if (__any_sync(0xffffffffu, bad)) badmask |= 1u << jc;
+            const bool last_item = pc + 1 >= j_np;
+            if (WANT_ACGT && last_item) {                      // last item of the query: its counts
 #pragma unroll
                 for (int dd = 16; dd > 0; dd >>= 1) {
                     cntA += __shfl_down_sync(0xffffffffu, cntA, dd);
@@ -916,13 +927,76 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                     cntT += __shfl_down_sync(0xffffffffu, cntT, dd);
                 }
                 if (lane == 0) {
-                    int64_t *aq = acgt + 4 * (qb + j);
+                    int64_t *aq = acgt + 4 * (qb + jc);
                     aq[0] = cntA; aq[1] = cntC; aq[2] = cntG; aq[3] = cntT;
                 }
                 cntA = cntC = cntG = cntT = 0;
             }
+            if (!last_item) ++pc;
+            else {
+                const uint32_t rest = jc < 31 ? nz & (0xffffffffu << (jc + 1)) : 0u;
+                jc = rest ? __ffs(rest) - 1 : 32;
+                pc = 0;
+            }
             __syncwarp();                                      // every lane is done with the slot
-            if (t + BK_NS < T) issue(t + BK_NS);
+            if (ji < 32) issue();
+        }
+        // batch epilogue: every lane writes the ragged first / last word of its OWN query (at most 15 bytes each) from
+        // the nearest complete 16 output bytes, read with plain loads (the sectors are in L2: the items just fetched them)
+        {
+            bool mybad = false;
+            int rA = 0, rC = 0, rG = 0, rT = 0;
+            if (fast) {
+                const uint32_t a = pk & 15u;
+                const int elen = (int)((pk >> 4) & 15u);
+                const bool rev = (pk & 0x100u) != 0, upper = (pk & 0x200u) != 0, comp = (pk & 0x400u) != 0;
+                const uint32_t total = a + out_len, hi_last = total & 15u, nwords = (total + 15u) >> 4;
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {
+                    const bool first = side == 0;
+                    if (first ? a == 0u : hi_last == 0u) continue;
+                    uint32_t o[4], WE[6];
+                    const WordReq re = ow_locate(fq, rem_s, bpl, inv, elen, out_len, rev, first ? 0u : out_len - 16u);
+                    ow_load(re, WE);
+                    if (!ow_finish(WE, re, elen, rev, upper, comp, s_lut, o)) mybad = true;
+                    uint64_t lo = (uint64_t)o[0] | ((uint64_t)o[1] << 32), hi2 = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
+                    uint32_t b_lo, b_hi;                                     // slots [b_lo, b_hi) of the word are ours
+                    uint8_t *gw;
+                    if (first) {
+                        const uint32_t s8 = 8u * a;                          // outputs 0.. move up to slot a
+                        if (s8 < 64u) { hi2 = (hi2 << s8) | (lo >> (64u - s8)); lo <<= s8; } else { hi2 = lo << (s8 - 64u); lo = 0; }
+                        b_lo = a; b_hi = 16u; gw = dst0;
+                    } else {
+                        const uint32_t s8 = 8u * (16u - hi_last);            // the last hi_last outputs move down to slot 0
+                        if (s8 < 64u) { lo = (lo >> s8) | (hi2 << (64u - s8)); hi2 >>= s8; } else { lo = hi2 >> (s8 - 64u); hi2 = 0; }
+                        b_lo = 0u; b_hi = hi_last; gw = dst0 + 16u * (nwords - 1u);
+                    }
+                    const uint32_t x[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi2, (uint32_t)(hi2 >> 32)};
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) {
+                        const uint32_t b0 = 4u * i;
+                        uint32_t vm = 0;
+                        if (b_lo <= b0 && b0 + 4u <= b_hi) { *reinterpret_cast<uint32_t *>(gw + b0) = x[i]; vm = 0x80808080u; }
+                        else {
+#pragma unroll
+                            for (uint32_t b = 0; b < 4; ++b)
+                                if (b0 + b >= b_lo && b0 + b < b_hi) { gw[b0 + b] = (uint8_t)(x[i] >> (8u * b)); vm |= 0x80u << (8u * b); }
+                        }
+                        if (WANT_ACGT) {
+                            rA += count_letter(x[i], 0x61616161u, vm);
+                            rC += count_letter(x[i], 0x63636363u, vm);
+                            rG += count_letter(x[i], 0x67676767u, vm);
+                            rT += count_letter(x[i], 0x74747474u, vm);
+                        }
+                    }
+                }
+                if (WANT_ACGT) {                                     // the items' lane 0 wrote the full words' counts (np > 0)
+                    int64_t *aq = acgt + 4 * q;
+                    if (np > 0) { aq[0] += rA; aq[1] += rC; aq[2] += rG; aq[3] += rT; }
+                    else { aq[0] = rA; aq[1] = rC; aq[2] = rG; aq[3] = rT; }
+                }
+            }
+            badmask |= __ballot_sync(0xffffffffu, mybad);
         }
         // queries the bulk path could not serve (or that failed its layout check): whole warp, one at a time
         uint32_t fb = __ballot_sync(0xffffffffu, valid && (!fast || ((badmask >> lane) & 1u)) && (out_len64 > 0 || WANT_ACGT));
