@@ -865,20 +865,18 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                     if (rr >= j_bpl) { ++dq; rr -= j_bpl; }
                     const uint32_t c = j_bpl - rr;                                    // bytes left on this source line
                     const int soff = (int)(rk + (uint32_t)elen * dq) - base_rel;    // position in the slot
-                    const uint8_t *cp = sl + (soff & ~7);
-                    const uint2 xa = *reinterpret_cast<const uint2 *>(cp), xb = *reinterpret_cast<const uint2 *>(cp + 8),
-                                xc = *reinterpret_cast<const uint2 *>(cp + 16);
-                    const bool hiw = (soff & 4) != 0;
+                    // five 4-byte shared-memory loads from the 4-byte aligned position (the select network that 8- or 16-byte
+                    // loads need costs ALU-pipe instructions, and the ALU pipe is what limits this kernel: 74 % busy)
+                    const uint32_t *cp = reinterpret_cast<const uint32_t *>(sl + (soff & ~3));
                     const int sh = (soff & 3) * 8;
-                    const uint32_t y0 = hiw ? xa.y : xa.x, y1 = hiw ? xb.x : xa.y, y2 = hiw ? xb.y : xb.x,
-                                   y3 = hiw ? xc.x : xb.y, y4 = hiw ? xc.y : xc.x;
+                    const uint32_t y0 = cp[0], y1 = cp[1], y2 = cp[2], y3 = cp[3], y4 = cp[4];
                     uint32_t V[4] = {__funnelshift_r(y0, y1, sh), __funnelshift_r(y1, y2, sh), __funnelshift_r(y2, y3, sh),
                                      __funnelshift_r(y3, y4, sh)};
                     bool ok = true;
                     if (c < 16u) {                                                    // one line break inside the word
-                        uint32_t y5 = hiw ? 0u : xc.y;
+                        uint32_t y5 = 0u;
                         if (elen == 2) {
-                            if (hiw && sh == 24) y5 = *reinterpret_cast<const uint32_t *>(cp + 24);
+                            if (sh == 24) y5 = cp[5];
                             const uint32_t vw = c < 8u ? (c < 4u ? V[0] : V[1]) : (c < 12u ? V[2] : V[3]);
                             ok = ((vw >> (8 * (c & 3u))) & 0xffu) == 0x0du;           // the first skipped byte must be '\r'
                         }
@@ -896,8 +894,7 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                     }
                     // conservative layout check: every kept byte must lie in 0x40..0x7f (letters)
                     const uint32_t all = V[0] & V[1] & V[2] & V[3], hi = V[0] | V[1] | V[2] | V[3];
-                    ok = ok && (all & 0x40404040u) == 0x40404040u && (hi & 0x80808080u) == 0u;
-                    if (!ok) bad = true;
+                    if (((~all & 0x40404040u) | (hi & 0x80808080u)) != 0u || !ok) bad = true;
                     xform16(V, upper, comp, s_lut);
                     uint32_t o[4];
                     if (rev) {
@@ -916,7 +913,7 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                     }
                 }
             }
-            if (__any_sync(0xffffffffu, bad)) badmask |= 1u << jc;
+            if (bad) badmask |= 1u << jc;                       // per lane; OR-reduced after the batch
             const bool last_item = pc + 1 >= j_np;
             if (WANT_ACGT && last_item) {                      // last item of the query: its counts
 #pragma unroll
@@ -996,7 +993,7 @@ __global__ void __launch_bounds__(XTHREADS, 3) extract_bulk_kernel(
                     else { aq[0] = rA; aq[1] = rC; aq[2] = rG; aq[3] = rT; }
                 }
             }
-            badmask |= __ballot_sync(0xffffffffu, mybad);
+            badmask = __reduce_or_sync(0xffffffffu, badmask) | __ballot_sync(0xffffffffu, mybad);
         }
         // queries the bulk path could not serve (or that failed its layout check): whole warp, one at a time
         uint32_t fb = __ballot_sync(0xffffffffu, valid && (!fast || ((badmask >> lane) & 1u)) && (out_len64 > 0 || WANT_ACGT));

@@ -37,6 +37,9 @@ namespace fxg {
 
 #ifndef FXG_MARK_MINB
 #define FXG_MARK_MINB 6
+#ifndef FXG_MARK_IMAD
+#define FXG_MARK_IMAD 0
+#endif
 #endif
 constexpr int REGION   = 2048;            // bytes per warp
 constexpr int SEGCAP   = 128;             // newline-list entries kept per region (lines >= 16 B on average)
@@ -158,6 +161,9 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
     const int64_t base = r * REGION;
     const uint8_t *file = P.file;
     const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
+#if FXG_MARK_IMAD
+    const uint32_t kone = reg_const(1u);
+#endif
 
     uint4 v[4];
     if (base + REGION <= n) {
@@ -190,7 +196,11 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         s_data[warp][j * 32 + lane] = v[j];
+#if FXG_MARK_IMAD
+        m[j] = chunk_eq_mask_m(v[j], k0a, k7f, k80, kone);
+#else
         m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80);
+#endif
         cmax = max(cmax, __popc(m[j]));
     }
     const bool any2 = __any_sync(0xffffffffu, cmax >= 2);          // e.g. the "+" line of a FASTQ record
