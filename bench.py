@@ -1072,8 +1072,13 @@ def run_b200(args):
             c.L.fxg_host_free(p)
     if not args.skip_fastq:
         run_fastq(c, args, result)
-    result["comm"] = {"nranks": c.world, "collective": "ncclAllGather via fxg_shard_exchange (libfxg.so, dlopen libnccl.so.2)"
-                      if c.world > 1 else "none (single rank: device copy)"}
+    p2p = bool(c.world > 1 and c.comm.handle and c.L.fxg_comm_uses_p2p(c.comm.handle))
+    result["comm"] = {"nranks": c.world,
+                      "collective": ("none (single rank: device copy)" if c.world == 1 else
+                                     "fxg_shard_exchange over peer-memory mailboxes: one kernel per rank stores its 128-byte block into every "
+                                     "rank's HBM over NVLink/NVSwitch (CUDA IPC mappings) and waits for the peers' flags; NCCL only at set-up"
+                                     if p2p else "ncclAllGather via fxg_shard_exchange (libfxg.so, dlopen libnccl.so.2)"),
+                      "p2p_mailboxes": p2p}
     if c.rank == 0:
         print(json.dumps(result), flush=True)
     if c.world > 1:

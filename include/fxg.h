@@ -210,6 +210,12 @@ int  fxg_comm_unique_id(void *id_out);
 int  fxg_comm_create(fxg_ctx *ctx, const void *id, int nranks, int rank, fxg_comm **out);
 int  fxg_comm_nranks(const fxg_comm *comm);
 int  fxg_comm_rank(const fxg_comm *comm);
+/* 1 if fxg_shard_exchange runs over the peer-memory mailboxes (P2P stores into every rank's HBM over NVLink / NVSwitch,
+ * mapped with CUDA IPC at fxg_comm_create: one kernel, no collective library on the path), 0 if it falls back to
+ * ncclAllGather (IPC or peer access unavailable, or FXG_COMM=nccl). */
+int  fxg_comm_uses_p2p(const fxg_comm *comm);
+/* after a stream synchronisation: FXG_ECUDA if a mailbox wait timed out (a peer never arrived), else FXG_OK */
+int  fxg_comm_check(fxg_comm *comm);
 void fxg_comm_destroy(fxg_comm *comm);
 
 /* split points found ON THE DATA: first offset >= from at which a line starts (want_header = 0) or a FASTA

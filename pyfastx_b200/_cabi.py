@@ -104,6 +104,8 @@ SIGNATURES = {
     "fxg_comm_create": (i32, [vp, vp, i32, i32, P(vp)]),
     "fxg_comm_nranks": (i32, [vp]),
     "fxg_comm_rank": (i32, [vp]),
+    "fxg_comm_uses_p2p": (i32, [vp]),
+    "fxg_comm_check": (i32, [vp]),
     "fxg_comm_destroy": (None, [vp]),
     "fxg_split_point_dev": (i32, [vp, vp, i64, i32, P(i64)]),
     "fxg_split_point_path": (i32, [C.c_char_p, i64, i32, P(i64), P(i64)]),

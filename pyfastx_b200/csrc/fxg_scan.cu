@@ -1426,7 +1426,8 @@ extern "C" int fxg_scan_sharded(fxg_ctx *ctx, fxg_comm *comm, const fxg_file *f,
     fxg_shard_info *d_all = (fxg_shard_info *)ctx->misc.ptr;
     if ((rc = fxg_scan_begin(ctx, f, mode, base_offset, flags, nullptr))) return rc;
     if ((rc = fxg_shard_exchange(ctx, comm, own_info(ctx), d_all, sizeof(fxg_shard_info)))) return rc;
-    return fxg_scan_finish(ctx, d_all, nranks, rank, d_rows_out, stats, all_host);
+    if ((rc = fxg_scan_finish(ctx, d_all, nranks, rank, d_rows_out, stats, all_host))) return rc;
+    return comm ? fxg_comm_check(comm) : FXG_OK;
 }
 
 extern "C" int fxg_fasta_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset, int flags,

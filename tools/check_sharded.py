@@ -39,7 +39,8 @@ def main():
             if os.path.exists(p):
                 os.unlink(p)
     dist.barrier()
-    out = {"world": world}
+    from pyfastx_b200 import _cabi
+    out = {"world": world, "p2p_mailboxes": bool(_cabi.lib().fxg_comm_uses_p2p(comm.handle)) if comm.handle else False}
     for fmt, path in (("fasta", fa_path), ("fastq", fq_path)):
         t0 = time.perf_counter()
         res = shard.build_index_sharded(path, fmt, engine=eng, comm=comm, index_file=path + ".fxi")
