@@ -580,7 +580,7 @@ def run_fasta(c, args, result):
         "gpu_launches": t["launches"],
         "clocks": clk,
         "roofline": {**scan_roofline(c, t, shard_bytes, n_rows, 48, "mark_kernel<FASTA>"),
-                     **ncu_traffic("mark_kernel", shard_bytes)},
+                     **ncu_traffic("scan_all_fasta", shard_bytes + 48 * n_rows)},
     })
     return dfile, info, rows, st
 
@@ -635,10 +635,10 @@ def run_extract(c, args, dfile, info, rows, result, host_file):
         rec = {"metric": "subseq_extract_Mbases_per_s", "value": tot_bases * args.steps / (x_ms * 1e-3) / 1e6,
                "unit": "Mbases/s", "ms_per_step": x_ms / args.steps, "queries_per_gpu": nq,
                "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "extract_group_kernel", "achieved": ach, "peak": c.peak,
+               "roofline": {"bound": "hbm", "kernel": "extract_bulk_kernel", "achieved": ach, "peak": c.peak,
                             "unit": "GB/s", "frac": ach / c.peak, "frac_of_nominal_8TBs": ach / 8000.0,
                             "algorithmic_bytes_per_launch": alg, "kernel_ms": g_ms,
-                            **(ncu_traffic("extract_kernel", alg) if not mixed else {"traffic": None})}}
+                            **ncu_traffic("extract_kernel_mixed" if mixed else "extract_kernel", alg)}}
         if mixed:
             out["mixed_length"] = rec
             del d_rid, d_s, d_e, d_fl, d_ooff, d_out
@@ -871,7 +871,8 @@ def run_fastq(c, args, result):
                                   "completed on the device" % (S / 1e9, R, c.world),
                       "range_of_rank0": [int(q0), int(q1)], "rows_rank0": int(n_rows), "first_line_rank0": int(st["lead_lines"])},
            "gpu_launches": t["launches"],
-           "roofline": scan_roofline(c, t, shard_bytes, n_rows, 32, "mark_kernel<FASTQ>")}
+           "roofline": {**scan_roofline(c, t, shard_bytes, n_rows, 32, "mark_kernel<FASTQ>"),
+                        **ncu_traffic("scan_all_fastq", shard_bytes + 32 * n_rows)}}
     # ---- parity: ALL rows of this rank against oracle/fxo.c on the downloaded range ----
     if not args.no_parity:
         try:
