@@ -40,6 +40,9 @@ namespace fxg {
 #ifndef FXG_MARK_IMAD
 #define FXG_MARK_IMAD 0
 #endif
+#ifndef FXG_MARK_EXP
+#define FXG_MARK_EXP 0
+#endif
 #endif
 constexpr int REGION   = 2048;            // bytes per warp
 constexpr int SEGCAP   = 128;             // newline-list entries kept per region (lines >= 16 B on average)
@@ -113,89 +116,191 @@ __device__ __forceinline__ uint4 ld_stream16(const uint8_t *p) {
 }
 
 // FASTQ name cut (fastq.c:104-117: the name ends at the first ' ', strchr semantics) of a line that begins
-// with '@' at region byte a-1, searched in the region's shared-memory copy: the first byte below 0x21 in a
-// NAMEWIN-byte window decides -- ' ' -> its offset; '\n', NUL or "\r\n" -> 254 (no blank: the whole line);
-// anything else (tab, lone '\r', window or region end reached) -> 255 = the rows kernel searches the file.
-// Measured on C4 (126M reads): the rows kernel gets 1.2 ms faster, mark 3.5 ms slower (it is issue bound) -- so the
-// side list is compiled out by default and the rows kernel searches the name line in the file (FXG_MARK_CUT=1 for A/B).
+// with '@' at region byte a-1, found by mark while the bytes are on chip: the rows kernel otherwise has to fetch the
+// start of every name line from DRAM a second time just to find the first blank -- ncu r02 (profiles/r02_traffic.json):
+// 166 B of DRAM reads per read for a 32-byte row, 20.9 GB on C4, the kernel bandwidth bound on that traffic.
+// Loop-free probe of the FXG_CUT_WORDS aligned words that follow the '@' in the region's shared-memory copy: a SWAR
+// "byte < 0x21" test per word, the per-byte flags packed four to a nibble by one multiply (on the FMA pipe) so that
+// the position of the first such byte is one find-first-set.  The first byte below 0x21 decides -- ' ' -> its offset;
+// '\n', NUL or "\r\n" -> 254 (no blank: the whole line); anything else (tab, lone '\r'), a window without such a
+// byte or one that runs past the region -> 255 = the rows kernel searches the file for that read.
 #ifndef FXG_MARK_CUT
 #define FXG_MARK_CUT 0
 #endif
-constexpr int NAMEWIN = 96;
+#ifndef FXG_CUT_WORDS
+#define FXG_CUT_WORDS 6
+#endif
+__device__ __forceinline__ uint32_t swz_unit(uint32_t u);
+template <int V> __device__ __forceinline__ uint32_t region_byte(const uint8_t *sb, uint32_t p);
+template <int V>
 __device__ __forceinline__ uint32_t name_cut_smem(const uint8_t *sb, uint32_t a) {
-    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(sb);
-    const uint32_t end = min(a + (uint32_t)NAMEWIN, (uint32_t)REGION);
-    uint32_t wi = a >> 2;
-    uint32_t w = w32[wi];
-    // 0x80 per byte below 0x21 (bytes >= 0x80 never match)
-    uint32_t lt = ~((((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w)) & 0x80808080u & (0xffffffffu << (8u * (a & 3u)));
-    while (!lt) {
-        ++wi;
-        if (wi * 4u >= end) return 255u;
-        w = w32[wi];
-        lt = ~((((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w)) & 0x80808080u;
+    uint32_t M = 0;                                                               // bit p <-> byte 4 * (a >> 2) + p
+#pragma unroll
+    for (int k = 0; k < FXG_CUT_WORDS; ++k) {
+        const uint32_t wq = min((a >> 2) + (uint32_t)k, (uint32_t)(REGION / 4 - 1));   // stays inside the region's copy
+        const uint32_t w = reinterpret_cast<const uint32_t *>(sb)[V == 2 ? ((swz_unit(wq >> 2) << 2) | (wq & 3u)) : wq];
+        const uint32_t lt = ~((((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w)) & 0x80808080u;      // 0x80 per byte below 0x21
+        M |= ((lt * 0x00204081u) >> 28) << (4 * k);
     }
-    const uint32_t idx = (uint32_t)(__ffs(lt) - 1) >> 3;
-    const uint32_t p = wi * 4u + idx;
-    if (p >= end) return 255u;
-    const uint32_t b = (w >> (8u * idx)) & 0xffu;
-    const uint32_t c = p - a;
-    if (b == ' ') return c < 254u ? c : 255u;
+    M &= 0xffffffffu << (a & 3u);                                                 // bytes before the name
+    if (!M) return 255u;
+    const uint32_t p = (a & ~3u) + (uint32_t)(__ffs(M) - 1);
+    if (p >= (uint32_t)REGION) return 255u;
+    if (p >= ((a >> 2) + (uint32_t)FXG_CUT_WORDS) * 4u) return 255u;               // (clamped word read twice)
+    const uint32_t b = region_byte<V>(sb, p);
+    if (b == ' ') return p - a;                                                   // < 4 * FXG_CUT_WORDS <= 32
     if (b == '\n' || b == 0u) return 254u;
-    if (b == '\r' && p + 1u < (uint32_t)REGION && sb[p + 1u] == '\n') return 254u;
+    if (b == '\r' && p + 1u < (uint32_t)REGION && region_byte<V>(sb, p + 1u) == '\n') return 254u;
     return 255u;
 }
 
 // =============================================================================================
 // mark: newline list + counts of one 2 KiB region per warp
 // =============================================================================================
-template <int MODE>   // 0 = FASTA, 1 = FASTQ
+// FXG_MARK_V = 2 (r02): every lane tests 64 CONTIGUOUS bytes.  The loads stay coalesced (lane l takes 16 bytes of each
+// of the four 512-byte quarters); the region is transposed on its way through shared memory, where pass 2 needs it
+// anyway: 16-byte unit u is stored at u ^ ((u >> 3) & 7), which makes both the quarter-major stores and the lane-major
+// loads (units 4l .. 4l+3) bank-conflict free.  With contiguous bytes per lane the file order of the newlines is the
+// lane order, so ONE pair of ballots ranks the whole region (r01: one or two ballots and a rank per quarter), and
+// the per-byte flags are packed into a position-ordered 64-bit mask by integer multiply-adds -- work for the FMA pipe
+// where the r01 code kept the ALU pipe 74 % busy (profiles/r02_scan_extract_ncu.txt).
+// Which pass 1 a mode uses is a compile-time choice (measured, 10 GB each, prefetching loop): see DESIGN.md section 3.
+#ifndef FXG_MARK_V_FASTA
+#define FXG_MARK_V_FASTA 1
+#endif
+#ifndef FXG_MARK_V_FASTQ
+#define FXG_MARK_V_FASTQ 2
+#endif
+#ifndef FXG_MARK_RPW
+#define FXG_MARK_RPW 1            // consecutive regions per warp.  > 1: the loads of region i + 1 are in flight while region i is
+                                  // worked on -- measured (2, 4, 8 regions at 4 or 5 CTAs per SM for the extra registers): 5-15 % SLOWER
+                                  // than one region per warp at 6 CTAs per SM; the kernel is bound by instruction issue, not by latency
+#endif
+__device__ __forceinline__ uint32_t swz_unit(uint32_t u) { return u ^ ((u >> 3) & 7u); }
+// byte p (0 .. REGION-1) of a region held in swizzled (V = 2) or linear (V = 1) shared memory
+template <int V>
+__device__ __forceinline__ uint32_t region_byte(const uint8_t *sb, uint32_t p) {
+    return V == 2 ? sb[(swz_unit(p >> 4) << 4) | (p & 15u)] : sb[p];
+}
+
+template <int MODE, int V>   // MODE: 0 = FASTA, 1 = FASTQ; V: pass-1 variant
 __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(const ScanParams P) {
-    __shared__ uint4    s_data[MARK_WARPS][REGION / 16];   // the region's bytes (neighbour-byte lookups)
+    __shared__ uint4    s_data[MARK_WARPS * (REGION / 16) + (FXG_MARK_CUT ? 2 : 0)];   // the regions' bytes (neighbour-byte lookups; + 32 B: the name probe of the last warp may read past its region)
     __shared__ uint16_t s_ent[MARK_WARPS][SEGCAP];         // newline positions, then complete entries
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t r = (int64_t)blockIdx.x * MARK_WARPS + warp;
-    if (r >= P.nreg) return;
+    const int64_t r0 = ((int64_t)blockIdx.x * MARK_WARPS + warp) * FXG_MARK_RPW;
+    if (r0 >= P.nreg) return;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int64_t n = P.n;
-    const int64_t base = r * REGION;
     const uint8_t *file = P.file;
     const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
 #if FXG_MARK_IMAD
     const uint32_t kone = reg_const(1u);
 #endif
 
-    uint4 v[4];
-    if (base + REGION <= n) {
-        const uint8_t *src = file + base + lane * 16;
+    // the 2 KiB of region rr: four coalesced 16-byte streaming loads per lane, all in flight together
+    auto load_region = [&](int64_t rr, uint4 (&vv)[4]) {
+        const int64_t base = rr * REGION;
+        if (base + REGION <= n) {
+            const uint8_t *src = file + base + lane * 16;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = ld_stream16(src + j * 512);
-    } else {
+            for (int j = 0; j < 4; ++j) vv[j] = ld_stream16(src + j * 512);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t o = base + j * 512 + lane * 16;
-            if (o + 16 <= n) { v[j] = ld_stream16(file + o); continue; }
-            // the chunk that contains EOF (or lies past it): bytes >= n read as 0, and a file that does
-            // not end in '\n' gets a virtual newline at n (kseq returns the last line all the same)
-            const bool virt = n > 0 && file[n - 1] != '\n';
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (int i = 0; i < 16; ++i) {
-                const int64_t x = o + i;
-                const uint32_t b = x < n ? file[x] : ((virt && x == n) ? 0x0au : 0u);
-                w[i >> 2] |= b << ((i & 3) * 8);
+            for (int j = 0; j < 4; ++j) {
+                const int64_t o = base + j * 512 + lane * 16;
+                if (o + 16 <= n) { vv[j] = ld_stream16(file + o); continue; }
+                // the chunk that contains EOF (or lies past it): bytes >= n read as 0, and a file that does
+                // not end in '\n' gets a virtual newline at n (kseq returns the last line all the same)
+                const bool virt = n > 0 && file[n - 1] != '\n';
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int i = 0; i < 16; ++i) {
+                    const int64_t x = o + i;
+                    const uint32_t b = x < n ? file[x] : ((virt && x == n) ? 0x0au : 0u);
+                    w[i >> 2] |= b << ((i & 3) * 8);
+                }
+                vv[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            v[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    };
+    uint4 vn[4];
+    load_region(r0, vn);
+#pragma unroll 1
+    for (int it = 0; it < FXG_MARK_RPW; ++it) {
+    const int64_t r = r0 + it;
+    if (r >= P.nreg) break;
+    const int64_t base = r * REGION;
+    uint4 v[4] = {vn[0], vn[1], vn[2], vn[3]};
+    if (it + 1 < FXG_MARK_RPW && r + 1 < P.nreg) load_region(r + 1, vn);     // prefetch: in flight during this region's work
+    uint32_t nlc = 0;
+    uint16_t *ent = s_ent[warp];
+
+    if constexpr (V == 2) {
+    // ---- pass 1 (V2): transpose through shared memory, 64 contiguous bytes per lane, one ranking for the region ----
+    uint4 *sd = s_data + warp * (REGION / 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sd[swz_unit((uint32_t)(j * 32 + lane))] = v[j];
+    __syncwarp();
+    uint32_t lo = 0, hi = 0;                      // bit p of hi:lo <-> byte 64 * lane + p is a newline
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 x = sd[swz_unit((uint32_t)(4 * lane + i))];
+        const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t f = byte_eq_mask_r(w4[c], k0a, k7f, k80);            // 0x80 per newline byte
+            const uint32_t nib = (f * 0x00204081u) >> 28;                       // the four flags as a nibble, byte order
+            const int k = 4 * i + c;
+            if (k < 8) lo = nib * (1u << (4 * k)) + lo;                         // multiply-adds: FMA pipe
+            else hi = nib * (1u << (4 * (k - 8))) + hi;
         }
     }
-
+#if FXG_MARK_EXP
+    nlc = __reduce_add_sync(0xffffffffu, (uint32_t)(__popc(lo) + __popc(hi)));
+    if (lane == 0) P.rc[r] = make_uint2(nlc, 0u);
+    if (FXG_MARK_EXP == 1) continue;
+    nlc = 0;
+#endif
+    {
+        const uint32_t c = (uint32_t)(__popc(lo) + __popc(hi));
+        const uint32_t b1 = __ballot_sync(0xffffffffu, c >= 1u), b2 = __ballot_sync(0xffffffffu, c >= 2u);
+        const uint32_t b3 = __ballot_sync(0xffffffffu, c >= 3u);
+        const uint32_t pbase = (uint32_t)lane * 64u;
+        if (!b3) {
+            // lines of 32 bytes or more: at most two newlines in a lane's 64 bytes
+            const uint32_t idx = (uint32_t)(__popc(b1 & lt_mask) + __popc(b2 & lt_mask));
+            nlc = (uint32_t)(__popc(b1) + __popc(b2));
+            if (c) {
+                const uint32_t p1 = lo ? (uint32_t)(__ffs(lo) - 1) : 32u + (uint32_t)(__ffs(hi) - 1);
+                if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(pbase + p1);
+                if (c >= 2u) {
+                    if (lo) lo &= lo - 1u; else hi &= hi - 1u;
+                    const uint32_t p2 = lo ? (uint32_t)(__ffs(lo) - 1) : 32u + (uint32_t)(__ffs(hi) - 1);
+                    if (idx + 1u < (uint32_t)SEGCAP) ent[idx + 1u] = (uint16_t)(pbase + p2);
+                }
+            }
+        } else {
+            // short lines: exclusive scan of the per-lane counts, every lane walks its own newlines in order
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o2 = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o2;
+            }
+            nlc = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t idx = incl - c;
+            while (lo) { if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(pbase + (uint32_t)(__ffs(lo) - 1)); lo &= lo - 1u; ++idx; }
+            while (hi) { if (idx < (uint32_t)SEGCAP) ent[idx] = (uint16_t)(pbase + 32u + (uint32_t)(__ffs(hi) - 1)); hi &= hi - 1u; ++idx; }
+        }
+    }
+    __syncwarp();
+    } else {
     // ---- pass 1: positions, ranked in file order (chunk-major, lane-minor) ------------------
     uint32_t m[4];
-    uint32_t nlc = 0;
     int cmax = 0;
-    uint16_t *ent = s_ent[warp];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        s_data[warp][j * 32 + lane] = v[j];
+        s_data[warp * (REGION / 16) + j * 32 + lane] = v[j];
 #if FXG_MARK_IMAD
         m[j] = chunk_eq_mask_m(v[j], k0a, k7f, k80, kone);
 #else
@@ -203,6 +308,11 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
 #endif
         cmax = max(cmax, __popc(m[j]));
     }
+#if FXG_MARK_EXP     // timing experiment only (results invalid): count, no ranking, no list
+    nlc = __reduce_add_sync(0xffffffffu, (uint32_t)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3])));
+    if (lane == 0) P.rc[r] = make_uint2(nlc, 0u);
+    if (FXG_MARK_EXP == 1) continue;
+#endif
     const bool any2 = __any_sync(0xffffffffu, cmax >= 2);          // e.g. the "+" line of a FASTQ record
     const bool multi = any2 && __any_sync(0xffffffffu, cmax >= 3);
     if (!any2) {
@@ -268,9 +378,10 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
         }
     }
     __syncwarp();
+    }   // pass-1 variant
 
     // ---- pass 2: one lane per newline: neighbour byte -> flag; counts; write-out --------------
-    const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data[warp]);
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(s_data + warp * (REGION / 16));
     uint32_t hc = 0;
     if (nlc <= (uint32_t)SEGCAP) {
         uint16_t *dst = P.seg + r * SEGCAP;
@@ -282,13 +393,13 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
             if (k < nlc) {
                 const uint32_t pos = ent[k];
                 e = pos;
-                if (FXG_MARK_CUT && MODE == 1 && pos + 2u < (uint32_t)REGION && sb[pos + 1u] == '@') cutv = name_cut_smem(sb, pos + 2u);
+                if (FXG_MARK_CUT && MODE == 1 && pos + 2u < (uint32_t)REGION && region_byte<V>(sb, pos + 1u) == '@') cutv = name_cut_smem<V>(sb, pos + 2u);
                 if (MODE == 0) {
-                    const uint32_t next = pos < (uint32_t)(REGION - 1) ? (uint32_t)sb[pos + 1]
+                    const uint32_t next = pos < (uint32_t)(REGION - 1) ? region_byte<V>(sb, pos + 1u)
                                                                       : (base + REGION < n ? (uint32_t)file[base + REGION] : 0u);
                     if (next == '>') e |= E_HDR;
                 } else {
-                    const uint32_t prev = pos > 0 ? (uint32_t)sb[pos - 1] : (base > 0 ? (uint32_t)file[base - 1] : 0u);
+                    const uint32_t prev = pos > 0 ? region_byte<V>(sb, pos - 1u) : (base > 0 ? (uint32_t)file[base - 1] : 0u);
                     if (prev == '\r') e |= E_CR;
                 }
             }
@@ -323,8 +434,8 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
         if (MODE == 0) {
             uint32_t myh = 0;
             for (int x = lane; x < REGION; x += 32)
-                if (sb[x] == '\n') {
-                    const uint32_t next = x < REGION - 1 ? (uint32_t)sb[x + 1] : (base + REGION < n ? (uint32_t)file[base + REGION] : 0u);
+                if (region_byte<V>(sb, (uint32_t)x) == '\n') {
+                    const uint32_t next = x < REGION - 1 ? region_byte<V>(sb, (uint32_t)x + 1u) : (base + REGION < n ? (uint32_t)file[base + REGION] : 0u);
                     myh += next == '>';
                 }
             hc = __reduce_add_sync(0xffffffffu, myh);
@@ -334,6 +445,8 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
             if (MODE == 0) P.rec2[r] = make_uint4(0u, 0xffffffffu, 0u, 0u);
         }
     }
+    __syncwarp();                                  // the warp's shared-memory buffers are reused by its next region
+    }   // regions of this warp
 }
 
 // =============================================================================================
@@ -1297,11 +1410,11 @@ extern "C" int fxg_scan_begin(fxg_ctx *ctx, const fxg_file *f, int mode, int64_t
     const int64_t nb = (nreg + PS_BLOCK - 1) / PS_BLOCK, nreg_pad = nb * PS_BLOCK;
     FXG_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, 1024, ctx->stream));
     if (nreg_pad > nreg) FXG_CUDA(cudaMemsetAsync(P.rc + nreg, 0, (size_t)(nreg_pad - nreg) * 8, ctx->stream));
-    const unsigned grid = (unsigned)((nreg + MARK_WARPS - 1) / MARK_WARPS);
+    const unsigned grid = (unsigned)((nreg + (int64_t)MARK_WARPS * FXG_MARK_RPW - 1) / ((int64_t)MARK_WARPS * FXG_MARK_RPW));
     {
         FxgProfScope prof(ctx, FXG_PROF_SCAN);
-        if (mode == 0) mark_kernel<0><<<grid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
-        else mark_kernel<1><<<grid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+        if (mode == 0) mark_kernel<0, FXG_MARK_V_FASTA><<<grid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
+        else mark_kernel<1, FXG_MARK_V_FASTQ><<<grid, MARK_WARPS * 32, 0, ctx->stream>>>(P);
     }
     FXG_CUDA(cudaGetLastError());
     {
