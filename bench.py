@@ -731,7 +731,8 @@ def run_e2e_and_cpu(c, args, info, rows, st, host_file, result):
                                              "first difference at %d: %r vs %r" % (j, names[j], qs[j], qe[j], minus[j], len(g), len(want), k,
                                                                                  g[max(0, k - 8):k + 24], want[max(0, k - 8):k + 24]))
                 result["extract"]["per_object_idiom"] = {
-                    "api": "fa[name][s:e].seq / .antisense through pyfastx_b200 (one GPU launch + one sync per query)",
+                    "api": "fa[name][s:e].seq / .antisense through pyfastx_b200 (one query per call: resident service kernel fed through "
+                           "mapped host memory, no launch / stream sync per query; FXG_ONE_SERVICE=0 = launch + sync per query)",
                     "queries_per_s": sel.size / per_obj, "Mbases_per_s": float((qe - qs).sum()) / per_obj / 1e6,
                     "queries": int(sel.size)}
                 t1 = time.perf_counter()

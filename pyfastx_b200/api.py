@@ -17,6 +17,10 @@ import numpy as np
 
 from . import _cabi, fxi
 from .engine import get_engine
+try:
+    from ._fast import extract_one as _fast_one       # compiled bridge into the C-ABI (per-object getters)
+except Exception:                                      # not built: the ctypes path of engine.extract_one
+    _fast_one = None
 
 __all__ = ["Fasta", "Fastq", "Fastx", "Sequence", "Read", "FastaKeys", "FastqKeys", "version", "gzip_check",
            "reverse_complement"]
@@ -268,6 +272,8 @@ class Fasta:
         self._drows = None
         self._con = None
         self._comp_cache = None
+        self._slen_cache = None
+        self._one_args = None
         if build_index:
             self.build_index()
             if full_index:
@@ -365,8 +371,13 @@ class Fasta:
         raise KeyError("the key must be index number or sequence name")
 
     def __getitem__(self, key):
-        i = self._row_id(key)
-        return Sequence(self, i, 0, int(self._rows["slen"][i]), True, report_end=False)
+        i = self._names.find(key) if type(key) is str else -2       # the common call: a name
+        if i < 0:
+            i = self._row_id(key)
+        sl = self._slen_cache
+        if sl is None or len(sl) != len(self._rows):
+            sl = self._slen_cache = np.ascontiguousarray(self._rows["slen"])
+        return Sequence(self, i, 0, int(sl[i]), True, report_end=False)
 
     def __iter__(self):
         self._need_index()
@@ -418,6 +429,14 @@ class Fasta:
         return [buf[off[i]:off[i + 1]].decode("latin-1") for i in range(rid.size)]
 
     def _one(self, i, s, e, extra=0):
+        if _fast_one is not None:
+            a = self._one_args
+            if a is None or a[3] is not self._drows:
+                eng = self._st.engine
+                a = self._one_args = (eng.ctx.value, self._st.dfile.handle.value, self._drows.devptr, self._drows, self._drows.n_rows)
+            if e <= s:
+                return ""
+            return _fast_one(a[0], a[1], a[2], a[4], i, s, e, (_cabi.X_UPPER if self.uppercase else 0) | extra).decode("latin-1")
         return self._st.engine.extract_one(self._st.dfile, self._drows, i, s, e, self._flags(extra)).decode("latin-1")
 
     # ---- reference methods -------------------------------------------------------------------------
@@ -572,10 +591,13 @@ class Sequence:
         self._fa, self.id = fasta, row_id + 1
         self._i, self._s, self._e = row_id, s, e
         self._complete = complete
-        self.name = fasta._names.get(row_id)
         # reference quirk Q10, reproduced: a whole record obtained by index or name reports end = 0
         # (src/index.c:482-483); only the iterator sets end = seq_len (src/index.c:522); slices report s + 1 .. e
         self.start, self.end = s + 1, (e if report_end else 0)
+
+    @property
+    def name(self):
+        return self._fa._names.get(self._i)
 
     def __len__(self):
         return self._e - self._s

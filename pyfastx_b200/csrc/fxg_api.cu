@@ -96,9 +96,14 @@ extern "C" int fxg_ctx_create(int device, fxg_ctx **out) {
     return FXG_OK;
 }
 
+void fxg_svc_stop(fxg_ctx *ctx);
+
 extern "C" void fxg_ctx_destroy(fxg_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    fxg_svc_stop(c);
+    if (c->svc_stream) cudaStreamDestroy(c->svc_stream);
+    if (c->svc_req) cudaFreeHost(c->svc_req);
     cudaStreamSynchronize(c->stream);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_one) cudaFreeHost(c->h_one);

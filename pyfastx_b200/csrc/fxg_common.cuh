@@ -70,6 +70,11 @@ struct fxg_ctx {
     FxgScratch   tile_desc, seg, cut, row_tmp, rows, counters, params, plan, misc, stage_file;
     void        *h_counters = nullptr;   // pinned, small
     void        *h_one = nullptr;        // pinned + mapped: output of single-query launches (fxg_extract_one_host)
+    // single-query service (resident kernel fed through mapped host memory)
+    void        *svc_req = nullptr, *svc_resp = nullptr;
+    cudaStream_t svc_stream = nullptr;
+    unsigned long long svc_next = 1;
+    bool         svc_running = false;
     // measurement hooks
     bool         profiling = false;
     cudaEvent_t  prof_ev[FXG_PROF_SLOTS][2] = {};

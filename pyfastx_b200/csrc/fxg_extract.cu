@@ -17,6 +17,7 @@
 #include "fxg_common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 
 namespace fxg {
 
@@ -1043,6 +1044,85 @@ __global__ void __launch_bounds__(XTHREADS) extract_one_kernel(
 }
 
 // K5: FASTQ reads: raw copies of rlen bytes at soff (sequence) and qoff (quality)
+// ---- single-query SERVICE: a resident one-CTA kernel that is handed queries through mapped host memory ----
+// `fa[name][s:e].seq` is one query per Python call; as a kernel launch plus a stream synchronisation it costs ~18 us of
+// driver round trips for ~2 us of work (37 k queries/s in r02's first bench line against 92 k for the reference's fread).
+// While a caller keeps asking, this kernel stays resident instead: warp 0 polls a 128-byte request block in mapped pinned
+// host memory (ONE coalesced 128-byte read per poll), the CTA serves the query exactly like extract_one_kernel, the bytes go
+// straight to mapped host memory, a system-wide fence and a sequence number tell the spinning host thread that they are
+// there.  No launch, no stream synchronisation, no driver call on the path.  The kernel leaves by itself after
+// FXG_SVC_IDLE_CYCLES without a request (and whenever the host sets `stop`), so it never holds the device for longer
+// than that: device-wide synchronisations (cudaFree ...) elsewhere in the process wait at most one idle period.
+// Request block (two 64-byte halves; a PCIe read may complete them separately): the host writes the second half with
+// `tail` last, then the first half with `head` last; the request is valid when head == tail == the expected number.
+struct __align__(128) OneRequest {
+    unsigned long long head;          // half A
+    const uint8_t *file; long long fsize, capacity; const fxg_fasta_row *rows; long long n_rows, rid, s;
+    long long e;                      // half B
+    int flags, stop;
+    long long pad[5];
+    unsigned long long tail;
+};
+static_assert(sizeof(OneRequest) == 128, "OneRequest layout");
+#ifndef FXG_SVC_IDLE_CYCLES
+#define FXG_SVC_IDLE_CYCLES 4000000ll      // ~2 ms at 1.9 GHz
+#endif
+
+__global__ void __launch_bounds__(XTHREADS) extract_service_kernel(const OneRequest *req, volatile unsigned long long *resp,
+                                                                    unsigned long long next_seq, uint8_t *__restrict__ out) {
+    __shared__ uint8_t s_lut[3][256];
+    __shared__ __align__(16) uint8_t s_stage[XWARPS][XSTAGE];
+    __shared__ __align__(16) uint32_t s_req[32];
+    __shared__ int s_go;
+    init_luts(s_lut);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (warp == 0) {
+            const long long t0 = clock64();
+            int go = 0;
+            for (;;) {
+                uint32_t w;
+                asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(w) : "l"(reinterpret_cast<const uint32_t *>(req) + lane) : "memory");
+                const unsigned long long head = (unsigned long long)__shfl_sync(0xffffffffu, w, 0) | ((unsigned long long)__shfl_sync(0xffffffffu, w, 1) << 32);
+                const unsigned long long tail = (unsigned long long)__shfl_sync(0xffffffffu, w, 30) | ((unsigned long long)__shfl_sync(0xffffffffu, w, 31) << 32);
+                const int stop = (int)__shfl_sync(0xffffffffu, w, 19);
+                if (head == next_seq && tail == next_seq) { s_req[lane] = w; go = 1; break; }
+                if (stop || clock64() - t0 > FXG_SVC_IDLE_CYCLES) break;
+            }
+            if (lane == 0) s_go = go;
+        }
+        __syncthreads();
+        if (!s_go) return;
+        const OneRequest *q = reinterpret_cast<const OneRequest *>(s_req);
+        const uint8_t *file = q->file;
+        const int64_t fsize = q->fsize, capacity = q->capacity, n_rows = q->n_rows, rid = q->rid, s = q->s, e = q->e;
+        const fxg_fasta_row *rows = q->rows;
+        const int flags = q->flags;
+        const bool row_ok = rid >= 0 && rid < n_rows;
+        fxg_fasta_row r;
+        memset(&r, 0, sizeof(r));
+        if (row_ok) r = rows[rid];
+        const int64_t len = e - s;
+        int64_t warps = (len + 2047) / 2048;
+        if (warps > XWARPS) warps = XWARPS;
+        const int64_t chunk = ((len + warps - 1) / warps + 15) & ~(int64_t)15;
+        const bool splittable = row_ok && r.norm && (r.pad[0] & 1) != 0 && !(flags & FXG_X_RAW);
+        int64_t ss = s, ee = e;
+        bool mine = true;
+        if (splittable) { ss = s + warp * chunk; ee = ss + chunk < e ? ss + chunk : e; }
+        else if (warp != 0) mine = false;
+        if (mine && ss < ee) {
+            const int64_t ooff = (flags & FXG_X_REVERSE) ? e - ee : ss - s;
+            serve_query_warp<false>(file, fsize, capacity, r, row_ok, ss, ee, flags, out + ooff, s_lut, s_stage[warp], lane, nullptr);
+        }
+        __threadfence_system();                     // the output bytes are in host memory before the number is
+        __syncthreads();
+        if (threadIdx.x == 0) { *resp = next_seq; __threadfence_system(); }
+        ++next_seq;
+    }
+}
+
 __global__ void __launch_bounds__(XTHREADS) reads_kernel(
     const uint8_t *__restrict__ file, int64_t fsize, int64_t capacity, const fxg_fastq_row *__restrict__ rows,
     int64_t n_rows, const int64_t *__restrict__ ids, int64_t nq, int flags, const int64_t *__restrict__ out_off,
@@ -1424,6 +1504,86 @@ extern "C" int fxg_composition_host(fxg_ctx *ctx, const fxg_file *f, const fxg_f
     return FXG_OK;
 }
 
+// ---- host side of the single-query service ----
+static const int FXG_EAGAIN_INTERNAL = -1000;
+static bool svc_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("FXG_ONE_SERVICE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
+void fxg_svc_stop(fxg_ctx *ctx) {                       // called by fxg_ctx_destroy and before buffers a query may name are freed
+    if (!ctx->svc_req) return;
+    OneRequest *rq = (OneRequest *)ctx->svc_req;
+    ((volatile OneRequest *)rq)->stop = 1;
+    __sync_synchronize();
+    if (ctx->svc_stream) cudaStreamSynchronize(ctx->svc_stream);
+    ((volatile OneRequest *)rq)->stop = 0;
+    ctx->svc_running = false;
+}
+static int svc_launch(fxg_ctx *ctx) {
+    void *d_req = nullptr, *d_resp = nullptr, *d_out = nullptr;
+    FXG_CUDA(cudaHostGetDevicePointer(&d_req, ctx->svc_req, 0));
+    FXG_CUDA(cudaHostGetDevicePointer(&d_resp, ctx->svc_resp, 0));
+    FXG_CUDA(cudaHostGetDevicePointer(&d_out, ctx->h_one, 0));
+    ctx->launches += 1;
+    extract_service_kernel<<<1, XTHREADS, 0, ctx->svc_stream>>>((const OneRequest *)d_req, (volatile unsigned long long *)d_resp,
+                                                                ctx->svc_next, (uint8_t *)d_out);
+    FXG_CUDA(cudaGetLastError());
+    ctx->svc_running = true;
+    return FXG_OK;
+}
+static int svc_query(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows, int64_t row_id, int64_t s,
+                     int64_t e, int32_t flags) {
+    if (!ctx->svc_req) {
+        if (cudaHostAlloc(&ctx->svc_req, 256, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); ctx->svc_req = nullptr; return FXG_EAGAIN_INTERNAL; }
+        memset(ctx->svc_req, 0, 256);
+        ctx->svc_resp = (uint8_t *)ctx->svc_req + 128;
+        if (cudaStreamCreateWithFlags(&ctx->svc_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return FXG_EAGAIN_INTERNAL; }
+        ctx->svc_next = 1;
+    }
+    // results of earlier work on the context's stream (staging, scan, row uploads) must be complete: every host entry point
+    // that produces them synchronises before it returns, so there is nothing to wait for here
+    volatile OneRequest *rq = (volatile OneRequest *)ctx->svc_req;
+    const unsigned long long n = ctx->svc_next;
+    // second half first, `tail` last; then the first half, `head` last (x86 keeps the store order)
+    rq->e = e; rq->flags = flags; rq->stop = 0;
+    __sync_synchronize();
+    rq->tail = n;
+    __sync_synchronize();
+    rq->file = f->d; rq->fsize = f->size; rq->capacity = f->capacity; rq->rows = d_rows; rq->n_rows = n_rows; rq->rid = row_id; rq->s = s;
+    __sync_synchronize();
+    rq->head = n;
+    __sync_synchronize();
+    if (!ctx->svc_running) { int rc = svc_launch(ctx); if (rc) return rc; }
+    volatile unsigned long long *resp = (volatile unsigned long long *)ctx->svc_resp;
+    // spin on the response word; look at the stream (a driver call) only every 100 us: that is where a kernel that
+    // left after its idle period, or a failed one, is noticed
+    uint32_t spins = 0;
+    auto t_last = std::chrono::steady_clock::now();
+    while (*resp != n) {
+        if ((++spins & 255u) == 0) {
+            const auto now = std::chrono::steady_clock::now();
+            if (std::chrono::duration<double>(now - t_last).count() < 100e-6) continue;
+            t_last = now;
+            const cudaError_t q = cudaStreamQuery(ctx->svc_stream);
+            if (q == cudaSuccess) {                      // the kernel left (idle period over) before it saw the request
+                if (*resp == n) break;
+                int rc = svc_launch(ctx);
+                if (rc) return rc;
+            } else if (q != cudaErrorNotReady) {
+                cudaGetLastError();
+                fxg_set_error("single-query service failed: %s", cudaGetErrorString(q));
+                ctx->svc_running = false;
+                return FXG_ECUDA;
+            }
+            if (spins > (1u << 28)) { fxg_set_error("single-query service timed out"); return FXG_ECUDA; }
+        }
+    }
+    __sync_synchronize();
+    ctx->svc_next = n + 1;
+    return FXG_OK;
+}
+
 // One query through one kernel launch and one stream synchronisation (no plan kernels, no H2D copies: the query
 // travels as kernel arguments).  Same result as fxg_extract_host with nq = 1.
 extern "C" int fxg_extract_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows,
@@ -1438,6 +1598,11 @@ extern "C" int fxg_extract_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_f
     if (!ctx->h_one) FXG_CUDA(cudaHostAlloc(&ctx->h_one, (size_t)ONE_PINNED + 64, cudaHostAllocMapped));
     uint8_t *d_out;
     const bool direct = len <= ONE_PINNED;
+    if (direct && svc_enabled() && len <= 65536) {
+        int rc = svc_query(ctx, f, d_rows, n_rows, row_id, s, e, flags);
+        if (rc == FXG_OK) { memcpy(out_host, ctx->h_one, (size_t)len); return FXG_OK; }
+        if (rc != FXG_EAGAIN_INTERNAL) return rc;       // else: the service is unavailable, take the launch path
+    }
     if (direct) {
         void *dp = nullptr;
         FXG_CUDA(cudaHostGetDevicePointer(&dp, ctx->h_one, 0));

@@ -47,6 +47,7 @@ class PackedNames:
         self.blob = np.ascontiguousarray(blob, dtype=np.uint8)
         self.off = np.ascontiguousarray(off, dtype=np.int64)
         self._tab = None
+        self._tabv = None
         self._bytes = None
 
     @classmethod
@@ -83,6 +84,16 @@ class PackedNames:
 
     def find(self, name):
         """0-based row of `name` (str or bytes) or -1"""
+        if _fast is not None and type(name) is str:              # the common call, without the generic machinery
+            tv = self._tabv
+            if tv is None:
+                tv = self._tabv = self._table().value
+            try:
+                i = _fast.name_find(tv, name.encode("utf-8"))
+            except UnicodeEncodeError:
+                i = -1
+            if i >= 0 or name.isascii():
+                return i
         L = _cabi.lib()
         tab = self._table()
         probe = (lambda b: _fast.name_find(tab.value, b)) if _fast is not None else (lambda b: L.fxg_nametab_find(tab, b, len(b)))
