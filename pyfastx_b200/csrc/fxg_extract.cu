@@ -1099,6 +1099,28 @@ __global__ void __launch_bounds__(XTHREADS) extract_service_kernel(const OneRequ
         const int64_t fsize = q->fsize, capacity = q->capacity, n_rows = q->n_rows, rid = q->rid, s = q->s, e = q->e;
         const fxg_fasta_row *rows = q->rows;
         const int flags = q->flags;
+        if (q->pad[0] == 1) {
+            // a FASTQ read: rows are fxg_fastq_row, rid = read id, s = 0 (sequence) / 1 (quality) -- read_one_kernel's job
+            if (warp == 0 && rid >= 0 && rid < n_rows) {
+                const fxg_fastq_row rr = reinterpret_cast<const fxg_fastq_row *>(rows)[rid];
+                if (rr.rlen > 0) {
+                    const int which = (int)s;
+                    GatherJob job;
+                    job.skip = 0; job.src_len = rr.rlen; job.out_len = rr.rlen;
+                    job.src = which ? rr.qoff : rr.soff;
+                    job.dst = out;
+                    job.flags = (which ? (flags & FXG_X_REVERSE) : flags) | FXG_X_RAW;      // qualities are never complemented
+                    const bool fastr = rr.rlen < (1ll << 30) && job.src >= 0 && job.src + rr.rlen + 32 <= capacity;
+                    if (!fastr || !pull_one<false>(file, job.src, 0, rr.rlen, 1u << 30, 1, job.flags, job.dst, s_lut, lane, nullptr))
+                        gather_one<false>(file, fsize, job, s_lut[0], s_stage[0], lane, nullptr);
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) { *resp = next_seq; __threadfence_system(); }
+            ++next_seq;
+            continue;
+        }
         const bool row_ok = rid >= 0 && rid < n_rows;
         fxg_fasta_row r;
         memset(&r, 0, sizeof(r));
@@ -1532,8 +1554,9 @@ static int svc_launch(fxg_ctx *ctx) {
     ctx->svc_running = true;
     return FXG_OK;
 }
-static int svc_query(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_rows, int64_t n_rows, int64_t row_id, int64_t s,
-                     int64_t e, int32_t flags) {
+static int svc_query(fxg_ctx *ctx, const fxg_file *f, const void *d_rows_any, int64_t n_rows, int64_t row_id, int64_t s,
+                     int64_t e, int32_t flags, int kind = 0) {
+    const fxg_fasta_row *d_rows = (const fxg_fasta_row *)d_rows_any;
     if (!ctx->svc_req) {
         if (cudaHostAlloc(&ctx->svc_req, 256, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); ctx->svc_req = nullptr; return FXG_EAGAIN_INTERNAL; }
         memset(ctx->svc_req, 0, 256);
@@ -1546,7 +1569,7 @@ static int svc_query(fxg_ctx *ctx, const fxg_file *f, const fxg_fasta_row *d_row
     volatile OneRequest *rq = (volatile OneRequest *)ctx->svc_req;
     const unsigned long long n = ctx->svc_next;
     // second half first, `tail` last; then the first half, `head` last (x86 keeps the store order)
-    rq->e = e; rq->flags = flags; rq->stop = 0;
+    rq->e = e; rq->flags = flags; rq->stop = 0; rq->pad[0] = kind;
     __sync_synchronize();
     rq->tail = n;
     __sync_synchronize();
@@ -1642,6 +1665,11 @@ extern "C" int fxg_read_one_host(fxg_ctx *ctx, const fxg_file *f, const fxg_fast
     if (!ctx->h_one) FXG_CUDA(cudaHostAlloc(&ctx->h_one, (size_t)ONE_PINNED + 64, cudaHostAllocMapped));
     const bool direct = rlen <= ONE_PINNED;
     uint8_t *d_out;
+    if (direct && svc_enabled() && rlen <= 65536) {
+        int rc = svc_query(ctx, f, d_rows, n_rows, read_id, which ? 1 : 0, rlen, flags, 1);
+        if (rc == FXG_OK) { memcpy(out_host, ctx->h_one, (size_t)rlen); return FXG_OK; }
+        if (rc != FXG_EAGAIN_INTERNAL) return rc;
+    }
     if (direct) {
         void *dp = nullptr;
         FXG_CUDA(cudaHostGetDevicePointer(&dp, ctx->h_one, 0));
