@@ -803,6 +803,73 @@ def run_e2e_and_cpu(c, args, info, rows, st, host_file, result):
                 os.unlink(p)
 
 
+def run_e2e_sharded(c, args, dfile, info, rows, st, host_file, result):
+    """N > 1: the drop-in multi-GPU build of ONE file on tmpfs through the public API shard.build_index_sharded -- every rank
+    stages ITS byte range of the file (pread -> pinned ring -> its own PCIe link), split-phase scan with the mailbox
+    exchange, rows + names gathered to rank 0, which writes the `.fxi`.  Timed from a barrier to a barrier, max over ranks."""
+    from pyfastx_b200 import shard
+    q0, q1 = info["range"]
+    S = info["S"]
+    port = os.environ.get("MASTER_PORT", "0")
+    path = os.path.join(shm_dir(), "fxg_bench_shared_%s.fa" % port)
+    if host_file is None:
+        host_file, hp = pinned_array(q1 - q0, np.uint8)
+        c.check(c.L.fxg_file_download(c.eng.ctx, dfile.handle, 0, host_file.ctypes.data, q1 - q0))
+    else:
+        hp = None
+    if c.rank == 0:
+        with open(path, "wb") as fh:
+            fh.truncate(S)
+    barrier(c)
+    t0 = time.perf_counter()
+    fd = os.open(path, os.O_WRONLY)
+    try:
+        mv, off, step = memoryview(host_file), 0, 256 << 20
+        while off < q1 - q0:
+            off += os.pwrite(fd, mv[off:off + step], q0 + off)
+    finally:
+        os.close(fd)
+    barrier(c)
+    if c.rank == 0:
+        log("wrote %s (%.2f GB, %d ranks in parallel) in %.1f s" % (path, S / 1e9, c.world, time.perf_counter() - t0))
+    try:
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        times = []
+        res = None
+        for k in range(e2e_steps + 1):                       # first build is the warm-up
+            if c.rank == 0 and os.path.exists(path + ".fxi"):
+                os.unlink(path + ".fxi")
+            barrier(c)
+            t0 = time.perf_counter()
+            res = shard.build_index_sharded(path, "fasta", engine=c.eng, comm=c.comm, index_file=path + ".fxi")
+            barrier(c)
+            dt = allmax(c, time.perf_counter() - t0)
+            if k:
+                times.append(dt)
+        assert np.array_equal(res["rows"]["boff"], rows["boff"]) and np.array_equal(res["rows"]["slen"], rows["slen"])
+        names_bytes = 0
+        if c.rank == 0:
+            assert len(res["all_rows"]) == args.records * c.world or len(res["all_rows"]) == int(args.records) * c.world
+            names_bytes = int(sum(int(p[1][-1]) for p in res["name_parts"]))
+            fxi_bytes = os.path.getsize(path + ".fxi")
+        best = float(np.mean(times))
+        if c.rank == 0:
+            result["e2e"] = {"value": S / best / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(S),
+                             "d2h_bytes_per_step": int(int(args.records) * c.world * 48 + names_bytes), "steps": e2e_steps,
+                             "seconds_per_build": best,
+                             "api": "pyfastx_b200.shard.build_index_sharded(path, 'fasta') on %d ranks: ONE tmpfs file of %.2f GB -> every rank "
+                                    "stages its byte range (pread -> pinned ring -> HBM) -> sharded scan -> rows + names gathered to rank 0 "
+                                    "-> .fxi written (native bulk writer, %d B)" % (c.world, S / 1e9, fxi_bytes)}
+    finally:
+        barrier(c)
+        if c.rank == 0:
+            for p in (path, path + ".fxi"):
+                if os.path.exists(p):
+                    os.unlink(p)
+        if hp is not None:
+            c.L.fxg_host_free(hp)
+
+
 def _ref_worker(args):
     spath, names, rid, qs, qe, minus = args
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
@@ -1054,6 +1121,8 @@ def run_b200(args):
     drows, local_rows = run_extract(c, args, dfile, info, rows, result, host_file)
     if single and not args.skip_e2e:
         run_e2e_and_cpu(c, args, info, rows, st, host_file, result)
+    elif not args.skip_e2e:
+        run_e2e_sharded(c, args, dfile, info, rows, st, host_file, result)
     else:
         result["e2e"] = None
     if single and not args.skip_bgzf:

@@ -310,14 +310,15 @@ extern "C" int fxg_file_from_host(fxg_ctx *c, const void *host, int64_t nbytes, 
     return rc;
 }
 
-// NUMA node that holds the page-cache pages of an open file (sampled at three offsets), -1 if unknown.
+// NUMA node that holds the page-cache pages of bytes [begin, end) of an open file (sampled at three offsets), -1 if unknown.
 // Readers pinned to that node copied 47 GB/s out of a tmpfs file on the 2-socket bench host, unpinned ones 25-30.
-static int file_numa_node(int fd, int64_t size) {
-    if (size <= 0) return -1;
+static int file_numa_node(int fd, int64_t begin, int64_t end) {
+    if (end <= begin) return -1;
     const long pg = sysconf(_SC_PAGESIZE);
     int votes[64] = {0};
     int best = -1;
-    const int64_t offs[3] = {0, (size / 2) / pg * pg, (size - 1) / pg * pg};
+    // inside the staged range: ranks of a sharded build read different parts of the file, which may sit on different nodes
+    const int64_t offs[3] = {begin / pg * pg, ((begin + end) / 2) / pg * pg, (end - 1) / pg * pg};
     for (int i = 0; i < 3; ++i) {
         void *m = mmap(nullptr, (size_t)pg, PROT_READ, MAP_SHARED, fd, (off_t)offs[i]);
         if (m == MAP_FAILED) continue;
@@ -389,7 +390,7 @@ static int stage_path_range(fxg_ctx *c, const char *path, int64_t begin, int64_t
     bool pin = false;
     const char *pe = getenv("FXG_STAGE_PIN");
     if (!(pe && pe[0] == '0') && n >= ((int64_t)256 << 20)) {
-        const int node = file_numa_node(fd, (int64_t)st.st_size);
+        const int node = file_numa_node(fd, begin, end);
         pin = node >= 0 && node_cpuset(node, &cs);
         if (getenv("FXG_TIMING")) fprintf(stderr, "[fxg timing] staging: file pages on NUMA node %d, %d readers%s\n", node, nt, pin ? " pinned there" : "");
     }
