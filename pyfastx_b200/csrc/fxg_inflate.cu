@@ -450,6 +450,47 @@ __global__ void __launch_bounds__(MT_THREADS, MT_WARPS_PER_SM * 32 / MT_THREADS)
     }
 }
 
+// ---- CRC-32 of every member's output against its gzip trailer (zlib, which the reference reads through, rejects a
+//      member whose CRC does not match; a bit flip that still decodes to the right length must not reach the index) ----
+// One thread per member, slicing-by-4 with the four 256-entry tables in shared memory; 16-byte loads once the output
+// pointer is aligned.  Sets status 9 for a member whose inflate status was 0 and whose CRC differs.
+constexpr int CRC_THREADS = 128;
+__global__ void __launch_bounds__(CRC_THREADS) crc_members_kernel(const uint8_t *__restrict__ comp, const int64_t *__restrict__ cmp_off,
+                                                                  const int64_t *__restrict__ ucmp_off, int64_t n_members,
+                                                                  const uint8_t *__restrict__ out, int32_t *__restrict__ status) {
+    __shared__ uint32_t T[4][256];
+    for (int i = threadIdx.x; i < 256; i += CRC_THREADS) {
+        uint32_t c = (uint32_t)i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+        T[0][i] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += CRC_THREADS) {
+        uint32_t c = T[0][i];
+        for (int t = 1; t < 4; ++t) { c = T[0][c & 0xffu] ^ (c >> 8); T[t][i] = c; }
+    }
+    __syncthreads();
+    const int64_t m = (int64_t)blockIdx.x * CRC_THREADS + threadIdx.x;
+    if (m >= n_members || status[m] != 0) return;
+    const uint8_t *p = out + ucmp_off[m];
+    int64_t len = ucmp_off[m + 1] - ucmp_off[m];
+    uint32_t crc = 0xffffffffu;
+    auto word = [&](uint32_t w) {
+        crc ^= w;
+        crc = T[3][crc & 0xffu] ^ T[2][(crc >> 8) & 0xffu] ^ T[1][(crc >> 16) & 0xffu] ^ T[0][crc >> 24];
+    };
+    while (len > 0 && (reinterpret_cast<uintptr_t>(p) & 15u)) { crc = T[0][(crc ^ *p) & 0xffu] ^ (crc >> 8); ++p; --len; }
+    for (; len >= 16; len -= 16, p += 16) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        word(v.x); word(v.y); word(v.z); word(v.w);
+    }
+    for (; len > 0; --len, ++p) crc = T[0][(crc ^ *p) & 0xffu] ^ (crc >> 8);
+    crc = ~crc;
+    const uint8_t *t = comp + cmp_off[m + 1] - 8;                      // CRC32, ISIZE: the last eight bytes of the member
+    const uint32_t want = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    if (crc != want) status[m] = 9;
+}
+
 }  // namespace fxg
 
 using namespace fxg;
@@ -524,6 +565,13 @@ extern "C" int fxg_inflate_members_dev(fxg_ctx *ctx, const fxg_file *compressed,
                                                                                 (fxi::MemberTables *)ctx->misc.ptr);
     }
     FXG_CUDA(cudaGetLastError());
+    const char *ce = getenv("FXG_BGZF_CRC");
+    if (!(ce && ce[0] == '0')) {                                 // member CRCs against their trailers (status 9 = mismatch)
+        ctx->launches += 1;
+        crc_members_kernel<<<(unsigned)((n_members + CRC_THREADS - 1) / CRC_THREADS), CRC_THREADS, 0, ctx->stream>>>(
+            compressed->d, d_cmp_off, d_ucmp_off, n_members, d_out, d_status);
+        FXG_CUDA(cudaGetLastError());
+    }
     return FXG_OK;
 }
 
@@ -548,13 +596,17 @@ extern "C" int fxg_file_from_bgzf_host(fxg_ctx *ctx, const void *host_buf, int64
     if (!rc) rc = fxg_rows_upload(ctx, tab, (n + 1) * 2, (int)sizeof(int64_t), &d_tab);
     if (!rc && cudaMalloc((void **)&d_status, (size_t)(n + 1) * sizeof(int32_t)) != cudaSuccess) { fxg_set_error("cudaMalloc failed"); rc = FXG_ENOMEM; }
     if (!rc) rc = fxg_inflate_members_dev(ctx, cf, (const int64_t *)d_tab, (const int64_t *)d_tab + n + 1, n, uf->d, total, d_status);
+    if (!rc && !(h_status = (int32_t *)malloc((size_t)(n + 1) * sizeof(int32_t)))) { fxg_set_error("out of host memory"); rc = FXG_ENOMEM; }
     if (!rc) {
-        h_status = (int32_t *)malloc((size_t)(n + 1) * sizeof(int32_t));
         cudaError_t e = cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { fxg_set_error("inflate failed: %s", cudaGetErrorString(e)); rc = FXG_ECUDA; }
         for (int64_t i = 0; !rc && i < n; ++i)
-            if (h_status[i]) { fxg_set_error("BGZF member %lld is corrupt (inflate status %d)", (long long)i, h_status[i]); rc = FXG_EFORMAT; }
+            if (h_status[i]) {
+                fxg_set_error(h_status[i] == 9 ? "BGZF member %lld: CRC-32 of the inflated bytes differs from the member trailer (status %d)"
+                                               : "BGZF member %lld is corrupt (inflate status %d)", (long long)i, h_status[i]);
+                rc = FXG_EFORMAT;
+            }
     }
     free(tab); free(h_status);
     if (d_tab) cudaFree(d_tab);

@@ -232,3 +232,66 @@ def test_compiled_object_layer_keys_and_fastx(tmp_path):
     assert len(recs) == 800 and isinstance(fq.keys(), pyfastx.FastqKeys)
     for q in fq_case["reads"][:10]:
         assert recs[q["id"]][1] == q["seq"] and recs[q["id"]][2] == q["qual"] and recs[q["id"]][0] == fq[q["id"]].name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("service", ["1", "0"])
+def test_per_object_getters_service_and_launch_paths(tmp_path, monkeypatch, service):
+    """fa[name][s:e].seq / .antisense and fq[i].seq / .qual one query per call -- through the resident service kernel
+    (mapped-memory requests, no launch per query) and through the launch + synchronise path: identical to the batched
+    API, also after the service kernel has left on its idle period (sleep) and for queries that span several warps"""
+    import time
+    monkeypatch.setenv("FXG_ONE_SERVICE", service)
+    import pyfastx_b200
+    from pyfastx_b200 import synth
+    p = tmp_path / "s.fa"
+    p.write_bytes(synth.synth_fasta(60, seed=11))
+    fa = pyfastx_b200.Fasta(str(p))
+    rng = np.random.default_rng(5)
+    names, qs, qe, minus = [], [], [], []
+    for k in range(300):
+        i = int(rng.integers(0, len(fa)))
+        n = len(fa[i])
+        L = int(rng.choice([1, 15, 16, 17, 100, 1000, 2047, 2048, 5000, n]))
+        L = min(L, n)
+        a = int(rng.integers(0, n - L + 1))
+        names.append(fa[i].name); qs.append(a); qe.append(a + L); minus.append(bool(k & 1))
+    want = fa.fetch_many(names, np.array(qs) + 1, np.array(qe), ["-" if m else "+" for m in minus])
+    for k in range(300):
+        sub = fa[names[k]][qs[k]:qe[k]]
+        assert (sub.antisense if minus[k] else sub.seq) == want[k], k
+        if k == 150:
+            time.sleep(0.02)                                  # longer than the service kernel's idle period: it relaunches
+    q = tmp_path / "s.fq"
+    q.write_bytes(synth.synth_fastq(500, seed=12))
+    fq = pyfastx_b200.Fastq(str(q))
+    ids = [int(x) for x in rng.integers(0, len(fq), size=100)]
+    sq, ql, off = fq.reads_many(ids)
+    for k, i in enumerate(ids):
+        r = fq[i]
+        want_seq = bytes(sq[off[k]:off[k + 1]]).decode()
+        assert r.seq == want_seq and r.qual == bytes(ql[off[k]:off[k + 1]]).decode()
+        assert r.antisense == pyfastx_b200.reverse_complement(want_seq)
+
+
+@pytest.mark.gpu
+def test_device_buffer_pool_reuse():
+    """fxg_file_free keeps one spare buffer per device; the next allocation that fits takes it (same pointer), a much
+    larger one does not, fxg_pool_trim returns it"""
+    from pyfastx_b200 import _cabi, engine
+    eng = engine.get_engine(0)
+    L = _cabi.lib()
+    L.fxg_pool_trim()
+    a = eng.alloc_file(600 << 20)
+    pa = a.devptr
+    a.free()
+    b = eng.alloc_file(400 << 20)                             # fits into the spare (within 2x + 256 MiB)
+    assert b.devptr == pa
+    b.free()
+    c = eng.alloc_file(20 << 20)                              # far smaller than the spare: a fresh allocation
+    assert c.devptr != pa
+    c.free()
+    L.fxg_pool_trim()
+    d = eng.alloc_file(100 << 20)
+    d.free()
+    L.fxg_pool_trim()

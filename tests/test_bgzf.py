@@ -104,6 +104,26 @@ def test_corrupt_member_is_reported():
 
 
 @pytest.mark.gpu
+def test_crc_mismatch_is_reported(monkeypatch):
+    """a member that inflates to the right length but whose bytes differ from what the trailer's CRC-32 covers (here: the
+    trailer's CRC field is altered; the deflate data is intact) is rejected like zlib rejects it -- and accepted with the
+    check switched off, which proves that it is the CRC kernel that caught it"""
+    from pyfastx_b200 import engine
+    eng = engine.get_engine(0)
+    data = synth.synth_fasta(50, seed=6)
+    z = bytearray(bgzf_compress(data))
+    rc, co, uo, tot = members(bytes(z))
+    z[int(co[1]) - 8] ^= 0x01                                # first member's CRC32 field
+    with pytest.raises(_cabi.FxgError) as ei:
+        eng.stage_bgzf(np.frombuffer(bytes(z), dtype=np.uint8))
+    assert "CRC-32" in str(ei.value)
+    monkeypatch.setenv("FXG_BGZF_CRC", "0")
+    f = eng.stage_bgzf(np.frombuffer(bytes(z), dtype=np.uint8))
+    assert bytes(f.download()) == data
+    f.free()
+
+
+@pytest.mark.gpu
 def test_fasta_on_bgzf_equals_plain(tmp_path):
     import pyfastx_b200 as pyfastx
     data = synth.synth_fasta(300, seed=20240601)
