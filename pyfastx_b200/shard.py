@@ -149,6 +149,41 @@ def gather_objects(obj, group=None):
     return out
 
 
+def gather_arrays(arrays, group=None):
+    """numpy arrays of every rank on rank 0, as raw bytes over point-to-point sends (NCCL: through device memory over
+    NVLink; gloo: host tensors) -- no pickling of tens of megabytes of rows and names per rank.  `arrays` is the same
+    sequence of arrays (same dtypes, any lengths) on every rank; rank 0 gets [per-rank list of arrays], others None."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [list(arrays)]
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    flat = [np.ascontiguousarray(a).view(np.uint8).reshape(-1) for a in arrays]
+    sizes = torch.tensor([f.size for f in flat], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [t.cpu().tolist() for t in all_sizes]
+    if rank != 0:
+        for f in flat:
+            if f.size:
+                dist.send(torch.from_numpy(f).to(dev), dst=0, group=group)
+        return None
+    out = [list(arrays)]
+    for r in range(1, world):
+        part = []
+        for k, a in enumerate(arrays):
+            n = int(all_sizes[r][k])
+            buf = torch.empty(n, dtype=torch.uint8, device=dev)
+            if n:
+                dist.recv(buf, src=r, group=group)
+            dt = np.asarray(a).dtype
+            part.append(buf.cpu().numpy().view(dt))
+        out.append(part)
+    return out
+
+
 # ---- the multi-GPU index build of one file on disk ------------------------------------------------------
 def build_index_sharded(path, fmt, engine=None, comm=None, index_file=None, full_name=False, group=None):
     """Run by every rank (torchrun): stage this rank's byte range of `path`, split-phase scan with the one
@@ -175,11 +210,14 @@ def build_index_sharded(path, fmt, engine=None, comm=None, index_file=None, full
             np.zeros(0, np.uint8), np.zeros(1, np.int64))
     finally:
         dfile.free()
-    parts = gather_objects((rows, names, name_off, st), group)
+    # rows, packed names and their offsets travel as raw bytes (no pickling); the only scalar rank 0 needs beyond the
+    # gathered shard infos is every rank's total sequence length
+    tl = np.array([int(st["total_len"])], dtype=np.int64)
+    parts = gather_arrays((rows, np.asarray(names, dtype=np.uint8), np.asarray(name_off, dtype=np.int64), tl), group)
     res = {"rows": rows, "stats": st, "infos": infos, "range": (a, b)}
     if comm.rank == 0:
         all_rows = np.concatenate([p[0] for p in parts])
-        total_len = sum(int(p[3]["total_len"]) for p in parts)
+        total_len = sum(int(p[3][0]) for p in parts)
         n_lines = int(infos["n_lines"].sum())
         res.update(all_rows=all_rows, total_len=total_len, n_lines=n_lines,
                    name_parts=[(p[1], p[2]) for p in parts])

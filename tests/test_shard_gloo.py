@@ -121,6 +121,17 @@ def _worker(rank, world, port, fa, fq, fq_path, q):
     assert int(infos["n_rows"][rank]) == len(rows)
     base, n_total = shard.fasta_layout(infos["n_rows"])
     fa_parts = shard.gather_objects((rows, total))
+    # the raw-byte gather used by build_index_sharded must deliver the same arrays (structured rows, an empty array,
+    # int64 offsets) as the pickling one
+    raw_parts = shard.gather_arrays((rows, np.zeros(0 if rank else 3, dtype=np.uint8), np.arange(rank + 2, dtype=np.int64)))
+    if rank == 0:
+        assert len(raw_parts) == world
+        for r in range(world):
+            assert raw_parts[r][0].dtype == rows.dtype and np.array_equal(raw_parts[r][0], fa_parts[r][0])
+            assert raw_parts[r][1].size == (0 if r else 3)
+            assert np.array_equal(raw_parts[r][2], np.arange(r + 2, dtype=np.int64))
+    else:
+        assert raw_parts is None
     # ---- FASTQ: shards start at line starts; global line phase from the gathered line counts -----------------
     lp = shard.line_split_points(fq, world)
     assert lp == shard.split_points_path(fq_path, world, False)          # pread search == in-memory search
