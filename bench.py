@@ -712,13 +712,16 @@ def run_e2e_and_cpu(c, args, info, rows, st, host_file, result):
                 assert len(fa) == n_rows and fa.size == int(st["total_len"])
                 assert np.array_equal(fa._rows["boff"], rows["boff"] - info["range"][0])
                 # the reference's per-object idiom through this package (a GPU round trip per query)
-                sel = np.arange(0, min(2000, c.x_keep[0].size))
+                sel = np.arange(0, min(20000, c.x_keep[0].size))
                 rid, qs, qe, minus = (x[sel] for x in c.x_keep[:4])
                 names = ["seq%d" % (info["records"][0] + int(i) + 1) for i in rid]
+                qs_l, qe_l = [int(v) for v in qs], [int(v) for v in qe]
+                for j in range(min(200, sel.size)):                  # untimed: the lazily built name table, the service kernel's
+                    _ = fa[names[j]][qs_l[j]:qe_l[j]].seq              # first launch (module load) -- one-time costs of an open file
                 t1 = time.perf_counter()
                 got = []
                 for j in range(sel.size):
-                    sub = fa[names[j]][int(qs[j]):int(qe[j])]
+                    sub = fa[names[j]][qs_l[j]:qe_l[j]]
                     got.append(sub.antisense if minus[j] else sub.seq)
                 per_obj = time.perf_counter() - t1
                 out_host, off_host = c.x_keep[5], c.x_keep[6]

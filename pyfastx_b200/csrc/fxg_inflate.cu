@@ -411,7 +411,10 @@ __device__ const uint8_t D_DIST_EXTRA[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4,
 __device__ const uint8_t D_CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 constexpr int MT_THREADS = 64;                                      // members per CTA
-constexpr int MT_WARPS_PER_SM = 36;                                 // resident warps the launch aims for (56 registers):
+#ifndef FXG_MT_WARPS
+#define FXG_MT_WARPS 36
+#endif
+constexpr int MT_WARPS_PER_SM = FXG_MT_WARPS;                                 // resident warps the launch aims for (56 registers):
                                                                     // 148 SMs x 36 x 32 lanes cover the 155,577 members of C5 in ONE round
 constexpr int SYM_BATCH = 32;                                      // symbols per lane between member / block checks
 

@@ -24,8 +24,14 @@
 
 namespace fxi {
 
-constexpr int TL_BITS = 9;            // primary literal/length table: 512 entries
-constexpr int TD_BITS = 8;            // primary distance table: 256 entries
+#ifndef FXG_TL_BITS
+#define FXG_TL_BITS 9
+#endif
+#ifndef FXG_TD_BITS
+#define FXG_TD_BITS 8
+#endif
+constexpr int TL_BITS = FXG_TL_BITS;  // primary literal/length table: 2^TL_BITS entries (longer codes: canonical slow path)
+constexpr int TD_BITS = FXG_TD_BITS;  // primary distance table
 
 // Per-member decode tables (one member = one thread; shared memory in the kernel).  2,240 bytes.
 struct MemberTables {
@@ -34,7 +40,7 @@ struct MemberTables {
     uint16_t litcnt[16], litsym[288]; // canonical tables: the slow path for long codes
     uint16_t distcnt[16], distsym[32];
 };
-static_assert(sizeof(MemberTables) == 2240, "MemberTables layout");
+static_assert(sizeof(MemberTables) == 2 * ((1 << TL_BITS) + (1 << TD_BITS)) + 704, "MemberTables layout");
 
 enum { INF_OK = 0, INF_BAD_HEADER = 1, INF_BAD_BLOCK = 2, INF_BAD_CODE = 3, INF_OVERRUN = 4, INF_SIZE = 5 };
 
