@@ -118,7 +118,7 @@ typedef struct fxg_ctx  fxg_ctx;    /* one per (process, GPU).  NOT thread-safe:
                                      * device pointers returned from context scratch (scan rows) stay valid only
                                      * until the next scan on the same context.                                   */
 typedef struct fxg_file fxg_file;   /* a FASTA/FASTQ byte stream resident in HBM */
-typedef struct fxg_comm fxg_comm;   /* NCCL communicator of the ranks that share one index build */
+typedef struct fxg_comm fxg_comm;   /* the ranks that share one index build: peer-memory mailboxes (+ the NCCL communicator used to set them up / as fallback) */
 
 /* ---- library / context ----------------------------------------------------------------- */
 int         fxg_abi_version(void);
@@ -184,8 +184,10 @@ int fxg_fastq_scan(fxg_ctx *ctx, const fxg_file *f, int64_t base_offset,
  * line (FASTA); see fxg_split_point_* below.  The scan is split where the only cross-shard dependency sits:
  *   fxg_scan_begin     mark + prefix over the shard (all of the file traffic); leaves the shard's
  *                      fxg_shard_info on the device.  No host synchronisation.
- *   fxg_shard_exchange ncclAllGather of the fxg_shard_info structs on the context's stream (NVLink/NVSwitch;
- *                      latency bound, 128 B per rank).  comm == NULL: single rank, a device copy.
+ *   fxg_shard_exchange every rank's fxg_shard_info to every rank, on the context's stream: ONE kernel that stores the
+ *                      128-byte block into all ranks' HBM mailboxes over NVLink/NVSwitch (peer memory mapped with CUDA
+ *                      IPC at fxg_comm_create) and waits for the peers' flags -- or an in-stream ncclAllGather where
+ *                      peer access is unavailable (fxg_comm_uses_p2p).  comm == NULL: single rank, a device copy.
  *   fxg_scan_finish    global line phase (fastq.c:93: line_num % 4 counts from the start of the FILE) and ID
  *                      base from the gathered counts, rows kernel, and for FASTQ the boundary-row merge: a
  *                      read is owned by the shard holding its name line and completed from the next shards'

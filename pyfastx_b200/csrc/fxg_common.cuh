@@ -165,19 +165,6 @@ __device__ __forceinline__ uint32_t chunk_eq_mask(const uint4 &v, uint32_t c4) {
     return byte_eq_mask(v.x, c4) | (byte_eq_mask(v.y, c4) >> 1) | (byte_eq_mask(v.z, c4) >> 2) |
            (byte_eq_mask(v.w, c4) >> 3);
 }
-// The same test with the addition issued as an integer multiply-add by an opaque 1 (`one` = reg_const(1)): IMAD runs on the
-// FMA pipe, LOP3 / IADD on the ALU pipe, and the ALU pipe is what limits the mark kernel (ncu r02: ALU 74 % busy, FMA 17 %).
-__device__ __forceinline__ uint32_t byte_eq_mask_m(uint32_t w, uint32_t c4, uint32_t k7f, uint32_t k80, uint32_t one) {
-    uint32_t u, t, r;
-    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(u) : "r"(w), "r"(c4), "r"(k7f));   // (a ^ b) & c
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(u), "r"(one), "r"(k7f));
-    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(r) : "r"(t), "r"(w), "r"(k80));    // ~(a | b) & c
-    return r;
-}
-__device__ __forceinline__ uint32_t chunk_eq_mask_m(const uint4 &v, uint32_t c4, uint32_t k7f, uint32_t k80, uint32_t one) {
-    return byte_eq_mask_m(v.x, c4, k7f, k80, one) | (byte_eq_mask_m(v.y, c4, k7f, k80, one) >> 1) |
-           (byte_eq_mask_m(v.z, c4, k7f, k80, one) >> 2) | (byte_eq_mask_m(v.w, c4, k7f, k80, one) >> 3);
-}
 // same with the three constants held in registers by the caller (hot loops)
 __device__ __forceinline__ uint32_t chunk_eq_mask_r(const uint4 &v, uint32_t c4, uint32_t k7f, uint32_t k80) {
     return byte_eq_mask_r(v.x, c4, k7f, k80) | (byte_eq_mask_r(v.y, c4, k7f, k80) >> 1) |

@@ -37,12 +37,6 @@ namespace fxg {
 
 #ifndef FXG_MARK_MINB
 #define FXG_MARK_MINB 6
-#ifndef FXG_MARK_IMAD
-#define FXG_MARK_IMAD 0
-#endif
-#ifndef FXG_MARK_EXP
-#define FXG_MARK_EXP 0
-#endif
 #endif
 constexpr int REGION   = 2048;            // bytes per warp
 constexpr int SEGCAP   = 128;             // newline-list entries kept per region (lines >= 16 B on average)
@@ -194,9 +188,6 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
     const int64_t n = P.n;
     const uint8_t *file = P.file;
     const uint32_t k0a = reg_const(0x0a0a0a0au), k7f = reg_const(0x7f7f7f7fu), k80 = reg_const(0x80808080u);
-#if FXG_MARK_IMAD
-    const uint32_t kone = reg_const(1u);
-#endif
 
     // the 2 KiB of region rr: four coalesced 16-byte streaming loads per lane, all in flight together
     auto load_region = [&](int64_t rr, uint4 (&vv)[4]) {
@@ -255,12 +246,6 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
             else hi = nib * (1u << (4 * (k - 8))) + hi;
         }
     }
-#if FXG_MARK_EXP
-    nlc = __reduce_add_sync(0xffffffffu, (uint32_t)(__popc(lo) + __popc(hi)));
-    if (lane == 0) P.rc[r] = make_uint2(nlc, 0u);
-    if (FXG_MARK_EXP == 1) continue;
-    nlc = 0;
-#endif
     {
         const uint32_t c = (uint32_t)(__popc(lo) + __popc(hi));
         const uint32_t b1 = __ballot_sync(0xffffffffu, c >= 1u), b2 = __ballot_sync(0xffffffffu, c >= 2u);
@@ -301,18 +286,9 @@ __global__ void __launch_bounds__(MARK_WARPS * 32, FXG_MARK_MINB) mark_kernel(co
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         s_data[warp * (REGION / 16) + j * 32 + lane] = v[j];
-#if FXG_MARK_IMAD
-        m[j] = chunk_eq_mask_m(v[j], k0a, k7f, k80, kone);
-#else
         m[j] = chunk_eq_mask_r(v[j], k0a, k7f, k80);
-#endif
         cmax = max(cmax, __popc(m[j]));
     }
-#if FXG_MARK_EXP     // timing experiment only (results invalid): count, no ranking, no list
-    nlc = __reduce_add_sync(0xffffffffu, (uint32_t)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3])));
-    if (lane == 0) P.rc[r] = make_uint2(nlc, 0u);
-    if (FXG_MARK_EXP == 1) continue;
-#endif
     const bool any2 = __any_sync(0xffffffffu, cmax >= 2);          // e.g. the "+" line of a FASTQ record
     const bool multi = any2 && __any_sync(0xffffffffu, cmax >= 3);
     if (!any2) {

@@ -249,7 +249,7 @@ class Engine:
         return rows, _stats_dict(st), infos
 
     def scan_sharded_dev(self, comm, dfile, mode, base_offset=0, full_name=False):
-        """begin -> in-stream ncclAllGather -> finish on this rank; rows stay on the device.
+        """begin -> in-stream exchange (peer-memory mailboxes, or ncclAllGather as fallback) -> finish on this rank; rows stay on the device.
         -> (device pointer to this shard's rows, stats dict, infos of all ranks)"""
         st = ScanStats()
         d_rows = C.c_void_p()

@@ -6,7 +6,8 @@ range is then moved forward to the next line start (FASTQ) or header-line start 
 stages its own range (its own PCIe link) and runs the split-phase scan of libfxg.so:
 
     fxg_scan_begin      mark + prefix over the shard -> {rows, lines, bytes, first three lines}
-    fxg_shard_exchange  ONE ncclAllGather of those 128-byte structs on the context's stream
+    fxg_shard_exchange  those 128-byte structs to every rank on the context's stream (P2P stores into peer HBM
+                        mailboxes; ncclAllGather where peer access is unavailable)
     fxg_scan_finish     global line phase (reference src/fastq.c:93) / ID base (src/index.c:240) from the
                         gathered counts, rows kernel, boundary-row merge on the device
 
