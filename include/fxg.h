@@ -351,6 +351,14 @@ int            fxg_gzip_inflate_host(const void *comp, int64_t nbytes, uint32_t 
 const uint8_t *fxg_gzip_data(const fxg_gzip_result *r, int64_t *size);
 int            fxg_gzip_index(const fxg_gzip_result *r, fxg_gzindex *gz);   /* pointers into r, valid until freed */
 void           fxg_gzip_free(fxg_gzip_result *r);
+/* Generic gzip with KNOWN checkpoints (the gzindex rows of an existing `.fxi`, or fxg_gzip_index): the compressed bytes go
+ * to the device and every checkpoint's segment -- from its (compressed offset, bit offset) with its 32 KiB window to the
+ * next checkpoint -- is inflated by its own GPU thread; replaces zran_seek + zran_read of the whole stream
+ * (src/index.c:685-686) and the sequential host pass on every later open.  Verified before it is returned: segment
+ * statuses, total length and the CRC-32 of the result (per-segment CRCs combined) against the gzip trailer;
+ * FXG_EFORMAT otherwise (concatenated members, stale checkpoints): the caller then takes fxg_gzip_inflate_host. */
+int            fxg_file_from_gzip_points_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, const fxg_gzindex *gz,
+                                              fxg_file **out);
 
 /* ---- full-index statistics on the resident file ---------------------------------
  * fxg_fasta_composition  per-record 128-bin byte composition, the counting loop of pyfastx_fasta_calc_composition

@@ -133,6 +133,7 @@ SIGNATURES = {
     "fxg_gzip_data": (vp, [vp, P(i64)]),
     "fxg_gzip_index": (i32, [vp, P(GzIndex)]),
     "fxg_gzip_free": (None, [vp]),
+    "fxg_file_from_gzip_points_host": (i32, [vp, vp, i64, P(GzIndex), P(vp)]),
     "fxg_fasta_composition": (i32, [vp, vp, vp, i64, i64, P(vp), P(i64), vp]),
     "fxg_fastq_stats": (i32, [vp, vp, vp, i64, i64, i32, P(FastqMeta)]),
     "fxg_free_host": (None, [vp]),

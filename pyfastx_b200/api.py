@@ -83,10 +83,11 @@ class _Staged:
     inflated on the GPU (one thread per member); other gzip streams are inflated by zlib on the host
     while staging (a single deflate stream has no independent entry points)."""
 
-    def __init__(self, path):
+    def __init__(self, path, index_hint=None):
         self.engine = get_engine()
         self.is_gzip = gzip_check(path)
         self.bgzf_members = 0
+        self.gzip_path = None        # how a plain .gz got into HBM: "gpu-checkpoints" | "host-zlib"
         self.gzindex = None          # zran-format checkpoints for the .fxi (reference src/util.c:442-540)
         if self.is_gzip:
             with open(path, "rb") as fh:
@@ -99,10 +100,22 @@ class _Staged:
             except _cabi.FxgError as ex:
                 if ex.code != _cabi.FXG_EFORMAT:
                     raise
-                # a single serial deflate stream: one zlib pass on the host (what the reference's gzread does too),
-                # collecting the zran checkpoints in the same pass; everything after runs on the GPU copy
-                view, self.gzindex, self._gz_handle = self.engine.gzip_inflate(comp)
-                self.dfile = self.engine.stage_bytes(view)
+                # a single serial deflate stream.  With the checkpoints of an earlier open (the gzindex rows of the
+                # .fxi) every segment is inflated by its own GPU thread, checked against the trailer's CRC-32 ...
+                pts = fxi.read_gzindex(index_hint) if index_hint and index_hint != ":memory:" and os.path.exists(index_hint) else None
+                if pts is not None and pts["compressed_size"] == comp.size and pts["windows"] == pts["npoints"] - 1:
+                    try:
+                        self.dfile = self.engine.stage_gzip_points(comp, pts)
+                        self.gzindex, self.gzip_path = pts, "gpu-checkpoints"
+                    except _cabi.FxgError as ex2:
+                        if ex2.code != _cabi.FXG_EFORMAT:
+                            raise
+                if self.gzip_path is None:
+                    # ... without them: the one sequential zlib pass on the host (the reference inflates the file twice:
+                    # gzread under the scan, then zran_build_index), collecting the zran checkpoints in the same pass
+                    view, self.gzindex, self._gz_handle = self.engine.gzip_inflate(comp)
+                    self.dfile = self.engine.stage_bytes(view)
+                    self.gzip_path = "host-zlib"
         else:
             import time as _t
             t0 = _t.perf_counter()
@@ -262,11 +275,11 @@ class Fasta:
         self.uppercase = bool(uppercase)
         self.full_name = bool(full_name)
         self.key_func = key_func
-        self._st = _Staged(file_name)
+        self.index_file = ":memory:" if memory_index else (os.fspath(index_file) if index_file else file_name + ".fxi")
+        self._st = _Staged(file_name, self.index_file)
         self.is_gzip = self._st.is_gzip
         if self._st.first_non_space() != ord(">"):
             raise RuntimeError("%s is not plain or gzip compressed fasta formatted file" % file_name)
-        self.index_file = ":memory:" if memory_index else (os.fspath(index_file) if index_file else file_name + ".fxi")
         self._rows = None
         self._names = None
         self._drows = None
@@ -723,11 +736,11 @@ class Fastq:
         if not os.path.exists(file_name):
             raise FileExistsError("input fastq file %s does not exists" % file_name)
         self.file_name = file_name
-        self._st = _Staged(file_name)
+        self.index_file = os.fspath(index_file) if index_file else file_name + ".fxi"
+        self._st = _Staged(file_name, self.index_file)
         self.is_gzip = self._st.is_gzip
         if self._st.first_non_space() != ord("@"):
             raise RuntimeError("%s is not plain or gzip compressed fastq formatted file" % file_name)
-        self.index_file = os.fspath(index_file) if index_file else file_name + ".fxi"
         self._phred = phred
         self._rows = None
         self._meta = None

@@ -14,6 +14,8 @@
 // Plain (non-BGZF) gzip streams are not handled here (no independent entry points without a
 // previous serial pass); the host layer inflates those while staging.
 #include "fxg_common.cuh"
+#include <zlib.h>
+#include <vector>
 #include "fxg_inflate_core.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -494,6 +496,59 @@ __global__ void __launch_bounds__(CRC_THREADS) crc_members_kernel(const uint8_t 
     if (crc != want) status[m] = 9;
 }
 
+// ---- generic gzip: one thread per zran checkpoint ----
+// A plain .gz file is one serial deflate stream; its checkpoints (compressed offset, bit offset, the 32 KiB of output in
+// front of it -- collected by the one sequential pass of csrc/fxg_gzip.cpp, or loaded from the `.fxi`) are independent
+// entry points: every thread decodes the segment from its checkpoint to the next one (both deflate block boundaries)
+// into the shared output buffer, taking the bytes its first matches reach back to from the checkpoint's window.  The
+// same fxi::Decoder as the BGZF kernel, started with begin_at().  `seg_crc` receives the CRC-32 of every segment's
+// output; the host combines them (crc32_combine) and compares with the gzip trailer.
+__global__ void __launch_bounds__(64) inflate_points_kernel(const uint8_t *__restrict__ in, int64_t in_size, const int64_t *__restrict__ cmp_off,
+                                                            const uint8_t *__restrict__ bits, const int64_t *__restrict__ ucmp_off,
+                                                            const int32_t *__restrict__ win_index, const uint8_t *__restrict__ windows,
+                                                            int wsize, int64_t n_points, uint8_t *out, int64_t out_cap,
+                                                            int32_t *__restrict__ status, fxi::MemberTables *tables) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    const fxi::DeflateConsts K = {D_LEN_BASE, D_LEN_EXTRA, D_DIST_BASE, D_DIST_EXTRA, D_CL_ORDER};
+    const int32_t wi = win_index[i];
+    status[i] = fxi::inflate_segment(in, in_size, cmp_off[i], (int)bits[i], out, out_cap, ucmp_off[i], ucmp_off[i + 1],
+                                     wi >= 0 ? windows + (size_t)wi * wsize : nullptr, wi >= 0 ? wsize : 0, tables[i], K);
+}
+
+// CRC-32 of out[off[i], off[i + 1]) per segment (slicing-by-4, as crc_members_kernel)
+__global__ void __launch_bounds__(CRC_THREADS) crc_segments_kernel(const int64_t *__restrict__ off, int64_t n, const uint8_t *__restrict__ out,
+                                                                   uint32_t *__restrict__ crc_out) {
+    __shared__ uint32_t T[4][256];
+    for (int i = threadIdx.x; i < 256; i += CRC_THREADS) {
+        uint32_t c = (uint32_t)i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0xEDB88320u & (0u - (c & 1u)));
+        T[0][i] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += CRC_THREADS) {
+        uint32_t c = T[0][i];
+        for (int t = 1; t < 4; ++t) { c = T[0][c & 0xffu] ^ (c >> 8); T[t][i] = c; }
+    }
+    __syncthreads();
+    const int64_t m = (int64_t)blockIdx.x * CRC_THREADS + threadIdx.x;
+    if (m >= n) return;
+    const uint8_t *p = out + off[m];
+    int64_t len = off[m + 1] - off[m];
+    uint32_t crc = 0xffffffffu;
+    auto word = [&](uint32_t w) {
+        crc ^= w;
+        crc = T[3][crc & 0xffu] ^ T[2][(crc >> 8) & 0xffu] ^ T[1][(crc >> 16) & 0xffu] ^ T[0][crc >> 24];
+    };
+    while (len > 0 && (reinterpret_cast<uintptr_t>(p) & 15u)) { crc = T[0][(crc ^ *p) & 0xffu] ^ (crc >> 8); ++p; --len; }
+    for (; len >= 16; len -= 16, p += 16) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p);
+        word(v.x); word(v.y); word(v.z); word(v.w);
+    }
+    for (; len > 0; --len, ++p) crc = T[0][(crc ^ *p) & 0xffu] ^ (crc >> 8);
+    crc_out[m] = ~crc;
+}
+
 }  // namespace fxg
 
 using namespace fxg;
@@ -618,5 +673,76 @@ extern "C" int fxg_file_from_bgzf_host(fxg_ctx *ctx, const void *host_buf, int64
     if (rc) { if (uf) fxg_file_free(uf); return rc; }
     *out = uf;
     if (n_members_out) *n_members_out = n;
+    return FXG_OK;
+}
+
+// Generic gzip with known checkpoints (from the `.fxi` of an earlier open, or from fxg_gzip_inflate_host): the compressed
+// bytes go to the device and every checkpoint's segment is inflated by its own thread -- no sequential host pass.
+// The CRC-32 of the result (per-segment CRCs combined on the host) must equal the gzip trailer's, as must the length;
+// anything else returns FXG_EFORMAT and the caller takes the sequential host path.
+extern "C" int fxg_file_from_gzip_points_host(fxg_ctx *ctx, const void *host_buf, int64_t nbytes, const fxg_gzindex *gz, fxg_file **out) {
+    FXG_CHECK_ARG(ctx && host_buf && gz && out && nbytes >= 18, "bad arguments");
+    FXG_LOCK(ctx);
+    *out = nullptr;
+    const int64_t n = gz->npoints, total = gz->uncompressed_size;
+    FXG_CHECK_ARG(n >= 1 && total >= 0 && gz->cmp_offset && gz->uncmp_offset && gz->compressed_size == nbytes, "bad checkpoint table");
+    const uint8_t *hb = (const uint8_t *)host_buf;
+    const uint32_t want_crc = (uint32_t)hb[nbytes - 8] | ((uint32_t)hb[nbytes - 7] << 8) | ((uint32_t)hb[nbytes - 6] << 16) | ((uint32_t)hb[nbytes - 5] << 24);
+    const uint32_t want_len = (uint32_t)hb[nbytes - 4] | ((uint32_t)hb[nbytes - 3] << 8) | ((uint32_t)hb[nbytes - 2] << 16) | ((uint32_t)hb[nbytes - 1] << 24);
+    if (want_len != (uint32_t)total) { fxg_set_error("gzip trailer length differs from the checkpoint table's"); return FXG_EFORMAT; }
+    std::vector<int64_t> uo((size_t)n + 1);
+    std::vector<int32_t> wi((size_t)n, -1);
+    std::vector<uint8_t> bt((size_t)n, 0);
+    int64_t nw = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        uo[(size_t)i] = gz->uncmp_offset[i];
+        if (gz->bits) bt[(size_t)i] = gz->bits[i];
+        if (gz->has_data && gz->has_data[i]) wi[(size_t)i] = (int32_t)nw++;
+        if (i && (gz->uncmp_offset[i] <= gz->uncmp_offset[i - 1] || gz->cmp_offset[i] < gz->cmp_offset[i - 1])) { fxg_set_error("checkpoints out of order"); return FXG_EFORMAT; }
+        if (i && !(gz->has_data && gz->has_data[i])) { fxg_set_error("checkpoint %lld has no window", (long long)i); return FXG_EFORMAT; }
+    }
+    uo[(size_t)n] = total;
+    if (uo[0] != 0 || uo[(size_t)n - 1] >= total + (total == 0) || (nw && (gz->window_size != 32768 || !gz->windows))) { fxg_set_error("unusable checkpoint table"); return FXG_EFORMAT; }
+    FXG_CUDA(cudaSetDevice(ctx->device));
+    fxg_file *cf = nullptr, *uf = nullptr;
+    void *d_co = nullptr, *d_uo = nullptr, *d_bt = nullptr, *d_wi = nullptr, *d_win = nullptr;
+    int32_t *d_status = nullptr;
+    uint32_t *d_crc = nullptr;
+    std::vector<int32_t> h_status((size_t)n);
+    std::vector<uint32_t> h_crc((size_t)n);
+    int rc = fxg_file_from_host(ctx, host_buf, nbytes, &cf);
+    if (!rc) rc = fxg_file_alloc(ctx, total, &uf);
+    if (!rc) rc = fxg_rows_upload(ctx, gz->cmp_offset, n, 8, &d_co);
+    if (!rc) rc = fxg_rows_upload(ctx, uo.data(), n + 1, 8, &d_uo);
+    if (!rc) rc = fxg_rows_upload(ctx, bt.data(), n, 1, &d_bt);
+    if (!rc) rc = fxg_rows_upload(ctx, wi.data(), n, 4, &d_wi);
+    if (!rc && nw) rc = fxg_rows_upload(ctx, gz->windows, nw, (int)gz->window_size, &d_win);
+    if (!rc && (cudaMalloc((void **)&d_status, (size_t)n * 4) != cudaSuccess || cudaMalloc((void **)&d_crc, (size_t)n * 4) != cudaSuccess)) { cudaGetLastError(); fxg_set_error("cudaMalloc failed"); rc = FXG_ENOMEM; }
+    if (!rc) rc = ctx->misc.reserve((size_t)n * sizeof(fxi::MemberTables));
+    if (!rc) {
+        ctx->launches += 2;
+        inflate_points_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(cf->d, cf->size, (const int64_t *)d_co, (const uint8_t *)d_bt,
+                                                                               (const int64_t *)d_uo, (const int32_t *)d_wi, (const uint8_t *)d_win,
+                                                                               (int)gz->window_size, n, uf->d, total, d_status,
+                                                                               (fxi::MemberTables *)ctx->misc.ptr);
+        crc_segments_kernel<<<(unsigned)((n + CRC_THREADS - 1) / CRC_THREADS), CRC_THREADS, 0, ctx->stream>>>((const int64_t *)d_uo, n, uf->d, d_crc);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_status.data(), d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_crc.data(), d_crc, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { fxg_set_error("inflate from checkpoints failed: %s", cudaGetErrorString(e)); rc = FXG_ECUDA; }
+    }
+    if (!rc) {
+        uLong crc = crc32(0L, Z_NULL, 0);
+        for (int64_t i = 0; i < n && !rc; ++i) {
+            if (h_status[(size_t)i]) { fxg_set_error("segment %lld of the gzip stream is corrupt (inflate status %d)", (long long)i, h_status[(size_t)i]); rc = FXG_EFORMAT; }
+            crc = crc32_combine(crc, (uLong)h_crc[(size_t)i], (z_off_t)(uo[(size_t)i + 1] - uo[(size_t)i]));
+        }
+        if (!rc && (uint32_t)crc != want_crc) { fxg_set_error("CRC-32 of the inflated bytes differs from the gzip trailer (several members, or stale checkpoints)"); rc = FXG_EFORMAT; }
+    }
+    for (void *p : {d_co, d_uo, d_bt, d_wi, d_win, (void *)d_status, (void *)d_crc}) if (p) cudaFree(p);
+    if (cf) fxg_file_free(cf);
+    if (rc) { if (uf) fxg_file_free(uf); return rc; }
+    *out = uf;
     return FXG_OK;
 }

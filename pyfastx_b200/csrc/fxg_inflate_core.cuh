@@ -141,7 +141,16 @@ FXI_HD bool build_table(const uint8_t *lens, int n, uint16_t *tab, int tab_bits,
 }
 
 // `len` bytes from out[src..) to out[dst..), src < dst, as DEFLATE defines it (overlap repeats the pattern).
-FXI_HD void copy_match(uint8_t *out, int64_t dst, int64_t src, int len, int64_t out_cap) {
+// Bytes of the source that lie before `o0` (a segment that starts at a zran checkpoint: its first matches reach back
+// into the 32 KiB of output in front of the checkpoint) come from the checkpoint's window `win[0 .. wlen)`, whose last
+// byte is output byte o0 - 1.
+FXI_HD void copy_match(uint8_t *out, int64_t dst, int64_t src, int len, int64_t out_cap, int64_t o0 = 0,
+                       const uint8_t *win = nullptr, int wlen = 0) {
+    while (len > 0 && src < o0) {                     // only with a window (the BGZF path checks dist <= opos - o0)
+        out[dst++] = win[wlen - (int)(o0 - src)];
+        ++src; --len;
+    }
+    if (len <= 0) return;
     const int64_t dist = dst - src;
     while (len > 0) {
         const int n = len < 24 ? len : 24;
@@ -185,12 +194,30 @@ struct Decoder {
     int64_t opos, o0, o1, olim, dend;   // dend = c1 - 8: one past the deflate data
     int state, status;
     bool last;
+    // segment mode: decoding starts at a zran checkpoint (a deflate block boundary in the middle of a stream) and ends
+    // when the output reaches o1 -- the next checkpoint, also a block boundary -- or with the stream's last block
+    bool seg;
+    const uint8_t *win;
+    int wlen;
 
     FXI_HD void fail(int code) { status = code; state = DONE; }
+
+    // raw deflate data from compressed offset `cpos`; `bits` (0..7) leading bits of the block sit in the byte before it
+    // (zran's convention: inflatePrime(bits, in[cpos - 1] >> (8 - bits))); `w` = the wl bytes of output before o0
+    FXI_HD void begin_at(const uint8_t *in, int64_t in_size, int64_t cpos, int bits, int64_t out_cap, int64_t o0_, int64_t o1_,
+                         const uint8_t *w, int wl) {
+        status = INF_OK; state = NEED_BLOCK; last = false;
+        seg = true; win = w; wlen = wl;
+        o0 = o0_; o1 = o1_; opos = o0_; olim = o1_ < out_cap ? o1_ : out_cap; dend = in_size;
+        br.in = in; br.pos = cpos; br.end = in_size; br.lim = in_size; br.buf = 0; br.nbits = 0;
+        if (cpos < 0 || cpos > in_size || bits < 0 || bits > 7 || (bits && cpos < 1)) { fail(INF_BAD_HEADER); return; }
+        if (bits) { br.buf = (uint64_t)(in[cpos - 1] >> (8 - bits)); br.nbits = bits; }
+    }
 
     // gzip member header: 10 fixed bytes, FEXTRA (BGZF always), optional name/comment/crc
     FXI_HD void begin(const uint8_t *in, int64_t in_size, int64_t c0, int64_t c1, int64_t out_cap, int64_t o0_, int64_t o1_) {
         status = INF_OK; state = NEED_BLOCK; last = false;
+        seg = false; win = nullptr; wlen = 0;
         o0 = o0_; o1 = o1_; opos = o0_; olim = o1_ < out_cap ? o1_ : out_cap; dend = c1 - 8;
         br.in = in; br.pos = c0; br.end = c1 - 8; br.lim = in_size; br.buf = 0; br.nbits = 0;
         int64_t p = c0;
@@ -212,7 +239,7 @@ struct Decoder {
 
     // block header (+ stored data, + code lengths and tables): NEED_BLOCK -> SYMBOLS | NEED_BLOCK | DONE
     FXI_HD void begin_block(uint8_t *out, MemberTables &T, const DeflateConsts &K) {
-        if (last) { finish_member(); return; }
+        if (last || (seg && opos >= o1)) { finish_member(); return; }
         last = br.get(1) != 0;
         const int btype = (int)br.get(2);
         int hlit = 0, hdist = 0;
@@ -309,9 +336,9 @@ struct Decoder {
         br.refill();
         const int mdist = K.DIST_BASE[ds] + (int)br.peek(K.DIST_EXTRA[ds]);
         br.drop(K.DIST_EXTRA[ds]);
-        if (mdist > opos - o0) { fail(INF_BAD_CODE); return; }            // BGZF members are self-contained
+        if (mdist > opos - o0 + wlen) { fail(INF_BAD_CODE); return; }     // BGZF members are self-contained (wlen = 0)
         if (opos + mlen > olim) { fail(INF_OVERRUN); return; }
-        copy_match(out, opos, opos - mdist, mlen, out_cap);
+        copy_match(out, opos, opos - mdist, mlen, out_cap, o0, win, wlen);
         opos += mlen;
     }
 };
@@ -322,6 +349,18 @@ FXI_HD int inflate_member(const uint8_t *in, int64_t in_size, int64_t c0, int64_
                           int64_t o0, int64_t o1, MemberTables &T, const DeflateConsts &K) {
     Decoder d;
     d.begin(in, in_size, c0, c1, out_cap, o0, o1);
+    while (d.state != Decoder::DONE) {
+        if (d.state == Decoder::NEED_BLOCK) d.begin_block(out, T, K);
+        else d.step_symbol(out, out_cap, T, K);
+    }
+    return d.status;
+}
+
+// Decode the deflate data from a zran checkpoint (cpos, bits, window) into out[o0, o1) start to finish.
+FXI_HD int inflate_segment(const uint8_t *in, int64_t in_size, int64_t cpos, int bits, uint8_t *out, int64_t out_cap,
+                           int64_t o0, int64_t o1, const uint8_t *win, int wlen, MemberTables &T, const DeflateConsts &K) {
+    Decoder d;
+    d.begin_at(in, in_size, cpos, bits, out_cap, o0, o1, win, wlen);
     while (d.state != Decoder::DONE) {
         if (d.state == Decoder::NEED_BLOCK) d.begin_block(out, T, K);
         else d.step_symbol(out, out_cap, T, K);

@@ -158,6 +158,15 @@ class Engine:
         check(lib().fxg_gzip_index(h, C.byref(gz)))
         return view, gz, h
 
+    def stage_gzip_points(self, data, gz):
+        """generic gzip with known checkpoints (fxi.read_gzindex): every checkpoint's segment is inflated by its own GPU
+        thread, verified against the gzip trailer (length + CRC-32) -> DeviceFile.  FxgError(FXG_EFORMAT) if the
+        checkpoints do not fit the file (then: gzip_inflate)."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+        h = C.c_void_p()
+        check(lib().fxg_file_from_gzip_points_host(self.ctx, a.ctypes.data, a.size, C.byref(gz["struct"]), C.byref(h)))
+        return DeviceFile(self, h)
+
     def gzip_free(self, handle):
         lib().fxg_gzip_free(handle)
 

@@ -152,12 +152,51 @@ def bgzf_gzindex(comp, cmp_off, ucmp_off):
             np.ascontiguousarray(np.asarray(ucmp_off, dtype=np.int64)[keep])}
 
 
+def read_gzindex(path):
+    """the zran checkpoints stored in the `gzindex` table of an existing `.fxi` (row-per-field layout of
+    src/util.c:442-540) -> dict with a ready _cabi.GzIndex under "struct" (and the arrays it points into), or None when the
+    table is absent / empty / holds no usable points.  Used to inflate a plain .gz on the GPU from its checkpoints."""
+    import sqlite3
+    import struct
+    try:
+        con = sqlite3.connect("file:%s?mode=ro" % path, uri=True)
+        try:
+            blobs = [r[0] for r in con.execute("SELECT content FROM gzindex ORDER BY ID")]
+        finally:
+            con.close()
+    except sqlite3.Error:
+        return None
+    if len(blobs) < 8 or bytes(blobs[0]) != b"GZIDX":
+        return None
+    try:
+        csz, usz = struct.unpack("<Q", blobs[3])[0], struct.unpack("<Q", blobs[4])[0]
+        spacing, wsz, npts = (struct.unpack("<I", blobs[k])[0] for k in (5, 6, 7))
+        if len(blobs) < 8 + 4 * npts or npts < 1:
+            return None
+        cmp_off = np.array([struct.unpack("<Q", blobs[8 + 4 * i])[0] for i in range(npts)], dtype=np.int64)
+        ucmp_off = np.array([struct.unpack("<Q", blobs[9 + 4 * i])[0] for i in range(npts)], dtype=np.int64)
+        bits = np.array([blobs[10 + 4 * i][0] for i in range(npts)], dtype=np.uint8)
+        has = np.array([blobs[11 + 4 * i][0] for i in range(npts)], dtype=np.uint8)
+        wins = blobs[8 + 4 * npts:]
+        if len(wins) != int(has.sum()) or any(len(w) != wsz for w in wins):
+            return None
+        windows = np.frombuffer(b"".join(bytes(w) for w in wins), dtype=np.uint8).copy() if wins else np.zeros(1, np.uint8)
+    except (struct.error, IndexError, TypeError):
+        return None
+    g = _cabi.GzIndex(int(csz), int(usz), int(spacing), int(wsz), int(npts), cmp_off.ctypes.data, ucmp_off.ctypes.data,
+                      bits.ctypes.data, has.ctypes.data, windows.ctypes.data)
+    return {"struct": g, "keep": (cmp_off, ucmp_off, bits, has, windows), "npoints": int(npts),
+            "windows": int(has.sum()), "uncompressed_size": int(usz), "compressed_size": int(csz)}
+
+
 def _gz_struct(gz):
     """dict (BGZF member table, see bgzf_gzindex) or a ready _cabi.GzIndex (generic gzip, engine.gzip_inflate)"""
     if not gz:
         return None, None
     if isinstance(gz, _cabi.GzIndex):
         return gz, None
+    if "struct" in gz:                     # read_gzindex(): checkpoints loaded from an existing .fxi
+        return gz["struct"], gz["keep"]
     keep = (np.ascontiguousarray(gz["cmp_offset"], dtype=np.int64), np.ascontiguousarray(gz["uncmp_offset"], dtype=np.int64))
     g = _cabi.GzIndex(int(gz["compressed_size"]), int(gz["uncompressed_size"]), ZRAN_SPACING, ZRAN_WINDOW,
                       len(keep[0]), keep[0].ctypes.data, keep[1].ctypes.data, None, None, None)

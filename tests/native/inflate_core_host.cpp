@@ -20,3 +20,22 @@ extern "C" int fxi_host_inflate(const uint8_t *in, int64_t in_size, const int64_
     }
     return bad;
 }
+
+// one segment per zran checkpoint: (cmp_off, bits, ucmp_off[i] .. ucmp_off[i + 1]) with the 32 KiB window of the points
+// that have one (in point order); ucmp_off has n_points + 1 entries (the last = uncompressed size)
+extern "C" int fxi_host_inflate_points(const uint8_t *in, int64_t in_size, int64_t n_points, const int64_t *cmp_off,
+                                       const uint8_t *bits, const int64_t *ucmp_off, const uint8_t *has_data,
+                                       const uint8_t *windows, int window_size, uint8_t *out, int64_t out_cap, int32_t *status) {
+    int bad = 0;
+    int64_t k = 0;
+    for (int64_t i = 0; i < n_points; ++i) {
+        fxi::MemberTables T;
+        const fxi::DeflateConsts K = {LEN_BASE, LEN_EXTRA, DIST_BASE, DIST_EXTRA, CL_ORDER};
+        const uint8_t *w = nullptr;
+        int wl = 0;
+        if (has_data && has_data[i]) { w = windows + (int64_t)k * window_size; wl = window_size; ++k; }
+        status[i] = fxi::inflate_segment(in, in_size, cmp_off[i], bits ? bits[i] : 0, out, out_cap, ucmp_off[i], ucmp_off[i + 1], w, wl, T, K);
+        bad += status[i] != 0;
+    }
+    return bad;
+}

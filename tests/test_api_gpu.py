@@ -295,3 +295,33 @@ def test_device_buffer_pool_reuse():
     d = eng.alloc_file(100 << 20)
     d.free()
     L.fxg_pool_trim()
+
+
+@pytest.mark.gpu
+def test_plain_gzip_second_open_inflates_on_the_gpu_from_checkpoints(tmp_path):
+    """a plain (non-BGZF) .gz: the first open runs the one sequential host pass and stores real zran checkpoints in the
+    .fxi; the second open inflates every checkpoint's segment with its own GPU thread (verified against the gzip
+    trailer's CRC-32) -- same bytes, same rows, same sequences; checkpoints that do not fit the file fall back"""
+    import gzip as _gzip
+    import pyfastx_b200
+    from pyfastx_b200 import synth
+    raw = synth.synth_fasta(520, seed=31)                        # ~5.3 MB: several 1 MiB checkpoints
+    p = tmp_path / "plain.fa.gz"
+    p.write_bytes(_gzip.compress(raw, compresslevel=6))
+    a = pyfastx_b200.Fasta(str(p))
+    assert a._st.gzip_path == "host-zlib" and a.is_gzip
+    first, last, n, size = a[0].seq, a[len(a) - 1][100:3000].antisense, len(a), a.size
+    del a
+    b = pyfastx_b200.Fasta(str(p))
+    assert b._st.gzip_path == "gpu-checkpoints"
+    assert bytes(b._st.dfile.download()) == raw
+    assert (len(b), b.size) == (n, size) and b[0].seq == first and b[len(b) - 1][100:3000].antisense == last
+    del b
+    # another file's checkpoints (same index path): the CRC check rejects the result, the host pass takes over
+    raw2 = synth.synth_fasta(520, seed=32)
+    z2 = _gzip.compress(raw2, compresslevel=6)
+    q = tmp_path / "other.fa.gz"
+    q.write_bytes(z2)
+    os.replace(str(p) + ".fxi", str(q) + ".fxi")
+    c = pyfastx_b200.Fasta(str(q))
+    assert c._st.gzip_path == "host-zlib" and bytes(c._st.dfile.download()) == raw2

@@ -121,7 +121,15 @@ def test_fxi_for_plain_gzip_carries_windows_and_the_reference_opens_it(tmp_path)
     assert len(blobs) == 8 + 4 * k + nw and blobs[0] == b"GZIDX"
     assert struct.unpack("<I", blobs[7])[0] == k and all(len(b) == 32768 for b in blobs[8 + 4 * k:])
     assert blobs[8 + 4 * k:] == [pts["win"][i * 32768:(i + 1) * 32768] for i in range(nw)]
+    # the loader that feeds the GPU inflate-from-checkpoints path reads the same table back
+    back = fxi.read_gzindex(str(path) + ".fxi")
+    assert back is not None and back["npoints"] == k and back["windows"] == nw
+    assert back["compressed_size"] == len(z) and back["uncompressed_size"] == len(raw)
+    co, uo, bt, hs, wn = back["keep"]
+    assert np.array_equal(co, pts["cmp"]) and np.array_equal(uo, pts["ucmp"]) and np.array_equal(bt, pts["bits"])
+    assert np.array_equal(hs, pts["has"]) and wn.tobytes() == pts["win"]
     _cabi.lib().fxg_gzip_free(h)
+    assert fxi.read_gzindex(str(tmp_path / "absent.fxi")) is None
     ref = _ref()
     if ref is None:
         pytest.skip("oracle/_ref not built: row layout checked only")

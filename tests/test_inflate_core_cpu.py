@@ -85,3 +85,52 @@ def test_corrupt_members_are_reported(core):
     bad, out, st = inflate(core, bytes(z))
     assert bad >= 1 and st[0] != 0 and not st[1:].any()
     assert out[0xff00:] == data[0xff00:]             # the other members are unaffected
+
+
+# ---- segments: decoding from zran checkpoints (generic gzip) --------------------------------------------
+@pytest.fixture(scope="module")
+def core_points(core):
+    core.fxi_host_inflate_points.restype = C.c_int
+    core.fxi_host_inflate_points.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    return core
+
+
+@pytest.mark.parametrize("kind,level,spacing", [("dna", 6, 1 << 16), ("dna", 1, 1 << 15), ("fastq", 9, 1 << 17),
+                                                ("text", 6, 1 << 16), ("stored", 0, 1 << 16), ("runs", 6, 1 << 15)])
+def test_segments_from_checkpoints_match_zlib(core_points, kind, level, spacing):
+    """every checkpoint that the one sequential pass (csrc/fxg_gzip.cpp) collects starts an independent segment: the decoder
+    that the GPU runs one thread per segment, started at (compressed offset, bit offset) with the checkpoint's 32 KiB
+    window, reproduces the bytes up to the next checkpoint -- all segments together give the file"""
+    import gzip as _gzip
+    from test_gzip_cpu import inflate_host
+    from pyfastx_b200 import _cabi
+    rng = np.random.default_rng(3)
+    if kind == "dna":
+        data = synth.synth_fasta(400, seed=21)
+    elif kind == "fastq":
+        data = synth.synth_fastq(20000, seed=22)
+    elif kind == "text":
+        data = (b"the quick brown fox jumps over the lazy dog. " * 40000)[:1_500_000]
+    elif kind == "stored":
+        data = rng.integers(0, 256, size=600_000, dtype=np.uint8).tobytes()
+    else:
+        data = b"A" * 300_000 + b"ACGT" * 100_000 + bytes(range(256)) * 1000
+    z = _gzip.compress(data, compresslevel=level)
+    got, gz, pts, h = inflate_host(z, spacing)
+    try:
+        assert got == data
+        n = len(pts["cmp"])
+        assert n >= 1 and (n >= 3 or kind not in ("dna", "fastq"))
+        a = np.frombuffer(z, dtype=np.uint8).copy()
+        ucmp = np.concatenate([pts["ucmp"], [len(data)]]).astype(np.int64)
+        out = np.zeros(len(data) + 64, dtype=np.uint8)
+        st = np.zeros(n, dtype=np.int32)
+        win = np.frombuffer(pts["win"], dtype=np.uint8).copy() if pts["win"] else np.zeros(1, np.uint8)
+        bad = core_points.fxi_host_inflate_points(a.ctypes.data, a.size, n, pts["cmp"].ctypes.data, pts["bits"].ctypes.data,
+                                                  ucmp.ctypes.data, pts["has"].ctypes.data, win.ctypes.data, 32768,
+                                                  out.ctypes.data, len(data), st.ctypes.data)
+        assert bad == 0 and not st.any(), st[:8]
+        assert out[:len(data)].tobytes() == data
+    finally:
+        _cabi.lib().fxg_gzip_free(h)
